@@ -1,0 +1,142 @@
+/* votenet_b200 — C ABI of the B200 (sm_100a) VoteNet / PointNet++ inference hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / TensorFlow types.  Each entry point is the
+ * C-ABI twin of one reference launcher or CPU loop (cited per function; paths relative to the reference repo
+ * qq456cvb/VoteNet).  Conventions, all mirroring the reference's native side:
+ *   - every pointer is a DEVICE pointer to dense, row-major, contiguous data; inputs are const;
+ *   - the CALLER allocates every output and workspace buffer; the library never allocates or frees;
+ *   - launches are asynchronous on the given `stream` (a cudaStream_t passed as void*); no hidden host sync;
+ *     every entry point is re-entrant, stateless and CUDA-graph capturable;
+ *   - return 0 on success; VNB_ERR_INVALID for a shape / attribute violation (where the reference op raises
+ *     errors::InvalidArgument), VNB_ERR_CUDA for a CUDA launch error (which the reference never checks).
+ *     vnb_last_error() returns a thread-local message for the last non-zero return.
+ * There is no CPU fallback: without a CUDA device every compute entry point returns VNB_ERR_CUDA.
+ */
+#ifndef VOTENET_B200_H_
+#define VOTENET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VNB_OK 0
+#define VNB_ERR_INVALID 1
+#define VNB_ERR_CUDA 2
+
+#define VNB_ABI_VERSION 1
+
+int vnb_abi_version(void);
+const char* vnb_last_error(void);
+
+/* ------------------------------------------------------------------ tf_ops/sampling ------------------- */
+
+/* farthestpointsamplingLauncher(b,n,m,inp,temp,out)            tf_ops/sampling/tf_sampling_g.cu:203-205
+ * (op FarthestPointSample, tf_sampling.cpp:95-123; python farthest_point_sample(npoint, inp), tf_sampling.py:48-56)
+ * xyz (b,n,3) f32 -> out_idx (b,m) i32.  Bit-identical index sequence to the reference kernel (tie rule included).
+ * The reference's (32,n) `temp` scratch is not needed: the running min-distances live in registers.
+ * Limits: 1 <= n <= 65536; m >= 1 (m <= 0 is VNB_ERR_INVALID like the op's npoint>0 check, tf_sampling.cpp:99). */
+int vnb_farthest_point_sample(int b, int n, int m, const float* xyz, int* out_idx, void* stream);
+
+/* gatherpointLauncher(b,n,m,inp,idx,out)                        tf_sampling_g.cu:206-208
+ * inp (b,n,3), idx (b,m) -> out (b,m,3). */
+int vnb_gather_point(int b, int n, int m, const float* inp, const int* idx, float* out, void* stream);
+
+/* ------------------------------------------------------------------ tf_ops/grouping ------------------- */
+
+/* queryBallPointLauncher(b,n,m,radius,nsample,xyz1,xyz2,idx,pts_cnt)   tf_grouping_g.cu:125-128
+ * xyz1 (b,n,3) searched set, xyz2 (b,m,3) queries -> idx (b,m,nsample) i32, pts_cnt (b,m) i32.
+ * First `nsample` hits in ascending index order, padded with the first hit; rows of empty balls are left untouched
+ * exactly like the reference (tf_grouping_g.cu:14-34).  radius > 0, nsample > 0 (tf_grouping.cpp:71,74). */
+int vnb_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
+                         int* idx, int* pts_cnt, void* stream);
+
+/* groupPointLauncher(b,n,c,m,nsample,points,idx,out)            tf_grouping_g.cu:133-136
+ * points (b,n,c), idx (b,m,nsample) -> out (b,m,nsample,c). */
+int vnb_group_point(int b, int n, int c, int m, int nsample, const float* points, const int* idx, float* out,
+                    void* stream);
+
+/* ------------------------------------------------------------------ tf_ops/3d_interpolation ----------- */
+
+/* threenn_cpu(b,n,m,xyz1,xyz2,dist,idx)                         tf_interpolate.cpp:60-103
+ * xyz1 (b,n,3) unknown, xyz2 (b,m,3) known -> dist (b,n,3) SQUARED f32, idx (b,n,3) i32 (ascending, strict <). */
+int vnb_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist, int* idx, void* stream);
+
+/* threeinterpolate_cpu(b,m,c,n,points,idx,weight,out)           tf_interpolate.cpp:107-127
+ * points (b,m,c), idx (b,n,3), weight (b,n,3) -> out (b,n,c). */
+int vnb_three_interpolate(int b, int m, int c, int n, const float* points, const int* idx, const float* weight,
+                          float* out, void* stream);
+
+/* ------------------------------------------------------------------ tf_ops/3d_nms --------------------- */
+
+/* NonMaxSuppression3DOp::Compute                                 tf_nms3d.cpp:283-305 (+ :202-273)
+ * bbox (b,k,8,3), scores (b,k), objectiveness (b,k,2), 0 <= iou_threshold <= 1.   k <= 1024.
+ * Outputs (all caller-allocated):
+ *   keep      (b,k)   u8   1 where the box survives NMS (the per-cloud keep mask)
+ *   out_idx   (b*k,2) i32  rows (batch, box) of the survivors in the reference's GLOBAL descending-score order
+ *                          (exact score ties: ascending (batch, box) — the reference's order among exactly equal
+ *                          scores is a libstdc++ heap artefact)
+ *   out_count (1)     i32  number of valid rows in out_idx
+ * workspace: vnb_nms3d_workspace_bytes(b,k) bytes of device memory. */
+size_t vnb_nms3d_workspace_bytes(int b, int k);
+int vnb_nms3d(int b, int k, const float* bbox, const float* scores, const float* objectiveness, float iou_threshold,
+              uint8_t* keep, int* out_idx, int* out_count, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------ fused layers (boundary B) --------- */
+/* The dense arithmetic the reference delegates to TensorFlow/Tensorpack (Conv2D 1x1 + BN(EMA) + ReLU + reduce_max,
+ * utils.py:120-158,286-292; FullyConnected, model.py:53-61).  BatchNorm is folded into W,b by the host. */
+
+/* Packed weight image for the tensor-core kernels: fp16, [n_pad rows][k_pad cols] K-major, 128-byte-swizzled panels
+ * of 64 k-columns (the exact shared-memory image tcgen05.mma consumes).  n_pad = round_up(cout,16),
+ * k_pad = round_up(cin,16).  vnb_pack_weight_f16 converts W (cin,cout) f32 row-major (TF [Cin,Cout]) on device. */
+size_t vnb_weight_image_bytes(int cin, int cout);
+int vnb_pack_weight_f16(int cin, int cout, const float* w, void* image, void* stream);
+
+#define VNB_ACT_NONE 0
+#define VNB_ACT_RELU 1
+
+/* out[r, :] = act(in[r, :] @ W + bias) (+ residual[r, :])       rows x cin -> rows x cout
+ * precision 0: fp32 SIMT (W = (cin,cout) f32 in `w_f32`);  precision 1: fp16 tensor cores, fp32 accumulate
+ * (W = packed image in `w_img`).  Either out_f32 (rows,cout) or out_f16 (rows,cout) (or both) may be given. */
+int vnb_linear(int rows, int cin, int cout, const float* in, const float* w_f32, const void* w_img, const float* bias,
+               const float* residual, int act, float* out_f32, void* out_f16, int precision, void* stream);
+
+/* pointnet_sa_module grouping + shared MLP (3 layers) + max-pool, fused        utils.py:49-55,120-132
+ *   new_points[b,j,:] = max_s relu(L3(relu(L2(relu(L1([xyz[idx]-new_xyz, feat[idx]]))))))
+ * xyz (b,n,3), feat (b,n,c) f32, new_xyz (b,m,3), idx (b,m,nsample) with nsample == 64 -> out (b,m,c3) f32.
+ * Layer i has folded weights w{i} (cin_i,cout_i) f32 and bias b{i}; cin_1 = 3 + c (relative xyz first).
+ * precision 0: fp32 SIMT, weights read from w*_f32.
+ * precision 1: tensor cores.  Needs w2_img / w3_img (packed) and
+ *    - c <= 13 : layer 1 also on tensor cores from w1_img (K padded to 16);
+ *    - c  > 13 : layer 1 is hoisted through the gather: q = feat @ W1[3:,:] + b1 is computed ONCE per source point
+ *                by the caller (vnb_linear, fp16 output (b*n, c1)) and passed as `q_f16`; the kernel adds the
+ *                rank-3 relative-xyz term W1[0:3,:] (w1_f32 rows 0..2) per grouped row in fp32. */
+int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, const float* xyz, const float* feat,
+                         const float* new_xyz, const int* idx, int c1, int c2, int c3, const float* w1_f32,
+                         const float* b1, const float* w2_f32, const float* b2, const float* w3_f32, const float* b3,
+                         const void* w1_img, const void* w2_img, const void* w3_img, const void* q_f16, float* out,
+                         int precision, void* stream);
+
+/* pointnet_fp_module front half: inverse-distance weights + three_interpolate + concat     utils.py:279-286
+ * dist (b,n,3), idx (b,n,3) from vnb_three_nn; points2 (b,m,c2) known features; points1 (b,n,c1) skip features
+ * -> out (b,n,c2+c1) = [interpolated, points1]. */
+int vnb_fp_interpolate_concat(int b, int n, int m, int c1, int c2, const float* dist, const int* idx,
+                              const float* points1, const float* points2, float* out, void* stream);
+
+/* row-wise concat / split helpers: out (rows, ca+cb) = [a (rows,ca), b (rows,cb)]  and the inverse */
+int vnb_concat2(int rows, int ca, int cb, const float* a, const float* b, float* out, void* stream);
+int vnb_split2(int rows, int ca, int cb, const float* in, float* a, float* b, void* stream);
+
+/* box decode                                                    model.py:100-129 (+ dataset.py:36-49 mean sizes)
+ * proposals_xyz (b,k,3), proposals_output (b,k,79), class_mean_size (10,3)
+ * -> bboxes (b,k,8,3), scores (b,k) = max class logit (model.py:133), objectness (b,k,2), class_scores (b,k,10). */
+int vnb_decode_boxes(int b, int k, const float* proposals_xyz, const float* proposals_output,
+                     const float* class_mean_size, float* bboxes, float* scores, float* objectness,
+                     float* class_scores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOTENET_B200_H_ */

@@ -1,0 +1,80 @@
+"""ctypes binding of libvotenet_b200.so (the C ABI declared in include/votenet_b200.h).
+
+PyTorch is used for device memory and streams only.  There is NO CPU fallback: if the CUDA library has not been built
+the import fails loudly; if a tensor is not a contiguous CUDA tensor of the expected dtype the call raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvotenet_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build the sm_100a CUDA library first (python -m votenet_b200.build, or "
+        f"__graft_entry__.build()).  votenet_b200 has no CPU / PyTorch fallback."
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+_i, _f, _p, _sz = C.c_int, C.c_float, C.c_void_p, C.c_size_t
+_SIGS = {
+    "vnb_abi_version": ([], _i),
+    "vnb_last_error": ([], C.c_char_p),
+    "vnb_farthest_point_sample": ([_i, _i, _i, _p, _p, _p], _i),
+    "vnb_gather_point": ([_i, _i, _i, _p, _p, _p, _p], _i),
+    "vnb_query_ball_point": ([_i, _i, _i, _f, _i, _p, _p, _p, _p, _p], _i),
+    "vnb_group_point": ([_i, _i, _i, _i, _i, _p, _p, _p, _p], _i),
+    "vnb_three_nn": ([_i, _i, _i, _p, _p, _p, _p, _p], _i),
+    "vnb_three_interpolate": ([_i, _i, _i, _i, _p, _p, _p, _p, _p], _i),
+    "vnb_nms3d_workspace_bytes": ([_i, _i], _sz),
+    "vnb_nms3d": ([_i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p], _i),
+    "vnb_weight_image_bytes": ([_i, _i], _sz),
+    "vnb_pack_weight_f16": ([_i, _i, _p, _p, _p], _i),
+    "vnb_linear": ([_i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _i, _p], _i),
+    "vnb_sa_group_mlp_max": ([_i] * 5 + [_p] * 4 + [_i] * 3 + [_p] * 11 + [_i, _p], _i),
+    "vnb_fp_interpolate_concat": ([_i] * 5 + [_p] * 6, _i),
+    "vnb_concat2": ([_i, _i, _i, _p, _p, _p, _p], _i),
+    "vnb_split2": ([_i, _i, _i, _p, _p, _p, _p], _i),
+    "vnb_decode_boxes": ([_i, _i] + [_p] * 8, _i),
+}
+for _name, (_args, _res) in _SIGS.items():
+    _fn = getattr(lib, _name)  # AttributeError here == the library does not export a declared symbol
+    _fn.argtypes = _args
+    _fn.restype = _res
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+VNB_ERR_INVALID, VNB_ERR_CUDA = 1, 2
+
+if lib.vnb_abi_version() != 1:
+    raise ImportError("libvotenet_b200.so: ABI version mismatch (rebuild)")
+
+
+def check(rc):
+    """0 -> ok; VNB_ERR_INVALID -> ValueError (the reference raises InvalidArgument); VNB_ERR_CUDA -> RuntimeError."""
+    if rc == 0:
+        return
+    msg = lib.vnb_last_error().decode("utf-8", "replace")
+    if rc == VNB_ERR_INVALID:
+        raise ValueError(msg)
+    raise RuntimeError(f"votenet_b200 CUDA error: {msg}")
+
+
+def stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def dptr(t, dtype=None, name="tensor"):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    if not torch.is_tensor(t) or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA tensor (votenet_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())

@@ -1,0 +1,238 @@
+// 3-D NMS for B200: score-rank sort -> warp-ballot IoU bitmask -> greedy pass on the bitmask -> global ordering.
+//
+// Reference: tf_ops/3d_nms/tf_nms3d.cpp (single CPU thread): candidates = boxes with objectness[1] > objectness[0]
+// (:230), popped from a max-heap on score over the whole batch (:222-234); a candidate is dropped if any
+// already-selected box OF THE SAME CLOUD has IoU3D > thr (:248-255); IoU3D = BEV convex-polygon clip area x
+// y-overlap / union (:178-192).  Greedy NMS is order-dependent only through the score order, so per cloud it is
+// "walk candidates by descending score; keep iff no kept earlier candidate overlaps" — computed here as:
+//   K1  per cloud: rank candidates by (score desc, box index asc)                      [O(k^2) compares, 1 CTA]
+//   K2  bit (p,q), q<p, = IOUGreaterThanThreshold(candidate p, earlier candidate q)    [one warp -> one 32-bit word
+//       via __ballot_sync; argument order (candidate, selected) as at :250 because the clip is not symmetric in float]
+//   K3  per cloud: one warp walks p = 0..ncand-1 with the kept-set as a bitmask in registers
+//   K4  rows (batch, box) of the survivors in global descending-score order (the reference's output order)
+// This translation unit is compiled with -fmad=false: the reference is g++ -O2 for generic x86-64 (no FMA), so
+// every float/double expression below must stay un-fused to reproduce its roundings.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace vnb {
+
+// tf_nms3d.cpp:43-46
+__device__ __forceinline__ float nms_area2d(const float* bb) {
+  return sqrtf((bb[0] - bb[3]) * (bb[0] - bb[3]) + (bb[2] - bb[5]) * (bb[2] - bb[5])) *
+         sqrtf((bb[3] - bb[6]) * (bb[3] - bb[6]) + (bb[5] - bb[8]) * (bb[5] - bb[8]));
+}
+// :48-50
+__device__ __forceinline__ float nms_area3d(const float* bb) { return nms_area2d(bb) * (bb[1] - bb[13]); }
+
+// :53-67  even-odd ray cast against corners 0..3 projected on (x,z)
+__device__ __forceinline__ bool point_in_polygon(float px, float pz, const float* poly) {
+  bool result = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + 3) & 3;
+    if ((poly[i * 3 + 2] > pz) != (poly[j * 3 + 2] > pz) &&
+        (px < (poly[j * 3] - poly[i * 3]) * (pz - poly[i * 3 + 2]) / (poly[j * 3 + 2] - poly[i * 3 + 2]) + poly[i * 3]))
+      result = !result;
+  }
+  return result;
+}
+
+#define NMS_MIN(a, b) (((a) < (b)) ? (a) : (b))
+#define NMS_MAX(a, b) (((a) > (b)) ? (a) : (b))
+
+// :69-100  segment/segment intersection in double, narrowed to float
+__device__ __forceinline__ bool seg_intersect(float ax, float az, float bx, float bz, float cx, float cz, float dx,
+                                              float dz, float& ox, float& oz) {
+  double A1 = bz - az;
+  double B1 = ax - bx;
+  double C1 = A1 * ax + B1 * az;
+  double A2 = dz - cz;
+  double B2 = cx - dx;
+  double C2 = A2 * cx + B2 * cz;
+  double det = A1 * B2 - A2 * B1;
+  if (fabs(det) < 1e-7) return false;
+  double x = (B2 * C1 - B1 * C2) / det;
+  double z = (A1 * C2 - A2 * C1) / det;
+  bool on1 = (NMS_MIN(ax, bx) <= x) && (NMS_MAX(ax, bx) >= x) && (NMS_MIN(az, bz) <= z) && (NMS_MAX(az, bz) >= z);
+  bool on2 = (NMS_MIN(cx, dx) <= x) && (NMS_MAX(cx, dx) >= x) && (NMS_MIN(cz, dz) <= z) && (NMS_MAX(cz, dz) >= z);
+  if (on1 && on2) {
+    ox = (float)x;
+    oz = (float)z;
+    return true;
+  }
+  return false;
+}
+
+// :122-175  BEV clip area of box1 against box2 (each 8x3 corners; corners 0..3 = top face)
+__device__ float intersection2d(const float* b1, const float* b2) {
+  float px[24], pz[24], ang[24];
+  int np = 0;
+  for (int i = 0; i < 4; ++i)
+    if (point_in_polygon(b1[i * 3], b1[i * 3 + 2], b2)) { px[np] = b1[i * 3]; pz[np] = b1[i * 3 + 2]; ++np; }
+  for (int i = 0; i < 4; ++i)
+    if (point_in_polygon(b2[i * 3], b2[i * 3 + 2], b1)) { px[np] = b2[i * 3]; pz[np] = b2[i * 3 + 2]; ++np; }
+  for (int i = 0; i < 4; ++i) {
+    const int nx = (i + 1) & 3;
+    for (int e = 0; e < 4; ++e) {
+      const int en = (e + 1) & 3;
+      float ox, oz;
+      if (seg_intersect(b1[i * 3], b1[i * 3 + 2], b1[nx * 3], b1[nx * 3 + 2], b2[e * 3], b2[e * 3 + 2], b2[en * 3],
+                        b2[en * 3 + 2], ox, oz)) {
+        px[np] = ox; pz[np] = oz; ++np;
+      }
+    }
+  }
+  float mx = 0.f, mz = 0.f;
+  for (int i = 0; i < np; ++i) { mx += px[i]; mz += pz[i]; }
+  mx /= (float)np;  // 0/0 -> NaN when np == 0; loops below are then empty (area 0), as in the reference
+  mz /= (float)np;
+  for (int i = 0; i < np; ++i) ang[i] = atan2f(pz[i] - mz, px[i] - mx);
+  for (int i = 1; i < np; ++i) {  // sort by angle (:164-166); keys are distinct except for coincident points
+    float a = ang[i], x = px[i], z = pz[i];
+    int j = i - 1;
+    while (j >= 0 && a < ang[j]) { ang[j + 1] = ang[j]; px[j + 1] = px[j]; pz[j + 1] = pz[j]; --j; }
+    ang[j + 1] = a; px[j + 1] = x; pz[j + 1] = z;
+  }
+  float area = 0.f;
+  for (int i = 0, j = np - 1; i < np; j = i++)
+    area += fabsf((mx * (pz[i] - pz[j]) + px[i] * (pz[j] - mz) + px[j] * (mz - pz[i])) / 2);
+  return area;
+}
+
+// :178-192
+__device__ bool iou_greater(const float* bi, const float* bj, float thr) {
+  float inter2d = intersection2d(bi, bj);
+  float h = NMS_MIN(bi[1], bj[1]) - NMS_MAX(bi[13], bj[13]);
+  float inter3d = NMS_MAX(h, 0.f) * inter2d;
+  float iou = inter3d / (nms_area3d(bi) + nms_area3d(bj) - inter3d);
+  return iou > thr;
+}
+
+// K1: per cloud, rank candidates by (score desc, index asc).  order[b][rank] = box, ncand[b].
+__global__ void nms_rank_kernel(int k, const float* __restrict__ scores, const float* __restrict__ obj,
+                                int* __restrict__ order, int* __restrict__ ncand, uint8_t* __restrict__ keep,
+                                int* __restrict__ out_count) {
+  extern __shared__ float s_sc[];  // k scores, then k candidate flags (as int)
+  int* s_c = reinterpret_cast<int*>(s_sc + k);
+  __shared__ int s_n;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) s_n = 0;
+  if (b == 0 && threadIdx.x == 0) *out_count = 0;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    s_sc[i] = scores[(size_t)b * k + i];
+    s_c[i] = obj[((size_t)b * k + i) * 2 + 1] > obj[((size_t)b * k + i) * 2] ? 1 : 0;  // :230
+    keep[(size_t)b * k + i] = 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    if (!s_c[i]) continue;
+    const float si = s_sc[i];
+    int rank = 0;
+    for (int j = 0; j < k; ++j) rank += (s_c[j] && (s_sc[j] > si || (s_sc[j] == si && j < i))) ? 1 : 0;
+    order[(size_t)b * k + rank] = i;
+    atomicAdd(&s_n, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ncand[b] = s_n;
+}
+
+// K2: mask[b][p][w] bit (q & 31), q = 32 w + lane < p  <=>  candidate p is suppressed by earlier candidate q.
+__global__ void __launch_bounds__(256) nms_mask_kernel(int k, int W, float thr, const float* __restrict__ bbox,
+                                                        const int* __restrict__ order, const int* __restrict__ ncand,
+                                                        uint32_t* __restrict__ mask) {
+  const int b = blockIdx.y, p = blockIdx.x;
+  const int nc = ncand[b];
+  if (p >= nc) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* bi = bbox + ((size_t)b * k + order[(size_t)b * k + p]) * 24;
+  for (int w = warp; w < W; w += nw) {
+    const int q = w * 32 + lane;
+    bool sup = false;
+    if (q < p) sup = iou_greater(bi, bbox + ((size_t)b * k + order[(size_t)b * k + q]) * 24, thr);
+    unsigned m = __ballot_sync(0xffffffffu, sup);
+    if (lane == 0) mask[((size_t)b * k + p) * W + w] = m;
+  }
+}
+
+// K3: greedy pass.  One CTA per cloud stages the cloud's bitmask rows in shared memory; warp 0 walks them with the
+// kept-set held as W<=32 words, one per lane.
+__global__ void __launch_bounds__(256) nms_greedy_kernel(int k, int W, const int* __restrict__ order,
+                                                          const int* __restrict__ ncand,
+                                                          const uint32_t* __restrict__ mask, uint8_t* __restrict__ keep,
+                                                          uint8_t* __restrict__ kept_pos, int* __restrict__ out_count) {
+  extern __shared__ uint32_t s_mask[];
+  const int b = blockIdx.x;
+  const int nc = ncand[b];
+  for (int t = threadIdx.x; t < nc * W; t += blockDim.x) s_mask[t] = mask[(size_t)b * k * W + t];
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  uint32_t kept = 0;
+  int nkept = 0;
+  for (int p = 0; p < nc; ++p) {
+    uint32_t v = (lane < W) ? (s_mask[p * W + lane] & kept) : 0u;
+    if (!__any_sync(0xffffffffu, v != 0u)) {
+      if (lane == (p >> 5)) kept |= 1u << (p & 31);
+      if (lane == 0) keep[(size_t)b * k + order[(size_t)b * k + p]] = 1;
+      ++nkept;
+    }
+  }
+  if (lane == 0) atomicAdd(out_count, nkept);
+  (void)kept_pos;
+}
+
+// K4: global order of the survivors: descending score, exact ties by ascending (batch, box).
+__global__ void nms_emit_kernel(int total, int k, const float* __restrict__ scores, const uint8_t* __restrict__ keep,
+                                int* __restrict__ out_idx) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total || !keep[e]) return;
+  const float se = scores[e];
+  int rank = 0;
+  for (int f = 0; f < total; ++f) rank += (keep[f] && (scores[f] > se || (scores[f] == se && f < e))) ? 1 : 0;
+  out_idx[rank * 2 + 0] = e / k;
+  out_idx[rank * 2 + 1] = e % k;
+}
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace vnb
+
+using namespace vnb;
+
+extern "C" size_t vnb_nms3d_workspace_bytes(int b, int k) {
+  if (b <= 0 || k <= 0) return 256;
+  size_t W = (size_t)(k + 31) / 32;
+  return align256((size_t)b * k * 4) + align256((size_t)b * 4) + align256((size_t)b * k * W * 4);
+}
+
+extern "C" int vnb_nms3d(int b, int k, const float* bbox, const float* scores, const float* objectiveness,
+                         float iou_threshold, uint8_t* keep, int* out_idx, int* out_count, void* workspace,
+                         void* stream) {
+  VNB_REQUIRE(b >= 0 && k >= 0, "3D NMS expects (batch_size, nbbox, 8, 3) bbox shape.");            // tf_nms3d.cpp:287
+  VNB_REQUIRE(iou_threshold >= 0 && iou_threshold <= 1, "iou_threshold must be in [0, 1]");        // :300
+  VNB_REQUIRE(k <= 1024, "nms3d: at most 1024 boxes per cloud (got %d)", k);
+  cudaStream_t st = as_stream(stream);
+  if (b == 0 || k == 0) {
+    VNB_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int), st));
+    return VNB_OK;
+  }
+  const int W = (k + 31) / 32;
+  char* ws = static_cast<char*>(workspace);
+  int* order = reinterpret_cast<int*>(ws);
+  int* ncand = reinterpret_cast<int*>(ws + align256((size_t)b * k * 4));
+  uint32_t* mask = reinterpret_cast<uint32_t*>(ws + align256((size_t)b * k * 4) + align256((size_t)b * 4));
+  nms_rank_kernel<<<b, 256, (size_t)k * 8, st>>>(k, scores, objectiveness, order, ncand, keep, out_count);
+  if (int rc = check_launch("nms3d rank")) return rc;
+  nms_mask_kernel<<<dim3(k, b), 256, 0, st>>>(k, W, iou_threshold, bbox, order, ncand, mask);
+  if (int rc = check_launch("nms3d mask")) return rc;
+  size_t smem = (size_t)k * W * 4;
+  if (smem > 48 * 1024)
+    VNB_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_greedy_kernel<<<b, 256, smem, st>>>(k, W, order, ncand, mask, keep, nullptr, out_count);
+  if (int rc = check_launch("nms3d greedy")) return rc;
+  const int total = b * k;
+  nms_emit_kernel<<<(total + 127) / 128, 128, 0, st>>>(total, k, scores, keep, out_idx);
+  return check_launch("nms3d emit");
+}

@@ -1,0 +1,381 @@
+// HBM-bound point ops: gather_point, query_ball_point, group_point, three_nn, three_interpolate, the FP-module
+// front half, concat/split and box decode.  All integer/index outputs are bit-exact with the reference; the
+// floating-point contraction of every reference expression is spelled with intrinsics (never left to -fmad).
+#include "common.cuh"
+
+#include <math.h>
+
+namespace vnb {
+
+static thread_local char g_err[512] = "";
+char* err_buf() { return g_err; }
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gather_point — reference gatherpointKernel, tf_sampling_g.cu:172-181.  One thread per output point.
+__global__ void gather_point_kernel(int n, int m, const float* __restrict__ inp, const int* __restrict__ idx,
+                                    float* __restrict__ out, int total) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int bi = t / m;
+  int a = idx[t];
+  const float* s = inp + ((size_t)bi * n + a) * 3;
+  float* d = out + (size_t)t * 3;
+  d[0] = s[0];
+  d[1] = s[1];
+  d[2] = s[2];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// query_ball_point — reference query_ball_point_gpu, tf_grouping_g.cu:3-36.
+// One WARP per query: lanes test 32 consecutive points per step, __ballot_sync + popc gives the
+// order-preserving compaction ("first nsample in index order", :16-17), early exit once nsample hits are found.
+// The predicate max(sqrtf(d2),1e-20f) < radius is evaluated as d2 <= d2_max, where d2_max is the largest float
+// whose correctly-rounded sqrt is < radius (computed on the host; sqrt is monotone so no decision changes).
+constexpr int BQ_WARPS = 8;
+__global__ void __launch_bounds__(BQ_WARPS * 32) query_ball_kernel(int n, int m, float d2_max, int nsample,
+                                                                    const float* __restrict__ xyz1,
+                                                                    const float* __restrict__ xyz2,
+                                                                    int* __restrict__ idx, int* __restrict__ pts_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * BQ_WARPS + (threadIdx.x >> 5);
+  const int bi = blockIdx.y;
+  if (j >= m) return;
+  const float* p = xyz1 + (size_t)bi * n * 3;
+  const float* q = xyz2 + ((size_t)bi * m + j) * 3;
+  int* row = idx + ((size_t)bi * m + j) * nsample;
+  const float qx = q[0], qy = q[1], qz = q[2];
+  int cnt = 0;
+  int first = -1;
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    int k = k0 + lane;
+    bool hit = false;
+    if (k < n) {
+      float dx = qx - p[k * 3 + 0], dy = qy - p[k * 3 + 1], dz = qz - p[k * 3 + 2];
+      hit = d2_ref_gpu(dx, dy, dz) <= d2_max;
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, hit);
+    if (mask) {
+      if (first < 0) first = k0 + __ffs(mask) - 1;
+      int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+      if (hit && pos < nsample) row[pos] = k;
+      cnt += __popc(mask);
+      if (cnt >= nsample) break;
+    }
+  }
+  if (cnt > nsample) cnt = nsample;
+  if (cnt > 0)
+    for (int l = cnt + lane; l < nsample; l += 32) row[l] = first;  // pad with the first hit (:26-29)
+  if (lane == 0) pts_cnt[(size_t)bi * m + j] = cnt;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// group_point — reference group_point_gpu, tf_grouping_g.cu:40-57.  One warp per gathered row, lanes over channels.
+__global__ void group_point_kernel(int n, int c, int rows_per_batch, const float* __restrict__ points,
+                                   const int* __restrict__ idx, float* __restrict__ out, long long total_rows) {
+  long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= total_rows) return;
+  int lane = threadIdx.x & 31;
+  int bi = (int)(r / rows_per_batch);
+  int ii = idx[r];
+  const float* s = points + ((size_t)bi * n + ii) * c;
+  float* d = out + (size_t)r * c;
+  for (int l = lane; l < c; l += 32) d[l] = s[l];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// three_nn — reference threenn_cpu, tf_interpolate.cpp:60-103.  Thread per unknown point; known points staged
+// through shared memory.  d is the UN-FUSED float expression ((dx*dx + dy*dy) + dz*dz) (the reference is g++ -O2
+// without FMA), strict '<' insertion so the earlier k wins ties.  (float)1e40 == +inf for unused slots (m < 3).
+constexpr int NN_TILE = 1024;
+__global__ void __launch_bounds__(128) three_nn_kernel(int n, int m, const float* __restrict__ xyz1,
+                                                        const float* __restrict__ xyz2, float* __restrict__ dist,
+                                                        int* __restrict__ idx) {
+  __shared__ float s[NN_TILE * 3];
+  const int bi = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = j < n;
+  float x1 = 0, y1 = 0, z1 = 0;
+  if (active) {
+    const float* u = xyz1 + ((size_t)bi * n + j) * 3;
+    x1 = u[0]; y1 = u[1]; z1 = u[2];
+  }
+  float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+  int i1 = 0, i2 = 0, i3 = 0;
+  const float* kn = xyz2 + (size_t)bi * m * 3;
+  for (int k0 = 0; k0 < m; k0 += NN_TILE) {
+    int cnt = min(NN_TILE, m - k0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt * 3; t += blockDim.x) s[t] = kn[(size_t)k0 * 3 + t];
+    __syncthreads();
+    if (active) {
+      for (int k = 0; k < cnt; ++k) {
+        float dx = __fsub_rn(s[k * 3 + 0], x1), dy = __fsub_rn(s[k * 3 + 1], y1), dz = __fsub_rn(s[k * 3 + 2], z1);
+        float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        int kk = k0 + k;
+        if (d < b1) {
+          b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = kk;
+        } else if (d < b2) {
+          b3 = b2; i3 = i2; b2 = d; i2 = kk;
+        } else if (d < b3) {
+          b3 = d; i3 = kk;
+        }
+      }
+    }
+  }
+  if (active) {
+    float* dd = dist + ((size_t)bi * n + j) * 3;
+    int* di = idx + ((size_t)bi * n + j) * 3;
+    dd[0] = b1; dd[1] = b2; dd[2] = b3;
+    di[0] = i1; di[1] = i2; di[2] = i3;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// three_interpolate — reference threeinterpolate_cpu, tf_interpolate.cpp:107-127.
+// out = p[i1]*w1 + p[i2]*w2 + p[i3]*w3, un-fused, left to right (:119).  One warp per output row.
+__global__ void three_interpolate_kernel(int m, int c, int n, const float* __restrict__ points,
+                                         const int* __restrict__ idx, const float* __restrict__ weight,
+                                         float* __restrict__ out, long long total_rows) {
+  long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= total_rows) return;
+  int lane = threadIdx.x & 31;
+  int bi = (int)(r / n);
+  const float w1 = weight[r * 3 + 0], w2 = weight[r * 3 + 1], w3 = weight[r * 3 + 2];
+  const float* p = points + (size_t)bi * m * c;
+  const float* p1 = p + (size_t)idx[r * 3 + 0] * c;
+  const float* p2 = p + (size_t)idx[r * 3 + 1] * c;
+  const float* p3 = p + (size_t)idx[r * 3 + 2] * c;
+  float* o = out + (size_t)r * c;
+  for (int l = lane; l < c; l += 32)
+    o[l] = __fadd_rn(__fadd_rn(__fmul_rn(p1[l], w1), __fmul_rn(p2[l], w2)), __fmul_rn(p3[l], w3));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pointnet_fp_module front half, utils.py:279-286: d = max(d,1e-10); w = (1/d) / sum(1/d); interpolate; concat
+// [interpolated (c2), skip (c1)].  One warp per unknown point.
+__global__ void fp_interp_concat_kernel(int n, int m, int c1, int c2, const float* __restrict__ dist,
+                                        const int* __restrict__ idx, const float* __restrict__ points1,
+                                        const float* __restrict__ points2, float* __restrict__ out,
+                                        long long total_rows) {
+  long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= total_rows) return;
+  int lane = threadIdx.x & 31;
+  int bi = (int)(r / n);
+  float d1 = fmaxf(dist[r * 3 + 0], 1e-10f), d2 = fmaxf(dist[r * 3 + 1], 1e-10f), d3 = fmaxf(dist[r * 3 + 2], 1e-10f);
+  float r1 = __fdiv_rn(1.0f, d1), r2 = __fdiv_rn(1.0f, d2), r3 = __fdiv_rn(1.0f, d3);
+  float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
+  float w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm), w3 = __fdiv_rn(r3, norm);
+  const float* p = points2 + (size_t)bi * m * c2;
+  const float* p1 = p + (size_t)idx[r * 3 + 0] * c2;
+  const float* p2 = p + (size_t)idx[r * 3 + 1] * c2;
+  const float* p3 = p + (size_t)idx[r * 3 + 2] * c2;
+  float* o = out + (size_t)r * (c1 + c2);
+  for (int l = lane; l < c2; l += 32)
+    o[l] = __fadd_rn(__fadd_rn(__fmul_rn(p1[l], w1), __fmul_rn(p2[l], w2)), __fmul_rn(p3[l], w3));
+  if (points1 != nullptr) {
+    const float* s = points1 + (size_t)r * c1;
+    for (int l = lane; l < c1; l += 32) o[c2 + l] = s[l];
+  }
+}
+
+__global__ void concat2_kernel(long long rows, int ca, int cb, const float* __restrict__ a,
+                               const float* __restrict__ b, float* __restrict__ out) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int c = ca + cb;
+  if (t >= rows * c) return;
+  long long r = t / c;
+  int l = (int)(t - r * c);
+  out[t] = l < ca ? a[r * ca + l] : b[r * cb + (l - ca)];
+}
+__global__ void split2_kernel(long long rows, int ca, int cb, const float* __restrict__ in, float* __restrict__ a,
+                              float* __restrict__ b) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int c = ca + cb;
+  if (t >= rows * c) return;
+  long long r = t / c;
+  int l = (int)(t - r * c);
+  if (l < ca) a[r * ca + l] = in[t];
+  else b[r * cb + (l - ca)] = in[t];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// box decode — model.py:100-129.  One thread per proposal.  NH=12, NS=NC=10 (config.py:2-3).
+constexpr int NH = 12, NS = 10, NC = 10, PCH = 5 + 2 * NH + 4 * NS + NC;
+__global__ void decode_kernel(int total, const float* __restrict__ pxyz, const float* __restrict__ pout,
+                              const float* __restrict__ mean_size, float* __restrict__ bboxes,
+                              float* __restrict__ scores, float* __restrict__ objectness,
+                              float* __restrict__ class_scores) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const float* po = pout + (size_t)t * PCH;
+  // argmax = first maximal index (tf.argmax), model.py:115,122
+  int sc = 0;
+  float best = po[5 + 2 * NH];
+  for (int i = 1; i < NS; ++i) {
+    float v = po[5 + 2 * NH + i];
+    if (v > best) { best = v; sc = i; }
+  }
+  int hc = 0;
+  best = po[5];
+  for (int i = 1; i < NH; ++i) {
+    float v = po[5 + i];
+    if (v > best) { best = v; hc = i; }
+  }
+  float size[3];
+  for (int a = 0; a < 3; ++a) {
+    float res = po[5 + 2 * NH + NS + sc * 3 + a];
+    size[a] = __fmul_rn(mean_size[sc * 3 + a], fmaxf(__fadd_rn(1.0f, res), 1e-6f));  // :119
+  }
+  float cx = __fadd_rn(pxyz[t * 3 + 0], po[2]), cy = __fadd_rn(pxyz[t * 3 + 1], po[3]),
+        cz = __fadd_rn(pxyz[t * 3 + 2], po[4]);  // :121
+  float hres = po[5 + NH + hc];
+  const float PI_F = 3.14159265358979323846f;
+  float ang = __fdiv_rn(__fmul_rn(__fadd_rn(__fmul_rn((float)hc, 2.0f), hres), PI_F), (float)NH);
+  const float TWO_PI = __fmul_rn(2.0f, PI_F);
+  // tf.floormod: result takes the sign of the divisor
+  float heading = fmodf(ang, TWO_PI);
+  if (heading < 0.0f) heading = __fadd_rn(heading, TWO_PI);
+  float c = cosf(heading), s = sinf(heading);
+  float l = size[0], w = size[1], h = size[2];  // lwh (x,z,y) order, model.py:108
+  const float sx[8] = {1, 1, -1, -1, 1, 1, -1, -1};
+  const float sy[8] = {1, 1, 1, 1, -1, -1, -1, -1};
+  const float sz[8] = {1, -1, -1, 1, 1, -1, -1, 1};
+  float* bb = bboxes + (size_t)t * 24;
+  for (int k = 0; k < 8; ++k) {
+    float x = __fmul_rn(sx[k], __fmul_rn(l, 0.5f)), y = __fmul_rn(sy[k], __fmul_rn(h, 0.5f)),
+          z = __fmul_rn(sz[k], __fmul_rn(w, 0.5f));
+    // rotation [[c,0,s],[0,1,0],[-s,0,c]] (model.py:107), einsum 'ijkl,ijlm->ijmk'
+    bb[k * 3 + 0] = __fadd_rn(__fadd_rn(__fmul_rn(c, x), __fmul_rn(s, z)), cx);
+    bb[k * 3 + 1] = __fadd_rn(y, cy);
+    bb[k * 3 + 2] = __fadd_rn(__fadd_rn(__fmul_rn(-s, x), __fmul_rn(c, z)), cz);
+  }
+  float mx = po[PCH - NC];
+  for (int i = 0; i < NC; ++i) {
+    float v = po[PCH - NC + i];
+    class_scores[(size_t)t * NC + i] = v;
+    mx = fmaxf(mx, v);
+  }
+  scores[t] = mx;
+  objectness[t * 2 + 0] = po[0];
+  objectness[t * 2 + 1] = po[1];
+}
+
+// Largest float t with sqrtf(t) < radius (host; IEEE sqrt is correctly rounded on both host and device).
+static float ball_d2_max(float radius) {
+  float t = radius * radius;
+  while (t > 0.0f && !(sqrtf(t) < radius)) t = nextafterf(t, 0.0f);
+  for (;;) {
+    float u = nextafterf(t, INFINITY);
+    if (sqrtf(u) < radius) t = u;
+    else break;
+  }
+  return t;
+}
+
+}  // namespace vnb
+
+using namespace vnb;
+
+extern "C" {
+
+int vnb_abi_version(void) { return VNB_ABI_VERSION; }
+const char* vnb_last_error(void) { return err_buf(); }
+
+int vnb_gather_point(int b, int n, int m, const float* inp, const int* idx, float* out, void* stream) {
+  VNB_REQUIRE(b >= 0 && n > 0 && m >= 0, "GatherPoint expects (batch_size,num_points,3) inp shape / (batch_size,num_result) idx shape");
+  int total = b * m;
+  if (total == 0) return VNB_OK;
+  gather_point_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(n, m, inp, idx, out, total);
+  return check_launch("gather_point");
+}
+
+int vnb_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
+                         int* idx, int* pts_cnt, void* stream) {
+  VNB_REQUIRE(radius > 0, "QueryBallPoint expects positive radius");          // tf_grouping.cpp:71
+  VNB_REQUIRE(nsample > 0, "QueryBallPoint expects positive nsample");        // tf_grouping.cpp:74
+  VNB_REQUIRE(b >= 0 && n >= 0 && m >= 0, "QueryBallPoint expects (batch_size, ndataset, 3) xyz1 shape.");
+  if (b == 0 || m == 0) return VNB_OK;
+  // max(sqrtf(d2),1e-20f) < radius: for radius <= 1e-20f nothing can hit (d2_max < 0 encodes that)
+  float d2_max = (radius <= 1e-20f) ? -1.0f : ball_d2_max(radius);
+  dim3 grid((m + BQ_WARPS - 1) / BQ_WARPS, b);
+  query_ball_kernel<<<grid, BQ_WARPS * 32, 0, as_stream(stream)>>>(n, m, d2_max, nsample, xyz1, xyz2, idx, pts_cnt);
+  return check_launch("query_ball_point");
+}
+
+int vnb_group_point(int b, int n, int c, int m, int nsample, const float* points, const int* idx, float* out,
+                    void* stream) {
+  VNB_REQUIRE(b >= 0 && n > 0 && c > 0 && m >= 0 && nsample >= 0, "GroupPoint expects (batch_size, num_points, channel) points shape");
+  long long rows = (long long)b * m * nsample;
+  if (rows == 0) return VNB_OK;
+  int wpb = 8;
+  group_point_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(n, c, m * nsample, points,
+                                                                                            idx, out, rows);
+  return check_launch("group_point");
+}
+
+int vnb_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist, int* idx, void* stream) {
+  VNB_REQUIRE(b >= 0 && n >= 0 && m >= 0, "ThreeNN expects (b,n,3) xyz1 shape.");
+  if (b == 0 || n == 0) return VNB_OK;
+  dim3 grid((n + 127) / 128, b);
+  three_nn_kernel<<<grid, 128, 0, as_stream(stream)>>>(n, m, xyz1, xyz2, dist, idx);
+  return check_launch("three_nn");
+}
+
+int vnb_three_interpolate(int b, int m, int c, int n, const float* points, const int* idx, const float* weight,
+                          float* out, void* stream) {
+  VNB_REQUIRE(b >= 0 && m > 0 && c > 0 && n >= 0, "ThreeInterpolate expects (b,m,c) points shape");
+  long long rows = (long long)b * n;
+  if (rows == 0) return VNB_OK;
+  int wpb = 8;
+  three_interpolate_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(m, c, n, points, idx,
+                                                                                                  weight, out, rows);
+  return check_launch("three_interpolate");
+}
+
+int vnb_fp_interpolate_concat(int b, int n, int m, int c1, int c2, const float* dist, const int* idx,
+                              const float* points1, const float* points2, float* out, void* stream) {
+  VNB_REQUIRE(b >= 0 && n >= 0 && m > 0 && c1 >= 0 && c2 > 0, "fp_interpolate_concat: bad shape");
+  long long rows = (long long)b * n;
+  if (rows == 0) return VNB_OK;
+  int wpb = 8;
+  fp_interp_concat_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(
+      n, m, c1, c2, dist, idx, c1 > 0 ? points1 : nullptr, points2, out, rows);
+  return check_launch("fp_interpolate_concat");
+}
+
+int vnb_concat2(int rows, int ca, int cb, const float* a, const float* b, float* out, void* stream) {
+  VNB_REQUIRE(rows >= 0 && ca >= 0 && cb >= 0, "concat2: bad shape");
+  long long total = (long long)rows * (ca + cb);
+  if (total == 0) return VNB_OK;
+  concat2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(rows, ca, cb, a, b, out);
+  return check_launch("concat2");
+}
+
+int vnb_split2(int rows, int ca, int cb, const float* in, float* a, float* b, void* stream) {
+  VNB_REQUIRE(rows >= 0 && ca >= 0 && cb >= 0, "split2: bad shape");
+  long long total = (long long)rows * (ca + cb);
+  if (total == 0) return VNB_OK;
+  split2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(rows, ca, cb, in, a, b);
+  return check_launch("split2");
+}
+
+int vnb_decode_boxes(int b, int k, const float* proposals_xyz, const float* proposals_output,
+                     const float* class_mean_size, float* bboxes, float* scores, float* objectness,
+                     float* class_scores, void* stream) {
+  VNB_REQUIRE(b >= 0 && k >= 0, "decode_boxes: bad shape");
+  int total = b * k;
+  if (total == 0) return VNB_OK;
+  decode_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(total, proposals_xyz, proposals_output,
+                                                                    class_mean_size, bboxes, scores, objectness,
+                                                                    class_scores);
+  return check_launch("decode_boxes");
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+"""Drop-in for the reference's tf_ops/sampling/tf_sampling.py (same function names, argument order, output
+dtypes/shapes) over CUDA tensors.  prob_sample is off the VoteNet path and not provided."""
+import torch
+
+from ._lib import check, dptr, lib, stream_ptr
+
+
+def _xyz3(t, name):
+    if t.dim() != 3 or t.shape[2] != 3:
+        raise ValueError(f"{name} expects (batch_size,num_points,3) inp shape")  # tf_sampling.cpp:105,131
+    return t
+
+
+def farthest_point_sample(npoint, inp):
+    """inp (B,N,3) f32 -> (B,npoint) i32.   Reference: tf_sampling.py:48-56 (FarthestPointSample, tf_sampling.cpp:95-123)."""
+    inp = _xyz3(inp, "FarthestPointSample")
+    b, n, _ = inp.shape
+    out = torch.empty((b, int(npoint)), dtype=torch.int32, device=inp.device)
+    check(lib.vnb_farthest_point_sample(b, n, int(npoint), dptr(inp, torch.float32, "inp"), dptr(out), stream_ptr()))
+    return out
+
+
+def gather_point(inp, idx):
+    """inp (B,N,3) f32, idx (B,M) i32 -> (B,M,3) f32.   Reference: tf_sampling.py:29-37 (GatherPoint, tf_sampling.cpp:126-148)."""
+    inp = _xyz3(inp, "GatherPoint")
+    if idx.dim() != 2 or idx.shape[0] != inp.shape[0]:
+        raise ValueError("GatherPoint expects (batch_size,num_result) idx shape")  # tf_sampling.cpp:136
+    b, n, _ = inp.shape
+    m = idx.shape[1]
+    out = torch.empty((b, m, 3), dtype=torch.float32, device=inp.device)
+    check(lib.vnb_gather_point(b, n, m, dptr(inp, torch.float32, "inp"), dptr(idx, torch.int32, "idx"), dptr(out),
+                               stream_ptr()))
+    return out

@@ -1,0 +1,149 @@
+"""PointNet++ layer library — drop-in for the reference's utils.py (pointnet_sa_module / pointnet_fp_module,
+/root/reference/utils.py:93-158,266-294) over CUDA tensors, with the fusion the reference cannot express:
+group_point(xyz) - centroid, group_point(features), concat, the 1x1-conv stack, BN, ReLU and reduce_max are ONE kernel
+(`vnb_sa_group_mlp_max`); three_interpolate + concat are one kernel feeding the tensor-core layers.
+
+`scope` names the weight set exactly as in the reference (tf.variable_scope(scope), utils.py:114,277); weights come from
+a `WeightStore` (BatchNorm folded, fp16 tensor-core images packed once).
+"""
+import torch
+
+from . import tf_grouping, tf_interpolate, tf_sampling
+from ._lib import check, dptr, lib, stream_ptr
+from .weights import fold_bn
+
+PRECISION_FP32 = 0     # fp32 SIMT kernels
+PRECISION_TENSOR = 1   # fp16 operands on tcgen05 tensor cores, fp32 accumulate
+HOIST_MIN_C = 14       # feature widths above 13 use the hoisted layer-1 formulation (see csrc/mlp_tc.cu)
+
+
+class Layer:
+    """One dense layer on the device: folded fp32 weight (cin,cout), bias, lazily packed tensor-core image."""
+
+    def __init__(self, W, b, device):
+        self.W = W.to(device=device, dtype=torch.float32).contiguous()
+        self.b = b.to(device=device, dtype=torch.float32).contiguous()
+        self.cin, self.cout = self.W.shape
+        self._img = None
+
+    @property
+    def img(self):
+        if self._img is None:
+            nbytes = lib.vnb_weight_image_bytes(self.cin, self.cout)
+            img = torch.empty((nbytes,), dtype=torch.uint8, device=self.W.device)
+            check(lib.vnb_pack_weight_f16(self.cin, self.cout, dptr(self.W), dptr(img), stream_ptr()))
+            self._img = img
+        return self._img
+
+    def rows(self, lo, hi):
+        """Sub-layer using input rows [lo,hi) of W (no bias) — used to split W1 into its xyz / feature parts."""
+        return Layer(self.W[lo:hi].contiguous(), torch.zeros_like(self.b), self.W.device)
+
+
+class WeightStore:
+    """Device-side weight set keyed by the reference's layer names ('sa1/conv0', 'fp1/conv_1', 'voting2', ...)."""
+
+    def __init__(self, weights, device="cuda", eps=1e-5, precision=PRECISION_TENSOR):
+        self.device = torch.device(device)
+        self.precision = precision
+        self.eps = eps
+        self._raw = weights
+        self._layers = {}
+
+    def layer(self, name):
+        if name not in self._layers:
+            W, b = fold_bn(self._raw, name, self.eps)
+            self._layers[name] = Layer(W, b, self.device)
+        return self._layers[name]
+
+    def derived(self, key, make):
+        if key not in self._layers:
+            self._layers[key] = make()
+        return self._layers[key]
+
+
+def linear(x, layer, act, precision, residual=None, out_f16=False):
+    """rows x cin -> rows x cout through vnb_linear.  Returns fp32 (or fp16 when out_f16)."""
+    rows, cin = x.shape
+    assert cin == layer.cin
+    if out_f16:
+        out = torch.empty((rows, layer.cout), dtype=torch.float16, device=x.device)
+        o32, o16 = None, out
+    else:
+        out = torch.empty((rows, layer.cout), dtype=torch.float32, device=x.device)
+        o32, o16 = out, None
+    check(lib.vnb_linear(rows, cin, layer.cout, dptr(x, torch.float32, "in"), dptr(layer.W),
+                         dptr(layer.img) if precision == PRECISION_TENSOR else None, dptr(layer.b),
+                         dptr(residual, torch.float32, "residual"), 1 if act else 0, dptr(o32), dptr(o16),
+                         int(precision), stream_ptr()))
+    return out
+
+
+def sa_group_mlp_max(xyz, points, new_xyz, idx, layers, precision, store=None, scope=None):
+    """Fused grouping + 3-layer shared MLP + max-pool (utils.py:49-55,120-132)."""
+    b, n, _ = xyz.shape
+    c = points.shape[2]
+    m, ns = idx.shape[1], idx.shape[2]
+    l1, l2, l3 = layers
+    out = torch.empty((b, m, l3.cout), dtype=torch.float32, device=xyz.device)
+    q = None
+    w1_img = w2_img = w3_img = None
+    if precision == PRECISION_TENSOR:
+        w2_img, w3_img = l2.img, l3.img
+        if c >= HOIST_MIN_C:
+            # layer 1 hoisted through the gather: q = feat @ W1[3:] + b1, once per source point, fp16
+            lf = store.derived(scope + "/conv0:feat", lambda: Layer(l1.W[3:].contiguous(), l1.b, l1.W.device))
+            q = linear(points.reshape(b * n, c), lf, act=False, precision=precision, out_f16=True)
+        else:
+            w1_img = l1.img
+    check(lib.vnb_sa_group_mlp_max(b, n, c, m, ns, dptr(xyz, torch.float32, "xyz"), dptr(points, torch.float32, "points"),
+                                   dptr(new_xyz, torch.float32, "new_xyz"), dptr(idx, torch.int32, "idx"), l1.cout,
+                                   l2.cout, l3.cout, dptr(l1.W), dptr(l1.b), dptr(l2.W), dptr(l2.b), dptr(l3.W),
+                                   dptr(l3.b), dptr(w1_img), dptr(w2_img), dptr(w3_img), dptr(q), dptr(out),
+                                   int(precision), stream_ptr()))
+    return out
+
+
+def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_all, scope, bn=True, pooling="max",
+                       knn=False, use_xyz=True, use_nchw=False, sample_xyz=None, *, weights):
+    """PointNet Set Abstraction module — signature of /root/reference/utils.py:93-94 plus the `weights` store.
+    Returns (new_xyz (B,npoint,3), new_points (B,npoint,mlp[-1] or mlp2[-1]), idx (B,npoint,nsample))."""
+    if group_all or knn or pooling != "max" or not use_xyz or points is None or not bn:
+        raise NotImplementedError("only the configuration VoteNet uses is on the B200 hot path: group_all=False, "
+                                  "knn=False, pooling='max', use_xyz=True, bn=True, points given (SURVEY.md §2.1)")
+    if len(mlp) != 3:
+        raise NotImplementedError("pointnet_sa_module: the fused kernel implements the 3-layer shared MLP VoteNet uses")
+    prec = weights.precision
+    fps_idx = tf_sampling.farthest_point_sample(npoint, sample_xyz if sample_xyz is not None else xyz)  # utils.py:42-45
+    new_xyz = tf_sampling.gather_point(xyz, fps_idx)
+    idx, _ = tf_grouping.query_ball_point(radius, nsample, xyz, new_xyz)                                 # utils.py:49
+    layers = [weights.layer(f"{scope}/conv{i}") for i in range(3)]
+    for l, co in zip(layers, mlp):
+        assert l.cout == co, f"{scope}: weight set does not match mlp={mlp}"
+    new_points = sa_group_mlp_max(xyz, points, new_xyz, idx, layers, prec, weights, scope)               # :50-55,120-132
+    if mlp2 is not None:                                                                                  # :149-155
+        b, m, c = new_points.shape
+        h = new_points.reshape(b * m, c)
+        for i in range(len(mlp2)):
+            h = linear(h, weights.layer(f"{scope}/conv_post_{i}"), act=i < len(mlp2) - 1, precision=prec)
+        new_points = h.reshape(b, m, -1)
+    return new_xyz, new_points, idx
+
+
+def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, scope, bn=True, *, weights):
+    """PointNet Feature Propagation module — signature of /root/reference/utils.py:266 plus the `weights` store."""
+    if not bn:
+        raise NotImplementedError("bn=False is not on the VoteNet path")
+    prec = weights.precision
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    c2 = points2.shape[2]
+    c1 = points1.shape[2] if points1 is not None else 0
+    dist, idx = tf_interpolate.three_nn(xyz1, xyz2)                                            # utils.py:278
+    cat = torch.empty((b * n, c2 + c1), dtype=torch.float32, device=xyz1.device)
+    check(lib.vnb_fp_interpolate_concat(b, n, m, c1, c2, dptr(dist), dptr(idx), dptr(points1, torch.float32, "points1"),
+                                        dptr(points2, torch.float32, "points2"), dptr(cat), stream_ptr()))  # :279-286
+    h = cat
+    for i in range(len(mlp)):                                                                  # :290-292
+        h = linear(h, weights.layer(f"{scope}/conv_{i}"), act=True, precision=prec)
+    return h.reshape(b, n, -1)
