@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — clouds/s of the full VoteNet inference forward (BASELINE.json configs[3]: backbone + vote module +
+proposal head + 3-D NMS, batch 8 x 20 000 points (xyz + height) per GPU) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of 8 synthetic SUN-RGB-D-shaped clouds per rank (weak scaling;
+at N>1 one NCCL all-gather of the per-rank detection records + the global merge are inside the step).
+Prints ONE JSON line (rank 0).  --impl reference times the CPU oracle (the reference's algorithms restated, see
+oracle/) on the host cores instead — the only other place besides cpu_baseline where oracle/ is executed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CLOUDS_PER_RANK = 8
+METRIC = "clouds/sec (20k pts, B=8) full VoteNet fwd"
+UNIT = "clouds/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU arm: the oracle restatement of the reference's path on the box's host cores, all threads it can use."""
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import dense as odense
+    from votenet_b200 import synth
+    from votenet_b200.config import VoteNetConfig
+    from votenet_b200.weights import make_synthetic_weights
+
+    cfg = VoteNetConfig()
+    w = make_synthetic_weights(cfg, 0)
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(1)
+    clouds = [synth.synthetic_cloud(i, cfg.num_points) for i in range(CLOUDS_PER_RANK)]
+
+    def one(i):
+        x = clouds[i % len(clouds)][None]
+        odense.votenet_forward(x, synth.height_feature(x), w, cfg, synth.CLASS_MEAN_SIZE)
+
+    t0 = time.time(); one(0); t1 = time.time() - t0
+    workers = min(cores, CLOUDS_PER_RANK)
+    # A step of this arm is a bounded sample of the batch: ONE of its 8 clouds through the full forward on one host
+    # thread; `workers` steps run concurrently so every host core is busy (the reference's CPU ops are single-threaded).
+    per_step = 1
+    with ThreadPoolExecutor(workers) as ex:
+        list(ex.map(one, range(max(args.warmup, workers))))
+        t0 = time.time()
+        list(ex.map(one, range(args.steps)))
+        dt = time.time() - t0
+    value = per_step * args.steps / dt
+    sample = (f"1 of {CLOUDS_PER_RANK} clouds per step (full forward incl. NMS, 20000 pts), {workers} steps in flight on "
+              f"{workers} host threads; single-thread latency {t1:.2f} s/cloud")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[3]: full VoteNet fwd, 8 clouds x 20000 pts (xyz+height), CPU oracle of the reference path"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(cfg, w, budget_s=20.0):
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import dense as odense
+    from votenet_b200 import synth
+
+    cores = len(os.sched_getaffinity(0))
+    workers = min(cores, CLOUDS_PER_RANK)
+    torch.set_num_threads(1)
+    clouds = [synth.synthetic_cloud(i, cfg.num_points)[None] for i in range(workers)]
+
+    def one(i):
+        odense.votenet_forward(clouds[i], synth.height_feature(clouds[i]), w, cfg, synth.CLASS_MEAN_SIZE)
+
+    t0 = time.time(); one(0); t1 = time.time() - t0
+    rounds = max(1, int(budget_s / max(t1, 1e-3) / 1.5))
+    rounds = min(rounds, 4)
+    with ThreadPoolExecutor(workers) as ex:
+        t0 = time.time()
+        for _ in range(rounds):
+            list(ex.map(one, range(workers)))
+        dt = time.time() - t0
+    torch.set_num_threads(cores)
+    return {"value": workers * rounds / dt, "unit": UNIT, "cores": workers, "kind": "port",
+            "sample": f"{workers * rounds} clouds of the same workload ({rounds} rounds x {workers} threads, 1 cloud per thread; "
+                      f"single-thread latency {t1:.2f} s/cloud)"}
+
+
+def kernel_table(eng, cfg, peaks, flush):
+    """Per-kernel device time (CUDA events on the launching stream, L2 flushed before each launch) and roofline
+    fraction from ALGORITHMIC bytes / flops (SURVEY.md §8(d) per-cloud figures x batch)."""
+    from votenet_b200._lib import check, dptr, lib, stream_ptr
+
+    B = eng.B
+    s = eng.slots[0]
+    st = torch.cuda.current_stream()
+
+    def t(fn, it=5):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(it):
+            flush.zero_()
+            a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+            a.record(st); fn(); b.record(st); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    rows = []
+    src = s.xyz
+    c = cfg.feature_dim
+    feat = s.feat
+    for li, l in enumerate(s.lv):
+        sa = cfg.sa[li]
+        ms = t(lambda: check(lib.vnb_farthest_point_sample(B, l.n, l.m, dptr(src), dptr(l.fps), stream_ptr())))
+        byt = B * (l.m - 1) * l.n * 16
+        rows.append(dict(kernel=f"fps_sa{li + 1}", ms=ms, bound="hbm(streaming-equivalent; on-chip kernel)", algo_bytes=byt,
+                         achieved=byt / ms / 1e6, peak=peaks["hbm"], unit="GB/s"))
+        ms = t(lambda: check(lib.vnb_query_ball_point(B, l.n, l.m, float(sa.radius), 64, dptr(src), dptr(l.xyz), dptr(l.idx),
+                                                      dptr(l.cnt), stream_ptr())))
+        byt = B * (l.n * 12 + l.m * 12 + l.m * 256 + l.m * 4)
+        rows.append(dict(kernel=f"ball_query_sa{li + 1}", ms=ms, bound="hbm", algo_bytes=byt, achieved=byt / ms / 1e6,
+                         peak=peaks["hbm"], unit="GB/s"))
+        ms = t(lambda: eng._sa(li, src, feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, st))
+        cin = 3 + c
+        fl = 0
+        for co in sa.mlp:
+            fl += cin * co; cin = co
+        fl = 2.0 * B * l.m * 64 * fl
+        rows.append(dict(kernel=f"sa{li + 1}_group_mlp_max", ms=ms, bound="tensor", algo_flops=fl, achieved=fl / ms / 1e9,
+                         peak=peaks["tc_burst"], unit="TFLOP/s"))
+        src, feat, c = l.xyz, l.feat, sa.mlp[-1]
+    for r in rows:
+        r["frac"] = r["achieved"] / r["peak"]
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", type=int, default=1)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    assert world == args.gpus or world == 1 and args.gpus == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from votenet_b200 import synth
+    from votenet_b200._lib import lib
+    from votenet_b200.config import VoteNetConfig
+    from votenet_b200.dist import all_gather_records, merge_gathered, shard_range
+    from votenet_b200.engine import Engine
+    from votenet_b200.weights import make_synthetic_weights
+
+    peaks = _peaks()
+    cfg = VoteNetConfig()  # BASELINE.json: 20 000 points, (xyz + height)
+    B, N = CLOUDS_PER_RANK, cfg.num_points
+    w = make_synthetic_weights(cfg, 0)
+    eng = Engine(cfg, w, B, device=dev, precision=args.precision, use_graph=not args.no_graph)
+
+    # ---- synthetic inputs: this rank's clouds; a ring of RING device-resident batches (164 MB > the 126 MB L2) so that
+    #      a step's inputs are never L2-resident from an earlier step
+    ids = list(shard_range(rank, world, B))
+    base = np.stack([synth.synthetic_cloud(i, N) for i in ids], 0)
+    RING = 64
+    ring_xyz, ring_feat = [], []
+    bx = torch.as_tensor(base, device=dev)
+    for r in range(RING):
+        a = 2 * np.pi * r / RING
+        rot = torch.tensor([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], dtype=torch.float32, device=dev)
+        x = (bx @ rot.T).contiguous() if r else bx.clone()
+        ring_xyz.append(x)
+        ring_feat.append((synth.FLOOR_Y - x[..., 1:2]).contiguous())
+    HR = 4
+    host_xyz = [ring_xyz[r].cpu().pin_memory() for r in range(HR)]
+    host_feat = [ring_feat[r].cpu().pin_memory() for r in range(HR)]
+    host_out = [torch.empty((eng.record_nbytes,), dtype=torch.uint8).pin_memory() for _ in range(HR)]
+    h2d = host_xyz[0].numel() * 4 + host_feat[0].numel() * 4
+    d2h = eng.record_nbytes
+
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    ctl = torch.cuda.current_stream(dev)
+
+    def step_device(i):
+        st = streams[i % 2]
+        rec = eng.infer_device(ring_xyz[i % RING], ring_feat[i % RING], stream=st)
+        if world > 1:
+            with torch.cuda.stream(st):
+                g = all_gather_records(rec.buf, world)
+                merge_gathered(g, B, cfg.proposal.npoint)
+
+    def step_host(i):
+        st = streams[i % 2]
+        eng.infer_host(host_xyz[i % HR], host_feat[i % HR], host_out[i % HR], stream=st)
+        if world > 1:
+            with torch.cuda.stream(st):
+                g = all_gather_records(eng.slots[(eng._step - 1) % len(eng.slots)].rec.buf, world)
+                merge_gathered(g, B, cfg.proposal.npoint)
+
+    def timed(step_fn, K, W):
+        for i in range(W):
+            step_fn(i)
+        for st in streams:
+            ctl.wait_stream(st)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        n0 = lib.vnb_launch_count()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        t0 = time.time()
+        e0.record(ctl)
+        for st in streams:
+            st.wait_event(e0)
+        for i in range(K):
+            step_fn(W + i)
+        for st in streams:
+            ctl.wait_stream(st)
+        e1.record(ctl)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        wall = time.time() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, wall, int(lib.vnb_launch_count() - n0)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, wall_dev, _ = timed(step_device, args.steps, args.warmup)
+    sampler.stop_flag.set()
+    ms_e2e, wall_e2e, _ = timed(step_host, args.steps, args.warmup)
+    lpf = eng.launches_per_forward or 0
+    launches = lpf * args.steps + (args.steps if world > 1 else 0)
+
+    value = world * B * args.steps / (ms_dev / 1e3)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+        ktab = kernel_table(eng, cfg, peaks, flush)
+        dom = max(ktab, key=lambda r: r["ms"])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom["kernel"])
+        roof = {"kernel": dom["kernel"], "bound": "hbm" if dom["unit"] == "GB/s" else "tensor", "achieved": dom["achieved"],
+                "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic,
+                "peak_source": peaks["src"], "ms_per_launch": dom["ms"],
+                "note": "FPS is an on-chip (register/DSMEM) kernel: achieved = streaming-equivalent bytes (m-1)*n*16 B per "
+                        "cloud / time, so it may exceed the HBM peak" if dom["kernel"].startswith("fps") else ""}
+        cpu = None if args.no_cpu_baseline else cpu_baseline(cfg, w)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 operands / f32 accumulate (tcgen05); f32 geometry; int32 indices" if args.precision == 1 else "f32",
+                "data": "synthetic",
+                "config": {"workload": "configs[3]: full VoteNet fwd (4 SA + 2 FP + vote + proposal + decode + 3D-NMS), "
+                                       f"{B} clouds x {N} pts (xyz+height) per GPU", "clouds_per_gpu": B, "points": N,
+                           "parallelism": f"dp{world} (clouds sharded, 1 all-gather of detections)" if world > 1 else "single GPU",
+                           "l2": f"inputs rotate over {RING} device-resident batches ({RING * h2d / 1e6:.0f} MB > 126 MB L2)",
+                           "pipelining": "2 steps in flight (2 workspaces, 2 streams): step i+1's FPS chain overlaps step i's MLP chain",
+                           "cuda_graph": not args.no_graph},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "launches_per_forward": lpf,
+                "roofline": roof, "kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in ktab],
+                "cpu_baseline": cpu, "clocks": sampler.summary(),
+                "wall_s": {"device_loop": wall_dev, "e2e_loop": wall_e2e}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,8 @@ extern "C" {
 
 int vnb_abi_version(void);
 const char* vnb_last_error(void);
+/* number of kernel launches this library has issued in this process (all threads); bench.py reports it */
+unsigned long long vnb_launch_count(void);
 
 /* ------------------------------------------------------------------ tf_ops/sampling ------------------- */
 
@@ -83,6 +85,14 @@ int vnb_three_interpolate(int b, int m, int c, int n, const float* points, const
 size_t vnb_nms3d_workspace_bytes(int b, int k);
 int vnb_nms3d(int b, int k, const float* bbox, const float* scores, const float* objectiveness, float iou_threshold,
               uint8_t* keep, int* out_idx, int* out_count, void* workspace, void* stream);
+
+/* Global ordering of NMS survivors across an all-gathered batch: `gathered` holds `world`
+ * records of `rank_stride` bytes; in each, scores (b,k) f32 sit at byte offset off_scores and keep (b,k) u8 at
+ * off_keep.  Writes rows (global_batch, box) with global_batch = rank*b + local, in descending score order (ties:
+ * ascending (global_batch, box)) and their number — the reference's (Nnms,2) output for the whole sharded batch
+ * (tf_nms3d.cpp:240-272). */
+int vnb_merge_detections(int world, int b, int k, const void* gathered, size_t rank_stride, size_t off_scores,
+                         size_t off_keep, int* out_idx, int* out_count, void* stream);
 
 /* ------------------------------------------------------------------ fused layers (boundary B) --------- */
 /* The dense arithmetic the reference delegates to TensorFlow/Tensorpack (Conv2D 1x1 + BN(EMA) + ReLU + reduce_max,

@@ -1,0 +1,152 @@
+"""GPU parity tests (`-m gpu`) of the dense layers: fp32 SIMT kernels to ~1e-5 and the tcgen05 tensor-core kernels
+(fp16 operands, fp32 accumulate) to the 1e-3 relative tolerance BASELINE.json states, against torch-CPU fp32 / the
+dense oracle on identical inputs."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import dense as D
+from oracle import ops as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 2e-5
+TOL_TC = 1e-3  # BASELINE.json: "within 1e-3 relative on the float MLP/interpolation outputs"
+
+
+def T(a, dev):
+    return torch.as_tensor(np.ascontiguousarray(a), device=dev)
+
+
+@pytest.mark.parametrize("rows,cin,cout,act,res", [(1000, 512, 256, True, False), (8192, 259, 256, True, False),
+                                                   (1024, 256, 259, False, True), (256, 128, 79, False, False),
+                                                   (4096, 128, 128, False, False), (5, 6, 64, True, False),
+                                                   (130, 16, 16, False, False), (129, 272, 272, True, True)])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_linear(cuda, rows, cin, cout, act, res, precision):
+    from votenet_b200.utils import Layer, linear
+
+    g = torch.Generator().manual_seed(rows + cin + cout)
+    x = torch.randn(rows, cin, generator=g)
+    W = torch.randn(cin, cout, generator=g) * (2.0 / cin) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    r = torch.randn(rows, cout, generator=g) if res else None
+    ref = x.double() @ W.double() + b.double()
+    if act:
+        ref = torch.relu(ref)
+    if res:
+        ref = ref + r.double()
+    layer = Layer(W, b, cuda)
+    got = linear(x.to(cuda), layer, act, precision, residual=r.to(cuda) if res else None)
+    torch.cuda.synchronize()
+    assert got.shape == (rows, cout)
+    e = rel_err(got.cpu().numpy(), ref.numpy())
+    assert e < (TOL_FP32 if precision == 0 else TOL_TC), f"rel err {e:.3e}"
+    if precision == 1:  # fp16 output path (used for the hoisted layer-1 pre-GEMM)
+        got16 = linear(x.to(cuda), layer, act, 1, residual=r.to(cuda) if res else None, out_f16=True)
+        assert got16.dtype == torch.float16
+        assert rel_err(got16.float().cpu().numpy(), ref.numpy()) < 2e-3
+
+
+def _sa_case(b, n, m, c, mlp, r, seed):
+    rng = np.random.default_rng(seed)
+    xyz = rng.random((b, n, 3), dtype=np.float32)
+    feat = rng.standard_normal((b, n, c)).astype(np.float32)
+    fps = O.farthest_point_sample(m, xyz)
+    new_xyz = O.gather_point(xyz, fps)
+    idx, _ = O.query_ball_point(r, 64, xyz, new_xyz)
+    g = torch.Generator().manual_seed(seed)
+    w = {}
+    cin = 3 + c
+    for i, co in enumerate(mlp):
+        w[f"s/conv{i}/W"] = torch.randn(cin, co, generator=g) * (2.0 / cin) ** 0.5
+        w[f"s/conv{i}/b"] = torch.randn(co, generator=g) * 0.05
+        w[f"s/conv{i}/bn/gamma"] = torch.rand(co, generator=g) * 0.4 + 0.8
+        w[f"s/conv{i}/bn/beta"] = torch.randn(co, generator=g) * 0.05
+        w[f"s/conv{i}/bn/mean/EMA"] = torch.randn(co, generator=g) * 0.05
+        w[f"s/conv{i}/bn/variance/EMA"] = torch.rand(co, generator=g) * 0.4 + 0.8
+        cin = co
+    # oracle: grouped tensor -> conv/BN/ReLU x3 -> max   (utils.py:50-55,120-132)
+    grouped = np.concatenate([O.group_point(xyz, idx) - new_xyz[:, :, None, :], O.group_point(feat, idx)], -1)
+    h = torch.as_tensor(grouped)
+    for i in range(3):
+        h = D.dense_layer(h, w, f"s/conv{i}")
+    ref = h.max(dim=2).values
+    return xyz, feat, new_xyz, idx, w, ref
+
+
+@pytest.mark.parametrize("b,n,m,c,mlp,r", [(2, 3000, 256, 1, (64, 64, 128), 0.15), (1, 2000, 128, 3, (64, 64, 128), 0.2),
+                                           (2, 1024, 128, 128, (128, 128, 256), 0.25), (1, 512, 64, 256, (128, 128, 256), 0.4),
+                                           (2, 1024, 64, 256, (128, 128, 128), 0.3)])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_sa_group_mlp_max(cuda, b, n, m, c, mlp, r, precision):
+    from votenet_b200.utils import WeightStore, sa_group_mlp_max
+
+    xyz, feat, new_xyz, idx, w, ref = _sa_case(b, n, m, c, mlp, r, seed=b * 1000 + n + c)
+    store = WeightStore(w, device=cuda, precision=precision)
+    layers = [store.layer(f"s/conv{i}") for i in range(3)]
+    got = sa_group_mlp_max(T(xyz, cuda), T(feat, cuda), T(new_xyz, cuda), T(idx, cuda), layers, precision, store, "s")
+    torch.cuda.synchronize()
+    e = rel_err(got.cpu().numpy(), ref.numpy())
+    assert e < (TOL_FP32 if precision == 0 else TOL_TC), f"rel err {e:.3e}"
+
+
+def test_fp_module_and_helpers(cuda):
+    from votenet_b200._lib import check, dptr, lib, stream_ptr
+    from votenet_b200.utils import WeightStore, pointnet_fp_module
+
+    rng = np.random.default_rng(77)
+    b, n, m, c1, c2 = 2, 512, 256, 256, 256
+    xyz1 = rng.random((b, n, 3), dtype=np.float32); xyz2 = rng.random((b, m, 3), dtype=np.float32)
+    p1 = rng.standard_normal((b, n, c1)).astype(np.float32); p2 = rng.standard_normal((b, m, c2)).astype(np.float32)
+    g = torch.Generator().manual_seed(5)
+    w = {}
+    cin = c1 + c2
+    for i, co in enumerate((256, 256)):
+        w[f"fp/conv_{i}/W"] = torch.randn(cin, co, generator=g) * (2.0 / cin) ** 0.5
+        w[f"fp/conv_{i}/b"] = torch.randn(co, generator=g) * 0.05
+        w[f"fp/conv_{i}/bn/gamma"] = torch.rand(co, generator=g) * 0.4 + 0.8
+        w[f"fp/conv_{i}/bn/beta"] = torch.randn(co, generator=g) * 0.05
+        w[f"fp/conv_{i}/bn/mean/EMA"] = torch.randn(co, generator=g) * 0.05
+        w[f"fp/conv_{i}/bn/variance/EMA"] = torch.rand(co, generator=g) * 0.4 + 0.8
+        cin = co
+    ref, ex = D.pointnet_fp_module(torch.as_tensor(xyz1), torch.as_tensor(xyz2), torch.as_tensor(p1), torch.as_tensor(p2),
+                                   (256, 256), "fp", w)
+    for precision, tol in ((0, TOL_FP32), (1, TOL_TC)):
+        store = WeightStore(w, device=cuda, precision=precision)
+        got = pointnet_fp_module(T(xyz1, cuda), T(xyz2, cuda), T(p1, cuda), T(p2, cuda), [256, 256], "fp", weights=store)
+        torch.cuda.synchronize()
+        assert rel_err(got.cpu().numpy(), ref.numpy()) < tol
+    # interpolate+concat front half alone: float-exact up to the 1/d weights (1e-6)
+    cat = torch.empty((b * n, c1 + c2), device=cuda)
+    td, ti, tp1, tp2 = T(ex["dist"].numpy(), cuda), T(ex["idx"], cuda), T(p1, cuda), T(p2, cuda)  # keep alive
+    check(lib.vnb_fp_interpolate_concat(b, n, m, c1, c2, dptr(td), dptr(ti), dptr(tp1), dptr(tp2), dptr(cat), stream_ptr()))
+    torch.cuda.synchronize()
+    want = np.concatenate([ex["interpolated"].numpy(), p1], -1).reshape(b * n, -1)
+    assert np.abs(cat.cpu().numpy() - want).max() < 1e-5
+    # concat2 / split2 round trip
+    a = torch.randn(100, 3, device=cuda); bb = torch.randn(100, 256, device=cuda)
+    o = torch.empty(100, 259, device=cuda)
+    check(lib.vnb_concat2(100, 3, 256, dptr(a), dptr(bb), dptr(o), stream_ptr()))
+    assert torch.equal(o, torch.cat([a, bb], 1))
+    a2 = torch.empty_like(a); b2 = torch.empty_like(bb)
+    check(lib.vnb_split2(100, 3, 256, dptr(o), dptr(a2), dptr(b2), stream_ptr()))
+    assert torch.equal(a2, a) and torch.equal(b2, bb)
+
+
+def test_decode_boxes(cuda):
+    from votenet_b200 import synth
+    from votenet_b200.model import decode_boxes
+
+    rng = np.random.default_rng(8)
+    b, k = 3, 256
+    pxyz = (rng.random((b, k, 3), dtype=np.float32) * 6 - 3).astype(np.float32)
+    pout = rng.standard_normal((b, k, 79)).astype(np.float32)
+    ref = D.decode_boxes(torch.as_tensor(pxyz), torch.as_tensor(pout), synth.CLASS_MEAN_SIZE)
+    bboxes, scores, obj, cls = decode_boxes(T(pxyz, cuda), T(pout, cuda), T(synth.CLASS_MEAN_SIZE, cuda))
+    torch.cuda.synchronize()
+    assert np.abs(bboxes.cpu().numpy() - ref["bboxes"].numpy()).max() < 2e-5
+    assert np.array_equal(scores.cpu().numpy(), ref["scores"].numpy())
+    assert np.array_equal(obj.cpu().numpy(), ref["objectness"].numpy())
+    assert np.array_equal(cls.cpu().numpy(), ref["class_scores"].numpy())

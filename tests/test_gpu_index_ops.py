@@ -1,0 +1,202 @@
+"""GPU parity tests (`-m gpu`) of the index / byte ops through the C ABI against the CPU oracle: bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_boxes
+from helpers import golden, make_golden
+from oracle import ops as O
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a, dev):
+    return torch.as_tensor(np.ascontiguousarray(a), device=dev)
+
+
+# ------------------------------------------------------------------------------------------------ FPS
+@pytest.mark.parametrize("n,m", [(1, 1), (2, 2), (33, 7), (512, 128), (513, 64), (1024, 256), (2048, 1024), (3000, 64),
+                                 (4096, 300), (5000, 200), (8192, 64), (20000, 256), (20480, 128)])
+def test_fps_matches_oracle(cuda, n, m):
+    from votenet_b200.tf_sampling import farthest_point_sample
+
+    rng = np.random.default_rng(n * 31 + m)
+    x = rng.random((3, n, 3), dtype=np.float32) * 4 - 2
+    got = farthest_point_sample(m, T(x, cuda)).cpu().numpy()
+    assert got.dtype == np.int32 and got.shape == (3, m)
+    assert np.array_equal(got, O.farthest_point_sample(m, x))
+
+
+def test_fps_tie_rule_and_duplicates(cuda):
+    from votenet_b200.tf_sampling import farthest_point_sample
+
+    x = np.zeros((2, 700, 3), np.float32)
+    x[0, 600] = (1, 0, 0); x[0, 100] = (1, 0, 0)          # 600 mod 512 = 88 < 100 -> 600 wins
+    x[1, 612] = (1, 0, 0); x[1, 100] = (1, 0, 0)          # same slot -> lower k wins
+    got = farthest_point_sample(5, T(x, cuda)).cpu().numpy()
+    assert np.array_equal(got, O.farthest_point_sample(5, x))
+    assert got[0, 1] == 600 and got[1, 1] == 100
+    # lattice cloud: massive exact ties in every round
+    rng = np.random.default_rng(0)
+    lat = (rng.integers(0, 6, (2, 3000, 3)) / 4).astype(np.float32)
+    assert np.array_equal(farthest_point_sample(400, T(lat, cuda)).cpu().numpy(), O.farthest_point_sample(400, lat))
+
+
+def test_fps_golden_and_full_size(cuda):
+    from votenet_b200 import synth
+    from votenet_b200.tf_sampling import farthest_point_sample, gather_point
+
+    g = golden("oracle_fps_ballquery")
+    x = make_golden.fps_inputs()
+    assert np.array_equal(farthest_point_sample(64, T(x, cuda)).cpu().numpy(), g["fps"])
+    # BASELINE configs[1] shape: 20000 -> 2048 on a synthetic SUN-RGB-D-shaped cloud, then the nested levels
+    xyz = synth.synthetic_batch(0, 2, 20000)
+    f1 = farthest_point_sample(2048, T(xyz, cuda))
+    assert np.array_equal(f1.cpu().numpy(), O.farthest_point_sample(2048, xyz))
+    l1 = gather_point(T(xyz, cuda), f1)
+    assert np.array_equal(l1.cpu().numpy(), O.gather_point(xyz, f1.cpu().numpy()))
+    f2 = farthest_point_sample(1024, l1).cpu().numpy()
+    assert np.array_equal(f2, np.tile(np.arange(1024, dtype=np.int32), (2, 1)))  # nested-FPS prefix property
+
+
+def test_fps_rejects_bad_arguments(cuda):
+    from votenet_b200.tf_sampling import farthest_point_sample
+
+    with pytest.raises(ValueError):
+        farthest_point_sample(0, torch.zeros(1, 8, 3, device=cuda))
+
+
+# ------------------------------------------------------------------------------------------------ ball query / group
+@pytest.mark.parametrize("n,m,r,ns", [(100, 10, 0.3, 8), (1000, 77, 0.15, 64), (4096, 512, 0.1, 32), (5000, 33, 0.5, 64),
+                                      (31, 31, 10.0, 64), (64, 3, 1e-3, 4)])
+def test_ball_query_matches_oracle(cuda, n, m, r, ns):
+    from votenet_b200.tf_grouping import query_ball_point
+
+    rng = np.random.default_rng(n + m)
+    x = rng.random((2, n, 3), dtype=np.float32)
+    q = x[:, rng.permutation(n)[:m]].copy()
+    idx, cnt = query_ball_point(r, ns, T(x, cuda), T(q, cuda))
+    ri, rc = O.query_ball_point(r, ns, x, q)
+    assert idx.dtype == torch.int32 and cnt.dtype == torch.int32
+    assert np.array_equal(cnt.cpu().numpy(), rc)
+    assert np.array_equal(idx.cpu().numpy(), ri)
+
+
+def test_ball_query_boundary_and_empty(cuda):
+    from votenet_b200.tf_grouping import query_ball_point
+
+    # points exactly ON the sphere (d == r in float): the predicate is strict '<' on sqrtf(d2)
+    x = np.zeros((1, 64, 3), np.float32)
+    x[0, :, 0] = np.linspace(0, 0.63, 64, dtype=np.float32)
+    q = np.zeros((1, 1, 3), np.float32)
+    for r in (0.2, 0.25, 0.30000001, 0.1, 0.05):
+        i0, c0 = O.query_ball_point(r, 16, x, q)
+        i1, c1 = query_ball_point(r, 16, T(x, cuda), T(q, cuda))
+        assert np.array_equal(c1.cpu().numpy(), c0) and np.array_equal(i1.cpu().numpy(), i0)
+    # empty ball: count 0, row never written (reference leaves it uninitialised; wrapper zero-fills)
+    far = np.full((1, 1, 3), 9.0, np.float32)
+    i1, c1 = query_ball_point(0.1, 8, T(x, cuda), T(far, cuda))
+    assert int(c1[0, 0]) == 0 and (i1 == 0).all()
+    with pytest.raises(ValueError):
+        query_ball_point(-1.0, 8, T(x, cuda), T(q, cuda))
+
+
+def test_ball_query_full_size_and_golden(cuda):
+    from votenet_b200 import synth
+    from votenet_b200.tf_grouping import group_point, query_ball_point
+
+    g = golden("oracle_fps_ballquery")
+    x = make_golden.fps_inputs()
+    nx = O.gather_point(x, g["fps"])
+    idx, cnt = query_ball_point(0.12, 16, T(x, cuda), T(nx, cuda))
+    assert np.array_equal(idx.cpu().numpy(), g["ball_idx"]) and np.array_equal(cnt.cpu().numpy(), g["ball_cnt"])
+    xyz = synth.synthetic_batch(5, 2, 20000)
+    f = O.farthest_point_sample(1024, xyz)
+    nx = O.gather_point(xyz, f)
+    idx, cnt = query_ball_point(0.2, 64, T(xyz, cuda), T(nx, cuda))
+    ri, rc = O.query_ball_point(0.2, 64, xyz, nx)
+    assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(cnt.cpu().numpy(), rc)
+    h = synth.height_feature(xyz)
+    gp = group_point(T(h, cuda), idx)
+    assert np.array_equal(gp.cpu().numpy(), O.group_point(h, ri))
+    gx = group_point(T(xyz, cuda), idx)
+    assert np.array_equal(gx.cpu().numpy(), O.group_point(xyz, ri))
+
+
+# ------------------------------------------------------------------------------------------------ three_nn / interpolate
+def test_interpolate_config1_golden(cuda):
+    """BASELINE.json configs[0] against the vectors produced by the reference's own tf_interpolate.cpp."""
+    from votenet_b200.tf_interpolate import three_interpolate, three_nn
+
+    g = golden("ref_interpolate_config1")
+    xyz1, xyz2, pts = make_golden.interp_inputs()
+    dist, idx = three_nn(T(xyz1, cuda), T(xyz2, cuda))
+    assert np.array_equal(idx.cpu().numpy(), g["idx"])
+    assert np.array_equal(dist.cpu().numpy(), g["dist"])
+    w = make_golden.fp_weights(g["dist"])
+    out = three_interpolate(T(pts, cuda), idx, T(w, cuda)).cpu().numpy()
+    assert np.array_equal(out[:, ::32], g["out_rows"])
+
+
+@pytest.mark.parametrize("n,m,c", [(512, 256, 256), (1024, 512, 256), (10, 2, 5), (7, 1, 3), (300, 1500, 16)])
+def test_three_nn_interpolate_matches_oracle(cuda, n, m, c):
+    from votenet_b200.tf_interpolate import three_interpolate, three_nn
+
+    rng = np.random.default_rng(n + m + c)
+    xyz1 = rng.random((2, n, 3), dtype=np.float32)
+    xyz2 = rng.random((2, m, 3), dtype=np.float32)
+    if n == 300:  # lattice -> exact ties
+        xyz1 = np.round(xyz1 * 4) / 4; xyz2 = np.round(xyz2 * 4) / 4
+    d0, i0 = O.three_nn(xyz1, xyz2)
+    d1, i1 = three_nn(T(xyz1, cuda), T(xyz2, cuda))
+    assert np.array_equal(i1.cpu().numpy(), i0)
+    assert np.array_equal(d1.cpu().numpy(), d0)
+    pts = rng.standard_normal((2, m, c)).astype(np.float32)
+    w = rng.random((2, n, 3), dtype=np.float32)
+    assert np.array_equal(three_interpolate(T(pts, cuda), i1, T(w, cuda)).cpu().numpy(), O.three_interpolate(pts, i0, w))
+
+
+# ------------------------------------------------------------------------------------------------ NMS
+@pytest.mark.parametrize("name", ["ref_nms_random", "ref_nms_degenerate", "ref_nms_thr0"])
+def test_nms_golden(cuda, name):
+    """Against outputs of the reference's own tf_nms3d.cpp (tests/golden/make_golden.py)."""
+    from votenet_b200.tf_nms3d import NMS3D
+
+    g = golden(name)
+    boxes, scores, obj = make_golden.nms_inputs(int(g["seed"]), int(g["b"]), int(g["k"]), bool(g["degenerate"]))
+    sel = NMS3D(T(boxes, cuda), T(scores, cuda), T(obj, cuda), float(g["thr"])).cpu().numpy()
+    assert np.array_equal(sel, g["selected"])
+
+
+@pytest.mark.parametrize("seed,b,k,deg,thr", [(0, 8, 256, False, 0.25), (1, 3, 100, False, 0.1), (2, 2, 256, True, 0.25),
+                                              (3, 1, 33, False, 0.0), (4, 2, 64, False, 1.0), (5, 1, 1, False, 0.25),
+                                              (6, 4, 300, False, 0.25)])
+def test_nms_matches_oracle(cuda, seed, b, k, deg, thr):
+    from votenet_b200.tf_nms3d import NMS3D, nms3d_raw
+
+    rng = np.random.default_rng(900 + seed)
+    boxes = random_boxes(rng, b, k, spread=2.0, degenerate=deg)
+    scores = rng.standard_normal((b, k)).astype(np.float32)
+    obj = rng.standard_normal((b, k, 2)).astype(np.float32)
+    ref_idx, ref_keep = O.NMS3D(boxes, scores, obj, thr, return_keep=True)
+    keep, idx, count = nms3d_raw(T(boxes, cuda), T(scores, cuda), T(obj, cuda), thr)
+    assert np.array_equal(keep.cpu().numpy().astype(bool), ref_keep)
+    assert int(count.item()) == len(ref_idx)
+    assert np.array_equal(NMS3D(T(boxes, cuda), T(scores, cuda), T(obj, cuda), thr).cpu().numpy(), ref_idx)
+
+
+def test_nms_demo_and_errors(cuda):
+    from test_oracle import _demo_boxes
+    from votenet_b200.tf_nms3d import NMS3D
+
+    bb = _demo_boxes()
+    scores = np.array([[0.5, 0.6]], "float32")
+    obj = np.array([[[0.3, 0.7], [0.4, 0.6]]], "float32")
+    assert NMS3D(T(bb, cuda), T(scores, cuda), T(obj, cuda), 0.5).cpu().tolist() == [[0, 1], [0, 0]]
+    assert NMS3D(T(bb, cuda), T(scores, cuda), T(obj, cuda), 0.49).cpu().tolist() == [[0, 1]]
+    none = np.array([[[0.9, 0.1], [0.9, 0.1]]], "float32")  # nothing passes objectness -> empty output
+    assert NMS3D(T(bb, cuda), T(scores, cuda), T(none, cuda), 0.5).shape == (0, 2)
+    with pytest.raises(ValueError):
+        NMS3D(T(bb, cuda), T(scores, cuda), T(obj, cuda), 1.5)
+    with pytest.raises(ValueError):
+        NMS3D(T(bb[:, :, :4], cuda), T(scores, cuda), T(obj, cuda), 0.5)

@@ -23,6 +23,8 @@ _i, _f, _p, _sz = C.c_int, C.c_float, C.c_void_p, C.c_size_t
 _SIGS = {
     "vnb_abi_version": ([], _i),
     "vnb_last_error": ([], C.c_char_p),
+    "vnb_launch_count": ([], C.c_ulonglong),
+    "vnb_merge_detections": ([_i, _i, _i, _p, _sz, _sz, _sz, _p, _p, _p], _i),
     "vnb_farthest_point_sample": ([_i, _i, _i, _p, _p, _p], _i),
     "vnb_gather_point": ([_i, _i, _i, _p, _p, _p, _p], _i),
     "vnb_query_ball_point": ([_i, _i, _i, _f, _i, _p, _p, _p, _p, _p], _i),

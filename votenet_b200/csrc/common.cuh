@@ -19,8 +19,11 @@ int set_err(int code, const char* fmt, ...);
     if (!(cond)) return ::vnb::set_err(VNB_ERR_INVALID, __VA_ARGS__); \
   } while (0)
 
-// after a launch: report (and clear) any launch error
+void count_launch();
+
+// after a launch: count it; report (and clear) any launch error
 static inline int check_launch(const char* what) {
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(VNB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return VNB_OK;

@@ -195,6 +195,31 @@ __global__ void nms_emit_kernel(int total, int k, const float* __restrict__ scor
   out_idx[rank * 2 + 1] = e % k;
 }
 
+// K4': the same ordering over an all-gathered set of per-rank records (strided fields).
+__global__ void merge_detections_kernel(int world, int per_rank, int k, const char* __restrict__ gathered,
+                                        size_t rank_stride, size_t off_scores, size_t off_keep,
+                                        int* __restrict__ out_idx, int* __restrict__ out_count) {
+  const int total = world * per_rank;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int re = e / per_rank, le = e % per_rank;
+  const uint8_t ke = *reinterpret_cast<const uint8_t*>(gathered + re * rank_stride + off_keep + le);
+  if (!ke) return;
+  const float se = *reinterpret_cast<const float*>(gathered + re * rank_stride + off_scores + (size_t)le * 4);
+  int rank = 0;
+  for (int r = 0; r < world; ++r) {
+    const float* sc = reinterpret_cast<const float*>(gathered + r * rank_stride + off_scores);
+    const uint8_t* kp = reinterpret_cast<const uint8_t*>(gathered + r * rank_stride + off_keep);
+    for (int f = 0; f < per_rank; ++f) {
+      const int ge = r * per_rank + f;
+      rank += (kp[f] && (sc[f] > se || (sc[f] == se && ge < e))) ? 1 : 0;
+    }
+  }
+  out_idx[rank * 2 + 0] = e / k;
+  out_idx[rank * 2 + 1] = e % k;
+  atomicAdd(out_count, 1);
+}
+
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace vnb
@@ -235,4 +260,16 @@ extern "C" int vnb_nms3d(int b, int k, const float* bbox, const float* scores, c
   const int total = b * k;
   nms_emit_kernel<<<(total + 127) / 128, 128, 0, st>>>(total, k, scores, keep, out_idx);
   return check_launch("nms3d emit");
+}
+
+extern "C" int vnb_merge_detections(int world, int b, int k, const void* gathered, size_t rank_stride,
+                                    size_t off_scores, size_t off_keep, int* out_idx, int* out_count, void* stream) {
+  VNB_REQUIRE(world > 0 && b >= 0 && k >= 0, "merge_detections: bad shape");
+  cudaStream_t st = as_stream(stream);
+  VNB_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int), st));
+  const int total = world * b * k;
+  if (total == 0) return VNB_OK;
+  merge_detections_kernel<<<(total + 127) / 128, 128, 0, st>>>(world, b * k, k, static_cast<const char*>(gathered),
+                                                             rank_stride, off_scores, off_keep, out_idx, out_count);
+  return check_launch("merge_detections");
 }

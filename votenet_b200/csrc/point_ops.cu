@@ -8,6 +8,8 @@
 namespace vnb {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 char* err_buf() { return g_err; }
 int set_err(int code, const char* fmt, ...) {
   va_list ap;
@@ -287,6 +289,7 @@ extern "C" {
 
 int vnb_abi_version(void) { return VNB_ABI_VERSION; }
 const char* vnb_last_error(void) { return err_buf(); }
+unsigned long long vnb_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int vnb_gather_point(int b, int n, int m, const float* inp, const int* idx, float* out, void* stream) {
   VNB_REQUIRE(b >= 0 && n > 0 && m >= 0, "GatherPoint expects (batch_size,num_points,3) inp shape / (batch_size,num_result) idx shape");
