@@ -20,6 +20,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# several steps are in flight on independent streams: give every stream its own hardware queue (default is 8)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -198,6 +200,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=int, default=1)
+    ap.add_argument("--inflight", type=int, default=4, help="steps in flight (independent workspaces + streams)")
+    ap.add_argument("--fps-cluster", type=int, default=None, help="tuning: CTAs per FPS cluster")
+    ap.add_argument("--fps-threads", type=int, default=None, help="tuning: threads per FPS CTA (256/512/1024)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -222,11 +227,16 @@ def main():
     from votenet_b200.engine import Engine
     from votenet_b200.weights import make_synthetic_weights
 
+    from votenet_b200._lib import check as _check
+    if args.fps_cluster is not None:
+        _check(lib.vnb_set_tuning(b"fps_cluster", args.fps_cluster))
+    if args.fps_threads is not None:
+        _check(lib.vnb_set_tuning(b"fps_threads", args.fps_threads))
     peaks = _peaks()
     cfg = VoteNetConfig()  # BASELINE.json: 20 000 points, (xyz + height)
     B, N = CLOUDS_PER_RANK, cfg.num_points
     w = make_synthetic_weights(cfg, 0)
-    eng = Engine(cfg, w, B, device=dev, precision=args.precision, use_graph=not args.no_graph)
+    eng = Engine(cfg, w, B, device=dev, precision=args.precision, use_graph=not args.no_graph, slots=args.inflight)
 
     # ---- synthetic inputs: this rank's clouds; a ring of RING device-resident batches (164 MB > the 126 MB L2) so that
     #      a step's inputs are never L2-resident from an earlier step
@@ -241,18 +251,19 @@ def main():
         x = (bx @ rot.T).contiguous() if r else bx.clone()
         ring_xyz.append(x)
         ring_feat.append((synth.FLOOR_Y - x[..., 1:2]).contiguous())
-    HR = 4
+    HR = max(4, args.inflight)
     host_xyz = [ring_xyz[r].cpu().pin_memory() for r in range(HR)]
     host_feat = [ring_feat[r].cpu().pin_memory() for r in range(HR)]
     host_out = [torch.empty((eng.record_nbytes,), dtype=torch.uint8).pin_memory() for _ in range(HR)]
     h2d = host_xyz[0].numel() * 4 + host_feat[0].numel() * 4
     d2h = eng.record_nbytes
 
-    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    NS = args.inflight
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     ctl = torch.cuda.current_stream(dev)
 
     def step_device(i):
-        st = streams[i % 2]
+        st = streams[i % NS]
         rec = eng.infer_device(ring_xyz[i % RING], ring_feat[i % RING], stream=st)
         if world > 1:
             with torch.cuda.stream(st):
@@ -260,7 +271,7 @@ def main():
                 merge_gathered(g, B, cfg.proposal.npoint)
 
     def step_host(i):
-        st = streams[i % 2]
+        st = streams[i % NS]
         eng.infer_host(host_xyz[i % HR], host_feat[i % HR], host_out[i % HR], stream=st)
         if world > 1:
             with torch.cuda.stream(st):
@@ -332,7 +343,7 @@ def main():
                                        f"{B} clouds x {N} pts (xyz+height) per GPU", "clouds_per_gpu": B, "points": N,
                            "parallelism": f"dp{world} (clouds sharded, 1 all-gather of detections)" if world > 1 else "single GPU",
                            "l2": f"inputs rotate over {RING} device-resident batches ({RING * h2d / 1e6:.0f} MB > 126 MB L2)",
-                           "pipelining": "2 steps in flight (2 workspaces, 2 streams): step i+1's FPS chain overlaps step i's MLP chain",
+                           "pipelining": f"{NS} steps in flight ({NS} workspaces, {NS} streams): later steps' FPS chains overlap earlier steps' MLP chains",
                            "cuda_graph": not args.no_graph},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},

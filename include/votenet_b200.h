@@ -32,6 +32,12 @@ int vnb_abi_version(void);
 const char* vnb_last_error(void);
 /* number of kernel launches this library has issued in this process (all threads); bench.py reports it */
 unsigned long long vnb_launch_count(void);
+/* Tuning knobs for experiments (defaults are what bench.py uses): "fps_mode" 0 = cluster barrier / 1 = tagged slots,
+ * "fps_cluster" 0 = auto or a forced cluster size, "ball_query_variant" 0 = exhaustive scan / 1 = grid + bitmap. */
+int vnb_set_tuning(const char* key, int value);
+/* Debugging aid: when given a device buffer of 16 x 8 int64, the next cluster-FPS launches (256 threads x 10 points)
+ * accumulate per-phase cycle counts of warp 0 of every CTA of cloud 0 into it; NULL switches it off. */
+int vnb_debug_fps_profile(void* device_buffer_16x8_i64);
 
 /* ------------------------------------------------------------------ tf_ops/sampling ------------------- */
 
@@ -39,8 +45,17 @@ unsigned long long vnb_launch_count(void);
  * (op FarthestPointSample, tf_sampling.cpp:95-123; python farthest_point_sample(npoint, inp), tf_sampling.py:48-56)
  * xyz (b,n,3) f32 -> out_idx (b,m) i32.  Bit-identical index sequence to the reference kernel (tie rule included).
  * The reference's (32,n) `temp` scratch is not needed: the running min-distances live in registers.
- * Limits: 1 <= n <= 65536; m >= 1 (m <= 0 is VNB_ERR_INVALID like the op's npoint>0 check, tf_sampling.cpp:99). */
+ * Limits: 1 <= n <= 32768; m >= 1 (m <= 0 is VNB_ERR_INVALID like the op's npoint>0 check, tf_sampling.cpp:99). */
 int vnb_farthest_point_sample(int b, int n, int m, const float* xyz, int* out_idx, void* stream);
+
+/* Same result as vnb_farthest_point_sample, for inputs that are themselves FPS-ordered (the nested levels sa2..sa4 and
+ * the proposal module run FPS on the previous level's FPS output, utils.py:43-45, model.py:89-93): the output is then
+ * the identity prefix 0..m-1 unless exact float ties reorder it.  This entry point PROVES that per cloud with a fully
+ * parallel check and runs the sequential sampler only for clouds where the proof fails; it is correct (bit-identical
+ * to vnb_farthest_point_sample) for ANY input, just not faster when the input is not FPS-ordered.
+ * workspace: vnb_fps_nested_workspace_bytes(b, m) bytes. */
+size_t vnb_fps_nested_workspace_bytes(int b, int m);
+int vnb_farthest_point_sample_nested(int b, int n, int m, const float* xyz, int* out_idx, void* workspace, void* stream);
 
 /* gatherpointLauncher(b,n,m,inp,idx,out)                        tf_sampling_g.cu:206-208
  * inp (b,n,3), idx (b,m) -> out (b,m,3). */
@@ -54,6 +69,13 @@ int vnb_gather_point(int b, int n, int m, const float* inp, const int* idx, floa
  * exactly like the reference (tf_grouping_g.cu:14-34).  radius > 0, nsample > 0 (tf_grouping.cpp:71,74). */
 int vnb_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
                          int* idx, int* pts_cnt, void* stream);
+
+/* Same outputs, bit for bit, computed through a uniform grid + per-query index bitmap instead of the exhaustive scan
+ * (see csrc/ball_query_grid.cu).  workspace: vnb_query_ball_point_workspace_bytes(b,n) bytes; with workspace == NULL
+ * (or n < 4096) this is vnb_query_ball_point. */
+size_t vnb_query_ball_point_workspace_bytes(int b, int n);
+int vnb_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
+                            int* idx, int* pts_cnt, void* workspace, void* stream);
 
 /* groupPointLauncher(b,n,c,m,nsample,points,idx,out)            tf_grouping_g.cu:133-136
  * points (b,n,c), idx (b,m,nsample) -> out (b,m,nsample,c). */

@@ -150,3 +150,26 @@ def test_decode_boxes(cuda):
     assert np.array_equal(scores.cpu().numpy(), ref["scores"].numpy())
     assert np.array_equal(obj.cpu().numpy(), ref["objectness"].numpy())
     assert np.array_equal(cls.cpu().numpy(), ref["class_scores"].numpy())
+
+
+def test_sa_kernel_variants_agree(cuda):
+    """The warp-specialised pipelined kernel (sa_ws.cu) and the single-role kernel perform the same arithmetic in the same
+    order: bit-identical outputs.  Also exercises many tiles per CTA (ring of barriers wraps many times)."""
+    from votenet_b200._lib import check, lib
+    from votenet_b200.utils import WeightStore, sa_group_mlp_max
+
+    for (b, n, m, c, mlp, r) in [(8, 2048, 1024, 128, (128, 128, 256), 0.2), (3, 1024, 254, 256, (128, 128, 128), 0.3)]:
+        xyz, feat, new_xyz, idx, w, ref = _sa_case(b, n, m, c, mlp, r, seed=77 + m)
+        store = WeightStore(w, device=cuda, precision=1)
+        layers = [store.layer(f"s/conv{i}") for i in range(3)]
+        args = (T(xyz, cuda), T(feat, cuda), T(new_xyz, cuda), T(idx, cuda), layers, 1, store, "s")
+        outs = []
+        try:
+            for v in (0, 1):
+                check(lib.vnb_set_tuning(b"sa_variant", v))
+                outs.append(sa_group_mlp_max(*args))
+                torch.cuda.synchronize()
+        finally:
+            check(lib.vnb_set_tuning(b"sa_variant", 1))
+        assert torch.equal(outs[0], outs[1])
+        assert rel_err(outs[1].cpu().numpy(), ref.numpy()) < TOL_TC

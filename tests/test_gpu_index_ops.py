@@ -200,3 +200,94 @@ def test_nms_demo_and_errors(cuda):
         NMS3D(T(bb, cuda), T(scores, cuda), T(obj, cuda), 1.5)
     with pytest.raises(ValueError):
         NMS3D(T(bb[:, :, :4], cuda), T(scores, cuda), T(obj, cuda), 0.5)
+
+
+# ------------------------------------------------------------------------------------------------ nested FPS / grid ball query
+@pytest.mark.parametrize("kind", ["fps_ordered", "random", "lattice", "ordered_with_duplicates", "m_gt_n"])
+def test_fps_nested_is_bit_identical(cuda, kind):
+    """vnb_farthest_point_sample_nested == vnb_farthest_point_sample == oracle, whether the parallel identity-prefix
+    proof succeeds (FPS-ordered input) or not (anything else -> per-cloud sequential fallback)."""
+    from votenet_b200.tf_sampling import farthest_point_sample, farthest_point_sample_nested
+
+    rng = np.random.default_rng(5)
+    b, n, m = 4, 2048, 1024
+    x = rng.random((b, n, 3), dtype=np.float32)
+    if kind in ("fps_ordered", "ordered_with_duplicates"):
+        big = rng.random((b, 9000, 3), dtype=np.float32)
+        x = O.gather_point(big, O.farthest_point_sample(n, big))
+        if kind == "ordered_with_duplicates":
+            x[1, 700] = x[1, 3]          # exact duplicate -> zero distance, ties
+            x[2, 1000:1100] = x[2, 5]
+    elif kind == "lattice":
+        x = (rng.integers(0, 9, (b, n, 3)) / 8).astype(np.float32)
+    elif kind == "m_gt_n":
+        n, m = 300, 400
+        x = x[:, :n].copy()
+    want = O.farthest_point_sample(m, x)
+    tx = T(x, cuda)
+    got = farthest_point_sample_nested(m, tx).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert np.array_equal(farthest_point_sample(m, tx).cpu().numpy(), want)
+    if kind == "fps_ordered":
+        assert np.array_equal(want, np.tile(np.arange(m, dtype=np.int32), (b, 1)))
+    # mixed batch: only cloud 0 is FPS-ordered, the others fall back
+    if kind == "random":
+        big = rng.random((1, 9000, 3), dtype=np.float32)
+        x[0] = O.gather_point(big, O.farthest_point_sample(n, big))[0]
+        assert np.array_equal(farthest_point_sample_nested(m, T(x, cuda)).cpu().numpy(), O.farthest_point_sample(m, x))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("thr,cl", [(256, 0), (256, 4), (256, 8), (256, 16), (512, 2), (512, 4), (1024, 2), (1024, 4)])
+def test_fps_exchange_variants(cuda, mode, thr, cl):
+    """Both cluster-exchange protocols and every cluster size give the reference's sequence."""
+    from votenet_b200._lib import check, lib
+    from votenet_b200 import synth
+    from votenet_b200.tf_sampling import farthest_point_sample
+
+    xyz = synth.synthetic_batch(3, 2, 20000)
+    want = O.farthest_point_sample(700, xyz)
+    lat = (np.random.default_rng(1).integers(0, 6, (2, 6000, 3)) / 4).astype(np.float32)
+    want_lat = O.farthest_point_sample(300, lat)
+    try:
+        check(lib.vnb_set_tuning(b"fps_mode", mode)); check(lib.vnb_set_tuning(b"fps_cluster", cl))
+        check(lib.vnb_set_tuning(b"fps_threads", thr))
+        assert np.array_equal(farthest_point_sample(700, T(xyz, cuda)).cpu().numpy(), want)
+        assert np.array_equal(farthest_point_sample(300, T(lat, cuda)).cpu().numpy(), want_lat)
+    finally:
+        check(lib.vnb_set_tuning(b"fps_mode", 1)); check(lib.vnb_set_tuning(b"fps_cluster", 0))
+        check(lib.vnb_set_tuning(b"fps_threads", 256))
+
+
+@pytest.mark.parametrize("n,m,r,ns,kind", [(20000, 2048, 0.2, 64, "room"), (20000, 300, 0.05, 16, "room"), (8192, 512, 0.4, 64, "uniform"),
+                                           (5000, 100, 3.0, 64, "uniform"), (6000, 200, 0.3, 32, "outside"), (4096, 64, 1e-4, 8, "uniform"),
+                                           (7000, 256, 0.25, 64, "flat")])
+def test_ball_query_grid_matches_scan(cuda, n, m, r, ns, kind):
+    """The grid + bitmap kernel (n >= 4096) is bit-identical to the exhaustive scan and to the oracle, including queries
+    outside the source bounding box, degenerate (planar) clouds, huge and tiny radii."""
+    from votenet_b200 import synth
+    from votenet_b200._lib import check, lib
+    from votenet_b200.tf_grouping import query_ball_point
+
+    rng = np.random.default_rng(n + m)
+    b = 2
+    if kind == "room":
+        x = synth.synthetic_batch(9, b, n)
+    else:
+        x = rng.random((b, n, 3), dtype=np.float32) * 4
+        if kind == "flat":
+            x[..., 1] = 0.5
+    q = x[:, rng.permutation(n)[:m]].copy()
+    if kind == "outside":
+        q = q + rng.normal(0, 0.5, q.shape).astype(np.float32)
+        q[:, :10] += 50.0
+    want_i, want_c = O.query_ball_point(r, ns, x, q)
+    gi, gc = query_ball_point(r, ns, T(x, cuda), T(q, cuda))
+    assert np.array_equal(gc.cpu().numpy(), want_c)
+    assert np.array_equal(gi.cpu().numpy(), want_i)
+    try:
+        check(lib.vnb_set_tuning(b"ball_query_variant", 0))
+        si, sc = query_ball_point(r, ns, T(x, cuda), T(q, cuda))
+    finally:
+        check(lib.vnb_set_tuning(b"ball_query_variant", 1))
+    assert torch.equal(si, gi) and torch.equal(sc, gc)

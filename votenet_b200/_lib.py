@@ -24,6 +24,12 @@ _SIGS = {
     "vnb_abi_version": ([], _i),
     "vnb_last_error": ([], C.c_char_p),
     "vnb_launch_count": ([], C.c_ulonglong),
+    "vnb_set_tuning": ([C.c_char_p, _i], _i),
+    "vnb_debug_fps_profile": ([_p], _i),
+    "vnb_fps_nested_workspace_bytes": ([_i, _i], _sz),
+    "vnb_farthest_point_sample_nested": ([_i, _i, _i, _p, _p, _p, _p], _i),
+    "vnb_query_ball_point_workspace_bytes": ([_i, _i], _sz),
+    "vnb_query_ball_point_ws": ([_i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p], _i),
     "vnb_merge_detections": ([_i, _i, _i, _p, _sz, _sz, _sz, _p, _p, _p], _i),
     "vnb_farthest_point_sample": ([_i, _i, _i, _p, _p, _p], _i),
     "vnb_gather_point": ([_i, _i, _i, _p, _p, _p, _p], _i),

@@ -21,9 +21,12 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 SOURCES = {
     "point_ops.cu": [],
     "fps.cu": [],
+    "ball_query_grid.cu": [],
     "nms3d.cu": ["-fmad=false"],
     "mlp_simt.cu": [],
     "mlp_tc.cu": [],
+    "sa_ws.cu": [],
+    "linear_tc.cu": [],
 }
 
 

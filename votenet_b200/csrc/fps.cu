@@ -4,23 +4,40 @@
 // one 512-thread block per cloud, running min-distances `temp` in GLOBAL memory re-read and conditionally
 // re-written every round, a 9-level shared-memory tree with 10 block barriers per round.
 //
-// Here: the cloud is spread over the registers of a cluster of CTAs (CL CTAs x T threads x P points/thread), the
-// running min-distance of every point stays in a register for all m-1 rounds, and one round costs
-//   scan (P fused distance updates per thread)  ->  2x redux.sync arg-max inside each warp
-//   ->  each warp's champion {key, xyz} is pushed into EVERY CTA's shared memory with st.async (DSMEM) that
-//       completes a transaction barrier (mbarrier) there  ->  every warp waits on its own CTA's barrier and reduces
-//       the CL*W champions locally.
-// No __syncthreads, no cluster barrier and no global-memory round trip inside the loop.
+// Here the cloud is spread over the REGISTERS of a cluster of CL CTAs x T threads x P points/thread; the running
+// min-distance of every point stays in a register for all m-1 rounds.  One round =
+//   scan (P fused distance updates per thread, first-max per thread)
+//   -> 2x redux.sync arg-max inside each warp -> champions to shared memory, ONE __syncthreads
+//   -> every warp reduces the W warp champions (2x redux.sync) to the CTA champion
+//   -> (CL > 1) warp 0 pushes {key, xyz} of the CTA champion into EVERY CTA of the cluster through distributed shared
+//      memory (one lane per destination), synchronised either by a cluster barrier (mode 0) or by tagged slots that the
+//      receivers poll in their own shared memory (mode 1); every warp then reduces the CL champions locally.
+// No global-memory traffic inside the loop except the 4-byte result of each round.
 //
 // Bit-exactness.  d = fmaf(dz,dz,fmaf(dx,dx,dy*dy)) with d* = point - last (the contraction nvcc emits for the
 // reference), temp = min(d, temp) from 1e38f.  The reference's winner is the candidate with maximal
-// temp, ties to the smallest (k mod 512), then the smallest k (per-thread strict '>' over k = t, t+512, ...; tree
-// keeps the lower slot).  All temps are >= +0 so their bit patterns order as unsigned integers; the 64-bit key
-//   (temp_bits << 32) | (0xFFFFFFFF - (((k & 511) << 20) | (k >> 9)))          (n <= 2^20)
-// reduced with an integer max reproduces exactly that rule under ANY reduction topology.
+// temp, ties to the smallest (k mod 512), then the smallest k (per-thread strict '>' over k = t, t+512, ...; the tree
+// keeps the lower slot).  All temps are >= +0 so their bit patterns order as unsigned integers; the key
+//   (temp_bits, 0x8000 | (0x7FFF - (((k & 511) << 6) | (k >> 9))))                (n <= 32768)
+// compared lexicographically and reduced with integer max reproduces exactly that rule under ANY reduction topology.
+// A thread owns points k = (i*CL + rank)*T + tid with CL*T a multiple of 512, so all its points share (k mod 512) and
+// its tie key decreases with i: "first strict maximum over i" is the reference's per-thread rule.
+//
+// Nested levels (SA2..SA4, proposal) run FPS on the previous level's FPS output, whose result is the identity prefix
+// 0..m-1 unless exact float ties reorder it.  vnb_farthest_point_sample_nested proves that per cloud
+// with a fully PARALLEL check (every round's arg-max condition is independent once the picks are hypothesised) and
+// only falls back to the sequential kernel for clouds where the proof fails — the output is always bit-identical.
 #include "common.cuh"
 
+#include <string_view>
+
 namespace vnb {
+
+extern int g_bq_variant;
+extern int g_sa_variant;
+int g_fps_mode = 1;   // 0: cluster barrier per round, 1: CTA champions in tagged slots + polling (default)
+int g_fps_cl = 0;     // 0: automatic cluster size, else forced (power of two <= 16)
+int g_fps_threads = 256;  // threads per CTA of the cluster kernel (256 / 512 / 1024)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -36,40 +53,21 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ void st_cluster_v2(uint32_t raddr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(raddr), "r"(a), "r"(b) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
+__device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr(p)) : "memory");
+  return v;
 }
-// bounded wait: a protocol bug traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-    if (spin > (1u << 24)) __trap();
-}
-// remote (DSMEM) stores that complete `bytes` on the destination CTA's mbarrier
-__device__ __forceinline__ void st_async_v2(uint32_t raddr, uint32_t a, uint32_t b, uint32_t rbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(raddr),
-               "r"(a), "r"(b), "r"(rbar)
-               : "memory");
-}
-__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
-                                            uint32_t rbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
-                   raddr),
-               "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar)
-               : "memory");
+__device__ __forceinline__ uint2 ld_volatile_v2(const void* p) {
+  uint2 v;
+  asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_addr(p)) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t redux_max(uint32_t v) {
   uint32_t r;
@@ -77,30 +75,33 @@ __device__ __forceinline__ uint32_t redux_max(uint32_t v) {
   return r;
 }
 
-__device__ __forceinline__ uint32_t tie_key(int k) { return 0xFFFFFFFFu - ((((uint32_t)k & 511u) << 20) | ((uint32_t)k >> 9)); }
+// 16-bit tie key: bit 15 = valid, low 15 bits = 0x7FFF - (((k & 511) << 6) | (k >> 9)); larger wins.
+__device__ __forceinline__ uint32_t tie_key(int k) { return 0x8000u | (0x7FFFu - ((((uint32_t)k & 511u) << 6) | ((uint32_t)k >> 9))); }
 __device__ __forceinline__ int tie_key_to_index(uint32_t key) {
-  uint32_t t = 0xFFFFFFFFu - key;
-  return (int)(((t & 0xFFFFFu) << 9) | (t >> 20));
+  uint32_t t = 0x7FFFu - (key & 0x7FFFu);
+  return (int)((t >> 6) | ((t & 63u) << 9));
 }
 
-// T threads per CTA, P points per thread, CL CTAs per cluster (launch attribute); W = T/32 warps.
-template <int T, int P>
+// T threads per CTA, P points per thread, CL CTAs per cluster (launch attribute, CL*T % 512 == 0); W = T/32 warps.
+// MODE 0: cluster barrier per round; MODE 1: tagged slots, receivers poll their own shared memory.
+// `flags` (may be null): per-cloud "already done" flags — a cluster whose cloud is flagged exits immediately.
+template <int T, int P, int MODE, bool SP, bool PROF = false>
 __global__ void __launch_bounds__(T) fps_cluster_kernel(int n, int m, int CL, const float* __restrict__ xyz,
-                                                        int* __restrict__ out) {
+                                                        int* __restrict__ out, const int* __restrict__ flags,
+                                                        long long* __restrict__ prof = nullptr) {
   constexpr int W = T / 32;
-  constexpr int MAXCH = 16 * W;  // champions per round at the largest cluster size (16)
-  // per round parity: champion keys (8 B) and coordinates (16 B), one slot per (cta, warp) of the cluster
-  __shared__ __align__(16) uint2 s_key[2][MAXCH];
-  __shared__ __align__(16) float4 s_xyz[2][MAXCH];
-  __shared__ __align__(8) uint64_t s_bar[2];
-  extern __shared__ __align__(16) float4 s_pts[];  // [T*P] this CTA's points (x,y,z,-) for the champion's coordinates
+  __shared__ __align__(16) uint2 s_wkey[2][W];    // warp champions: {tie key, temp bits}
+  __shared__ int s_wslot[2][W];                   //                 their slot in s_pts
+  __shared__ __align__(16) uint4 s_xa[2][16];     // CTA champions of the cluster: {temp bits, tag<<16 | tie, x, y}
+  __shared__ __align__(16) uint2 s_xb[2][16];     //                               {z, tag}
+  extern __shared__ __align__(16) float4 s_pts[];  // [T*P] this CTA's points (x,y,z,-)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cluster_ctarank();
   const int cloud = blockIdx.x / CL;
+  if (flags != nullptr && flags[cloud] != 0) return;  // whole cluster takes the same branch
   const float* pc = xyz + (size_t)cloud * n * 3;
   int* oc = out + (size_t)cloud * m;
-  const int nch = CL * W;  // champions per round
 
   float px[P], py[P], pz[P], td[P];
 #pragma unroll
@@ -110,90 +111,187 @@ __global__ void __launch_bounds__(T) fps_cluster_kernel(int n, int m, int CL, co
       px[i] = pc[(size_t)k * 3 + 0];
       py[i] = pc[(size_t)k * 3 + 1];
       pz[i] = pc[(size_t)k * 3 + 2];
+      td[i] = 1e38f;  // tf_sampling_g.cu:118
     } else {
       px[i] = py[i] = pz[i] = 0.f;
+      td[i] = -1.f;  // padding: min(d,-1) stays -1 and never beats the strict '>' against best = -1
     }
-    td[i] = 1e38f;  // tf_sampling_g.cu:118
-    s_pts[i * T + tid] = make_float4(px[i], py[i], pz[i], 0.f);
+    if (SP) s_pts[i * T + tid] = make_float4(px[i], py[i], pz[i], 0.f);
   }
-  if (tid == 0) {
-    mbar_init(smem_addr(&s_bar[0]), 1);
-    mbar_init(smem_addr(&s_bar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // round r uses barrier r&1: arm round 1 and round 2 now, round r+2 right after round r completes
-    const uint32_t tx = (uint32_t)nch * 24u;
-    mbar_arrive_expect_tx(smem_addr(&s_bar[1]), tx);
-    mbar_arrive_expect_tx(smem_addr(&s_bar[0]), tx);
+  if (tid < 32) {
+    s_xa[0][tid & 15] = make_uint4(0, 0, 0, 0); s_xa[1][tid & 15] = make_uint4(0, 0, 0, 0);
+    s_xb[0][tid & 15] = make_uint2(0, 0); s_xb[1][tid & 15] = make_uint2(0, 0);
   }
   if (rank == 0 && tid == 0) oc[0] = 0;  // first sample is index 0 (:114-116)
   __syncthreads();
-  cluster_sync_all();  // every CTA's barriers are initialised before any remote st.async can land
+  if (CL > 1) cluster_sync_all();  // every CTA's slots are initialised before any remote store can land
 
   float lx = pc[0], ly = pc[1], lz = pc[2];  // coordinates of the last pick (index 0)
-  const uint32_t my_slot = rank * W + warp;
+  const uint32_t key0 = tie_key((int)rank * T + tid);   // tie key of this thread's point i = 0
+  const uint32_t kstep = (uint32_t)(CL * T) >> 9;       // it decreases by this much per i
 
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt0 = 0;  // PROF only: cycles per phase, warp 0 of every CTA
+#define FPS_TICK(i)                                 \
+  if (PROF) {                                       \
+    long long _t = clock64();                       \
+    pacc[i] += _t - pt0;                            \
+    pt0 = _t;                                       \
+  }
   for (int r = 1; r < m; ++r) {
     const int par = r & 1;
-    // ---- scan: update running min-distances, per-thread champion -------------------------------------------
-    uint32_t bhi = 0, blo = 0;
+    if (PROF) pt0 = clock64();
+    // ---- scan: update running min-distances; first strict maximum over i ------------------------------------
+    float best = -1.f;
     int bi = 0;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      int k = (i * CL + (int)rank) * T + tid;
       float d = d2_ref_gpu(px[i] - lx, py[i] - ly, pz[i] - lz);
       td[i] = fminf(d, td[i]);
-      uint32_t hi = __float_as_uint(td[i]);
-      uint32_t lo = tie_key(k);
-      bool valid = k < n;
-      bool better = valid && (hi > bhi || (hi == bhi && lo > blo));
-      if (better) { bhi = hi; blo = lo; bi = i; }
+      if (td[i] > best) { best = td[i]; bi = i; }
     }
-    // ---- warp arg-max: two redux.sync ---------------------------------------------------------------------
-    uint32_t whi = redux_max(bhi);
-    uint32_t wlo = redux_max(bhi == whi ? blo : 0u);
-    // the champion lane (unique: tie keys are unique per point; an all-invalid warp sends key 0 from lane 0)
-    bool champ = (bhi == whi) && (blo == wlo);
-    unsigned cm = __ballot_sync(0xffffffffu, champ);
+    FPS_TICK(0)  // scan
+    const bool has = best >= 0.f;
+    const uint32_t bhi = has ? __float_as_uint(best) : 0u;
+    const uint32_t blo = has ? key0 - (uint32_t)bi * kstep : 0u;
+    // ---- warp arg-max: two redux.sync -----------------------------------------------------------------------
+    const uint32_t whi = redux_max(bhi);
+    const uint32_t wlo = redux_max(bhi == whi ? blo : 0u);
+    const unsigned cm = __ballot_sync(0xffffffffu, bhi == whi && blo == wlo);
     if (lane == __ffs(cm) - 1) {
-      float4 c = s_pts[bi * T + tid];
-      const uint32_t kaddr = smem_addr(&s_key[par][my_slot]);
-      const uint32_t xaddr = smem_addr(&s_xyz[par][my_slot]);
-      const uint32_t baddr = smem_addr(&s_bar[par]);
-      for (int dst = 0; dst < CL; ++dst) {
-        uint32_t rb = mapa(baddr, dst);
-        st_async_v2(mapa(kaddr, dst), wlo, whi, rb);
-        st_async_v4(mapa(xaddr, dst), __float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(c.z), 0u, rb);
+      s_wkey[par][warp] = make_uint2(wlo, whi);
+      if (SP) s_wslot[par][warp] = bi * T + tid;
+    }
+    FPS_TICK(1)  // warp arg-max + shared store
+    __syncthreads();
+    FPS_TICK(2)  // block barrier
+    // ---- CTA champion (every warp computes it; no second barrier) -------------------------------------------
+    uint2 kv = lane < W ? s_wkey[par][lane] : make_uint2(0u, 0u);
+    uint32_t chi = redux_max(kv.y);
+    uint32_t clo = redux_max(kv.y == chi ? kv.x : 0u);
+    const unsigned wm = __ballot_sync(0xffffffffu, lane < W && kv.y == chi && kv.x == clo);
+    const int cw = __ffs(wm) - 1;  // the warp that owns the CTA champion
+    float4 cpt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (SP) cpt = s_pts[s_wslot[par][cw]];
+    FPS_TICK(3)  // CTA champion
+    if (CL > 1) {
+      // ---- cluster exchange: the champion's own warp pushes {key, xyz} to every CTA (one lane per destination) --
+      const uint32_t tag = (uint32_t)r & 0xFFFFu;
+      if (warp == cw) {
+        float sx = px[0], sy = py[0], sz = pz[0];  // coordinates straight from the champion lane's registers
+#pragma unroll
+        for (int i = 1; i < P; ++i)
+          if (bi == i) { sx = px[i]; sy = py[i]; sz = pz[i]; }
+        const int cl = __ffs(cm) - 1;
+        sx = __shfl_sync(0xffffffffu, sx, cl); sy = __shfl_sync(0xffffffffu, sy, cl); sz = __shfl_sync(0xffffffffu, sz, cl);
+        if (lane < CL) {
+          st_cluster_v4(mapa(smem_addr(&s_xa[par][rank]), lane), chi, (tag << 16) | clo, __float_as_uint(sx),
+                        __float_as_uint(sy));
+          st_cluster_v2(mapa(smem_addr(&s_xb[par][rank]), lane), __float_as_uint(sz), tag);
+        }
       }
+      FPS_TICK(4)  // remote stores issued (only the champion warp does work here)
+      uint4 a = make_uint4(0, 0, 0, 0);
+      uint2 bq = make_uint2(0, 0);
+      if (MODE == 0) {
+        cluster_sync_all();
+        if (lane < CL) { a = s_xa[par][lane]; bq = s_xb[par][lane]; }
+      } else {
+        if (lane < CL) {
+          uint32_t spin = 0;
+          do {
+            a = ld_volatile_v4(&s_xa[par][lane]);
+            bq = ld_volatile_v2(&s_xb[par][lane]);
+            if (++spin > (1u << 22)) __trap();  // protocol bug: trap instead of hanging the GPU
+          } while ((a.y >> 16) != tag || bq.y != tag);
+        }
+        __syncwarp();
+      }
+      FPS_TICK(5)  // wait for all CTA champions
+      const uint32_t ahi = lane < CL ? a.x : 0u, alo = lane < CL ? (a.y & 0xFFFFu) : 0u;
+      chi = redux_max(ahi);
+      clo = redux_max(ahi == chi ? alo : 0u);
+      const unsigned gm = __ballot_sync(0xffffffffu, lane < CL && ahi == chi && alo == clo);
+      const int src = __ffs(gm) - 1;
+      lx = __uint_as_float(__shfl_sync(0xffffffffu, a.z, src));
+      ly = __uint_as_float(__shfl_sync(0xffffffffu, a.w, src));
+      lz = __uint_as_float(__shfl_sync(0xffffffffu, bq.x, src));
+    } else {
+      lx = cpt.x; ly = cpt.y; lz = cpt.z;
     }
-    // ---- wait for all champions of this round to land in OUR shared memory ---------------------------------
-    const uint32_t parity = (uint32_t)(((r - 1) >> 1) & 1);
-    mbar_wait(smem_addr(&s_bar[par]), parity);
-    if (tid == 0 && r + 2 < m) mbar_arrive_expect_tx(smem_addr(&s_bar[par]), (uint32_t)nch * 24u);  // arm round r+2
-    // ---- every warp reduces the nch champions (identical result everywhere) ---------------------------------
-    uint32_t chi = 0, clo = 0;
-    int cs = 0;
-    for (int s = lane; s < nch; s += 32) {
-      uint2 kv = s_key[par][s];
-      if (kv.y > chi || (kv.y == chi && kv.x > clo)) { chi = kv.y; clo = kv.x; cs = s; }
-    }
-    uint32_t ghi = redux_max(chi);
-    uint32_t glo = redux_max(chi == ghi ? clo : 0u);
-    unsigned gm = __ballot_sync(0xffffffffu, chi == ghi && clo == glo);
-    int gs = __shfl_sync(0xffffffffu, cs, __ffs(gm) - 1);
-    float4 w = s_xyz[par][gs];
-    lx = w.x; ly = w.y; lz = w.z;
-    if (rank == 0 && tid == 0) oc[r] = tie_key_to_index(glo);
+    if (rank == 0 && tid == 0) oc[r] = tie_key_to_index(clo);
+    FPS_TICK(6)  // final reduce + broadcast
   }
-  cluster_sync_all();  // nobody exits while a peer may still write into its shared memory
+#undef FPS_TICK
+  if (PROF && prof != nullptr && warp == 0 && lane == 0 && cloud == 0)
+    for (int i = 0; i < 8; ++i) prof[rank * 8 + i] = pacc[i];
+  if (CL > 1) cluster_sync_all();  // nobody exits while a peer may still write into its shared memory
 }
 
-template <int T, int P>
-static int launch_fps(int b, int n, int m, int CL, const float* xyz, int* out, cudaStream_t st) {
+// ---------------------------------------------------------------------------------------------------------------------
+// Parallel proof that FPS(xyz, m) == (0, 1, ..., m-1).  With picks 0..j-1 hypothesised, the running min-distance of
+// point k at round j is T_j[k] = min_{i<j} d(k,i) (min is exact), and round j picks j iff
+//   (T_j[k], tie(k)) < (T_j[j], tie(j))  for every k != j.
+// Kernel A: R[j] = T_j[j] for j < m (thread j, loop over i < j; triangular, m^2/2 distance evaluations per cloud).
+// Kernel B: thread k walks i = 0..m-2 keeping its running min and checks round j = i+1 against R[j].
+// Induction over j makes the hypothesis true whenever all checks pass.
+constexpr int VT = 256;
+__global__ void __launch_bounds__(128) fps_prefix_r_kernel(int n, int m, const float* __restrict__ xyz,
+                                                           float* __restrict__ R /* (b,m) */) {
+  extern __shared__ float sv[];  // xyz of picks 0 .. jend-1
+  const int cloud = blockIdx.y;
+  const float* pc = xyz + (size_t)cloud * n * 3;
+  const int j0 = blockIdx.x * 128, jend = min(m, j0 + 128);
+  for (int t = threadIdx.x; t < jend * 3; t += 128) sv[t] = pc[t];
+  __syncthreads();
+  const int j = j0 + threadIdx.x;
+  if (j >= m) return;
+  const float x = sv[j * 3], y = sv[j * 3 + 1], z = sv[j * 3 + 2];
+  float t = 1e38f;
+  for (int i = 0; i < j; ++i) t = fminf(t, d2_ref_gpu(x - sv[i * 3], y - sv[i * 3 + 1], z - sv[i * 3 + 2]));
+  R[(size_t)cloud * m + j] = t;
+}
+
+__global__ void __launch_bounds__(VT) fps_prefix_verify_kernel(int n, int m, const float* __restrict__ xyz,
+                                                                const float* __restrict__ R,
+                                                                int* __restrict__ fail /* per cloud, pre-zeroed */) {
+  extern __shared__ float sv[];  // [m*3] xyz of the m hypothesised picks, [m] R
+  float* sx = sv;
+  float* sR = sv + (size_t)m * 3;
+  const int cloud = blockIdx.y;
+  const float* pc = xyz + (size_t)cloud * n * 3;
+  for (int t = threadIdx.x; t < m * 3; t += VT) sx[t] = pc[t];
+  for (int t = threadIdx.x; t < m; t += VT) sR[t] = R[(size_t)cloud * m + t];
+  __syncthreads();
+  const int k = blockIdx.x * VT + threadIdx.x;
+  if (k >= n) return;
+  const float x = pc[(size_t)k * 3], y = pc[(size_t)k * 3 + 1], z = pc[(size_t)k * 3 + 2];
+  const uint32_t tk = tie_key(k);
+  float t = 1e38f;
+  bool bad = false;
+  for (int i = 0; i + 1 < m; ++i) {  // after this iteration t == T_{i+1}[k]
+    t = fminf(t, d2_ref_gpu(x - sx[i * 3], y - sx[i * 3 + 1], z - sx[i * 3 + 2]));
+    const int j = i + 1;
+    const float rj = sR[j];
+    if (k != j && (t > rj || (t == rj && tk > tie_key(j)))) bad = true;
+  }
+  if (bad) atomicOr(&fail[cloud], 1);
+}
+
+__global__ void fps_identity_kernel(int b, int m, const int* __restrict__ fail, int* __restrict__ out, int* __restrict__ done) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < b) done[t] = fail[t] ? 0 : 1;
+  if (t >= b * m) return;
+  if (!fail[t / m]) out[t] = t % m;
+}
+
+template <int T, int P, int MODE, bool SP>
+static int launch_fps(int b, int n, int m, int CL, const float* xyz, int* out, const int* flags, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(b * CL));
   cfg.blockDim = dim3(T);
-  cfg.dynamicSmemBytes = (size_t)T * P * sizeof(float4);
-  VNB_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+  cfg.dynamicSmemBytes = SP ? (size_t)T * P * sizeof(float4) : 0;
+  VNB_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<T, P, MODE, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cfg.dynamicSmemBytes));
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -202,30 +300,139 @@ static int launch_fps(int b, int n, int m, int CL, const float* xyz, int* out, c
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (CL > 8) VNB_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<T, P>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  VNB_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<T, P>, n, m, CL, xyz, out));
+  if (CL > 8)
+    VNB_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<T, P, MODE, SP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  long long* noprof = nullptr;
+  VNB_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<T, P, MODE, SP>, n, m, CL, xyz, out, flags, noprof));
   return check_launch("farthest_point_sample");
+}
+
+long long* g_fps_prof = nullptr;  // debugging: device buffer of 16*8 cycle counters (vnb_debug_fps_profile)
+
+static int launch_fps_prof(int b, int n, int m, int CL, const float* xyz, int* out, cudaStream_t st) {
+  auto kern = fps_cluster_kernel<256, 10, 1, false, true>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(b * CL));
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const int* noflags = nullptr;
+  VNB_CUDA(cudaLaunchKernelEx(&cfg, kern, n, m, CL, xyz, out, noflags, g_fps_prof));
+  return check_launch("farthest_point_sample (profiled)");
+}
+
+template <int T, int P>
+static int launch_fps_mode(int b, int n, int m, int CL, const float* xyz, int* out, const int* flags, cudaStream_t st) {
+  if (g_fps_prof != nullptr && T == 256 && P == 10 && CL > 1 && CL <= 8 && flags == nullptr)
+    return launch_fps_prof(b, n, m, CL, xyz, out, st);
+  if (CL == 1) return launch_fps<T, P, 1, true>(b, n, m, CL, xyz, out, flags, st);
+  if (g_fps_mode == 0) return launch_fps<T, P, 0, false>(b, n, m, CL, xyz, out, flags, st);
+  return launch_fps<T, P, 1, false>(b, n, m, CL, xyz, out, flags, st);
+}
+
+template <int T>
+static int fps_dispatch_t(int b, int n, int m, int CL, const float* xyz, int* out, const int* flags, cudaStream_t st) {
+  const int per = (n + CL * T - 1) / (CL * T);  // points per thread needed
+  if (per <= 1) return launch_fps_mode<T, 1>(b, n, m, CL, xyz, out, flags, st);
+  if (per <= 2) return launch_fps_mode<T, 2>(b, n, m, CL, xyz, out, flags, st);
+  if (per <= 4) return launch_fps_mode<T, 4>(b, n, m, CL, xyz, out, flags, st);
+  if (per <= 5) return launch_fps_mode<T, 5>(b, n, m, CL, xyz, out, flags, st);
+  if (per <= 8) return launch_fps_mode<T, 8>(b, n, m, CL, xyz, out, flags, st);
+  if (per <= 10) return launch_fps_mode<T, 10>(b, n, m, CL, xyz, out, flags, st);
+  if constexpr (T <= 512) {
+    if (per <= 16) return launch_fps_mode<T, 16>(b, n, m, CL, xyz, out, flags, st);
+    if constexpr (T <= 256) {
+      if (per <= 20) return launch_fps_mode<T, 20>(b, n, m, CL, xyz, out, flags, st);
+    }
+  }
+  return set_err(VNB_ERR_INVALID, "farthest_point_sample: %d points per thread do not fit (cluster %d x %d threads)", per, CL, T);
+}
+
+// Geometry: T threads per CTA (g_fps_threads: 256 / 512 / 1024) x CL CTAs per cluster (g_fps_cl or automatic).  Few big
+// CTAs minimise the SM footprint of one call (better throughput when several calls overlap); many small CTAs minimise
+// the latency of one call.  CL*T must be a multiple of 512 (per-thread tie rule, see the header comment).
+static int fps_dispatch(int b, int n, int m, const float* xyz, int* out, const int* flags, cudaStream_t st) {
+  int T = g_fps_threads;
+  int CL = g_fps_cl;
+  if (n <= 2048 && CL <= 1) {  // small clouds: one CTA of 512 threads
+    T = 512; CL = 1;
+  } else {
+    if (T != 256 && T != 512 && T != 1024) T = 256;
+    const int pmax = T == 256 ? 20 : (T == 512 ? 16 : 10);
+    if (CL < 1) CL = 1;
+    if (T == 256 && CL < 2) CL = 2;
+    while (CL < 16 && (long long)CL * T * pmax < n) CL *= 2;
+    if (g_fps_cl == 0) {  // automatic: ~10 points per thread
+      while (CL < 8 && (long long)CL * T * 10 < n) CL *= 2;
+    }
+  }
+  if (T == 1024) return fps_dispatch_t<1024>(b, n, m, CL, xyz, out, flags, st);
+  if (T == 512) return fps_dispatch_t<512>(b, n, m, CL, xyz, out, flags, st);
+  return fps_dispatch_t<256>(b, n, m, CL, xyz, out, flags, st);
 }
 
 }  // namespace vnb
 
 using namespace vnb;
 
-extern "C" int vnb_farthest_point_sample(int b, int n, int m, const float* xyz, int* out_idx, void* stream) {
+extern "C" int vnb_set_tuning(const char* key, int value) {
+  std::string_view k(key);
+  if (k == "fps_mode") g_fps_mode = value;
+  else if (k == "fps_cluster") g_fps_cl = value;
+  else if (k == "fps_threads") g_fps_threads = value;
+  else if (k == "ball_query_variant") vnb::g_bq_variant = value;
+  else if (k == "sa_variant") vnb::g_sa_variant = value;
+  else return set_err(VNB_ERR_INVALID, "set_tuning: unknown key %s", key);
+  return VNB_OK;
+}
+
+// debugging aid (not part of the drop-in boundary): per-phase cycle counters of the cluster FPS kernel
+extern "C" int vnb_debug_fps_profile(void* device_buffer_16x8_i64) {
+  vnb::g_fps_prof = static_cast<long long*>(device_buffer_16x8_i64);
+  return VNB_OK;
+}
+
+static int fps_check_args(int b, int n, int m) {
   VNB_REQUIRE(m > 0, "FarthestPointSample expects positive npoint");                     // tf_sampling.cpp:99
   VNB_REQUIRE(b >= 0 && n >= 1, "FarthestPointSample expects (batch_size,num_points,3) inp shape");  // :105
-  VNB_REQUIRE(n <= 65536, "farthest_point_sample: n = %d exceeds the on-chip limit of 65536 points per cloud", n);
+  VNB_REQUIRE(n <= 32768, "farthest_point_sample: n = %d exceeds the on-chip limit of 32768 points per cloud", n);
+  return VNB_OK;
+}
+
+extern "C" int vnb_farthest_point_sample(int b, int n, int m, const float* xyz, int* out_idx, void* stream) {
+  if (int rc = fps_check_args(b, n, m)) return rc;
+  if (b == 0) return VNB_OK;
+  return fps_dispatch(b, n, m, xyz, out_idx, nullptr, as_stream(stream));
+}
+
+extern "C" size_t vnb_fps_nested_workspace_bytes(int b, int m) {
+  return (size_t)(b > 0 ? b : 1) * (2 * sizeof(int) + (size_t)(m > 0 ? m : 1) * sizeof(float)) + 256;
+}
+
+extern "C" int vnb_farthest_point_sample_nested(int b, int n, int m, const float* xyz, int* out_idx, void* workspace,
+                                                void* stream) {
+  if (int rc = fps_check_args(b, n, m)) return rc;
   if (b == 0) return VNB_OK;
   cudaStream_t st = as_stream(stream);
-  // choose (cluster size, points per thread) so that CL * 256 * P >= n with the least padding
-  constexpr int T = 256;
-  if (n <= T * 2) return launch_fps<T, 2>(b, n, m, 1, xyz, out_idx, st);
-  if (n <= T * 4) return launch_fps<T, 4>(b, n, m, 1, xyz, out_idx, st);
-  if (n <= T * 8) return launch_fps<T, 8>(b, n, m, 1, xyz, out_idx, st);
-  if (n <= 4 * T * 4) return launch_fps<T, 4>(b, n, m, 4, xyz, out_idx, st);
-  if (n <= 8 * T * 4) return launch_fps<T, 4>(b, n, m, 8, xyz, out_idx, st);
-  if (n <= 8 * T * 8) return launch_fps<T, 8>(b, n, m, 8, xyz, out_idx, st);
-  if (n <= 8 * T * 10) return launch_fps<T, 10>(b, n, m, 8, xyz, out_idx, st);
-  if (n <= 8 * T * 16) return launch_fps<T, 16>(b, n, m, 8, xyz, out_idx, st);
-  return launch_fps<T, 16>(b, n, m, 16, xyz, out_idx, st);
+  const size_t smem = (size_t)m * 4 * sizeof(float);
+  if (m > n || smem > 200 * 1024)  // the identity prefix needs m <= n; huge m does not fit the proof kernel
+    return fps_dispatch(b, n, m, xyz, out_idx, nullptr, st);
+  int* fail = static_cast<int*>(workspace);
+  int* done = fail + b;
+  float* R = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)b * 2 * sizeof(int) + 255) / 256) * 256);
+  VNB_CUDA(cudaMemsetAsync(fail, 0, sizeof(int) * (size_t)b, st));
+  VNB_CUDA(cudaFuncSetAttribute(fps_prefix_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)m * 12)));
+  fps_prefix_r_kernel<<<dim3((m + 127) / 128, b), 128, (size_t)m * 12, st>>>(n, m, xyz, R);
+  if (int rc = check_launch("fps prefix R")) return rc;
+  VNB_CUDA(cudaFuncSetAttribute(fps_prefix_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fps_prefix_verify_kernel<<<dim3((n + VT - 1) / VT, b), VT, smem, st>>>(n, m, xyz, R, fail);
+  if (int rc = check_launch("fps prefix proof")) return rc;
+  fps_identity_kernel<<<(b * m + 255) / 256, 256, 0, st>>>(b, m, fail, out_idx, done);
+  if (int rc = check_launch("fps identity")) return rc;
+  // sequential kernel for the clouds whose proof failed (clusters of proven clouds exit at once)
+  return fps_dispatch(b, n, m, xyz, out_idx, done, st);
 }

@@ -3,9 +3,7 @@
 //  * pack_weight_kernel   W (cin,cout) f32  ->  fp16 [n_pad][k_pad] K-major image, 128-byte swizzled, in panels of 64
 //                         k-columns: byte-for-byte what tcgen05.mma reads from shared memory, so a weight tile is
 //                         staged by ONE 1-D bulk copy (cp.async.bulk, the TMA engine) per panel — no tensor map.
-//  * linear_tc_kernel     out = act(in @ W + b) (+res): 128-row tiles, K streamed in 128-column chunks through a
-//                         2-stage ring (activations converted fp32->fp16 and swizzled by the CTA's threads, weights by
-//                         bulk copy), one thread issues tcgen05.mma, epilogue from TMEM.
+//  * linear_tc_kernel     (linear_tc.cu) out = act(in @ W + b) (+res).
 //  * sa_tc_kernel         pointnet_sa_module's group -> 3-layer shared MLP -> max-pool in ONE kernel (utils.py:49-55,
 //                         120-132): a tile is 2 centroids x 64 samples = 128 rows.  Layer-1 input rows are produced by
 //                         the CTA's threads straight from the irregular gather (never materialised in HBM); layer
@@ -29,6 +27,12 @@ int linear_simt(int rows, int cin, int cout, const float* in, const float* w, co
 int sa_simt(int b, int n, int c, int m, const float* xyz, const float* feat, const float* new_xyz, const int* idx,
             int c1, int c2, int c3, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
             const float* b3, float* out, cudaStream_t st);
+int sa_ws_dispatch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, int c1, int c2, int c3,
+                   const float* w1x, const float* b2, const float* b3, const void* w2_img, const void* w3_img,
+                   const void* q, float* out, cudaStream_t st);
+int linear_tc(int rows, int cin, int cout, const float* in, const void* w_img, const float* bias, const float* res,
+              int act, float* out_f32, void* out_f16, cudaStream_t st);  // linear_tc.cu
+int g_sa_variant = 1;  // 0: single-role kernel (sa_tc_kernel), 1: warp-specialised pipeline (sa_ws.cu) where available
 
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(int cin, int cout, int k_pad, int n_pad, const float* __restrict__ w,
@@ -44,129 +48,6 @@ __global__ void pack_weight_kernel(int cin, int cout, int k_pad, int n_pad, cons
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// linear: grid (ceil(rows/128), ceil(n_pad/128)); 128 threads.
-constexpr int LIN_THREADS = 128;
-constexpr int LIN_A_STAGE = 128 * 256;  // 128 rows x 128 k x 2 B
-constexpr int LIN_B_STAGE = 128 * 256;  // up to 128 n-rows x 128 k x 2 B
-constexpr int LIN_SMEM = 2 * (LIN_A_STAGE + LIN_B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
-
-__global__ void __launch_bounds__(LIN_THREADS) linear_tc_kernel(int rows, int cin, int cout, int k_pad, int n_pad,
-                                                                const float* __restrict__ in,
-                                                                const char* __restrict__ w_img,
-                                                                const float* __restrict__ bias,
-                                                                const float* __restrict__ res, int act,
-                                                                float* __restrict__ out_f32,
-                                                                __half* __restrict__ out_f16) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA[2] = {smem, smem + LIN_A_STAGE};
-  uint8_t* sB[2] = {smem + 2 * LIN_A_STAGE, smem + 2 * LIN_A_STAGE + LIN_B_STAGE};
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (LIN_A_STAGE + LIN_B_STAGE));
-  uint64_t* full_b = bars;       // [2] weights landed
-  uint64_t* empty = bars + 2;    // [2] MMAs reading the stage have completed
-  uint64_t* done = bars + 4;     // all MMAs of the tile completed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * 128;
-  const int nt0 = blockIdx.y * 128;                 // first image row (output column) of this n-tile
-  const int nt = min(128, n_pad - nt0);             // multiple of 16
-  const int nchunks = (k_pad + 127) / 128;
-
-  if (tid == 0) {
-    mbar_init(&full_b[0], 1); mbar_init(&full_b[1], 1);
-    mbar_init(&empty[0], 1);  mbar_init(&empty[1], 1);
-    mbar_init(done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_ptr, 128);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_d = *tmem_ptr;
-  const uint32_t idesc = make_idesc_f16_f32(128, (uint32_t)nt);
-
-  const int r = row0 + tid;  // the activation row this thread stages
-  const bool vec_ok = (cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
-
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c & 1;
-    const int kc0 = c * 128;
-    const int kc = min(128, k_pad - kc0);  // multiple of 16
-    const int npan = (kc + 63) / 64;
-    if (c >= 2) mbar_wait(&empty[s], (uint32_t)(((c >> 1) - 1) & 1));  // stage free again
-    if (tid == 0) {
-      mbar_arrive_expect_tx(&full_b[s], (uint32_t)(npan * nt * 128));
-      for (int p = 0; p < npan; ++p)
-        bulk_g2s(sB[s] + (size_t)p * nt * 128, w_img + (size_t)((kc0 >> 6) + p) * n_pad * 128 + (size_t)nt0 * 128,
-                 (uint32_t)(nt * 128), &full_b[s]);
-    }
-    // stage this thread's activation row: fp32 -> fp16, 16-byte chunks at their swizzled position
-    {
-      const float* src = in + (size_t)r * cin + kc0;
-      const bool row_ok = r < rows;
-      for (int ch = 0; ch < kc / 8; ++ch) {
-        float v[8];
-        const int kb = kc0 + ch * 8;
-        if (row_ok && vec_ok && kb + 8 <= cin) {
-          float4 a = *reinterpret_cast<const float4*>(src + ch * 8);
-          float4 b = *reinterpret_cast<const float4*>(src + ch * 8 + 4);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = (row_ok && kb + i < cin) ? src[ch * 8 + i] : 0.f;
-        }
-        uint4 pk = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-        const uint32_t kk = (uint32_t)ch * 8;
-        *reinterpret_cast<uint4*>(sA[s] + (kk >> 6) * (128 * 128) + sw128_offset((uint32_t)tid, kk)) = pk;
-      }
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(&full_b[s], (uint32_t)((c >> 1) & 1));
-      tc_fence_after_sync();
-      const uint32_t a0 = smem_u32(sA[s]), b0 = smem_u32(sB[s]);
-      for (int ks = 0; ks < kc / 16; ++ks) {
-        const uint32_t pan = (uint32_t)ks >> 2, kin = (uint32_t)ks & 3;
-        mma_f16_ss(tmem_d, make_desc_sw128(a0 + pan * (128 * 128) + kin * 32),
-                   make_desc_sw128(b0 + pan * (uint32_t)(nt * 128) + kin * 32), idesc, (c > 0 || ks > 0) ? 1u : 0u);
-      }
-      mma_commit(&empty[s]);
-      if (c == nchunks - 1) mma_commit(done);
-    }
-  }
-  mbar_wait(done, 0);
-  tc_fence_after_sync();
-  // epilogue: warp w owns TMEM lanes 32w..32w+31 == tile rows
-  {
-    const int orow = row0 + warp * 32 + lane;
-    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
-    for (int cc = 0; cc < nt; cc += 16) {
-      uint32_t v[16];
-      tmem_ld_x16(taddr + (uint32_t)cc, v);
-      tmem_ld_wait();
-      if (orow < rows) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = nt0 + cc + i;
-          if (n < cout) {
-            float x = __uint_as_float(v[i]) + (bias ? bias[n] : 0.f);
-            if (act == VNB_ACT_RELU) x = fmaxf(x, 0.f);
-            if (res) x += res[(size_t)orow * cout + n];
-            if (out_f32) out_f32[(size_t)orow * cout + n] = x;
-            if (out_f16) out_f16[(size_t)orow * cout + n] = __float2half_rn(x);
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, 128);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -202,7 +83,7 @@ struct SaCfg {
 };
 
 template <int C1, int C2, int C3, bool HOIST>
-__global__ void __launch_bounds__(128) sa_tc_kernel(int n, int c, int m, int total_centroids,
+__global__ void __launch_bounds__(128) sa_tc_kernel(int n, int c, int m, int total_centroids, int tiles_per_cta,
                                                     const float* __restrict__ xyz, const float* __restrict__ feat,
                                                     const float* __restrict__ new_xyz, const int* __restrict__ idx,
                                                     const float* __restrict__ w1x /* (3,C1) f32: W1 rows 0..2 */,
@@ -258,7 +139,8 @@ __global__ void __launch_bounds__(128) sa_tc_kernel(int n, int c, int m, int tot
   const int ntiles = total_centroids / 2;
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int tile_end = min(ntiles, ((int)blockIdx.x + 1) * tiles_per_cta);
+  for (int tile = (int)blockIdx.x * tiles_per_cta; tile < tile_end; ++tile) {
     // ------------------------------------------------------------ producer: this thread's grouped row
     {
       const int g = tile * 2 + (tid >> 6);  // global centroid
@@ -437,9 +319,10 @@ static int launch_sa_tc(int b, int n, int c, int m, const float* xyz, const floa
   int per_sm = (227 * 1024) / Cfg::SMEM;
   if (per_sm > 512 / Cfg::TM_COLS) per_sm = 512 / Cfg::TM_COLS;
   if (per_sm < 1) per_sm = 1;
-  int grid = sms * per_sm;
-  if (grid > ntiles) grid = ntiles;
-  kern<<<grid, 128, Cfg::SMEM, st>>>(n, c, m, b * m, xyz, feat, new_xyz, idx, w1x, b1, b2, b3,
+  int tpc = ntiles / (2 * sms * per_sm);
+  tpc = tpc < 2 ? 2 : (tpc > 16 ? 16 : tpc);
+  const int grid = (ntiles + tpc - 1) / tpc;
+  kern<<<grid, 128, Cfg::SMEM, st>>>(n, c, m, b * m, tpc, xyz, feat, new_xyz, idx, w1x, b1, b2, b3,
                                      static_cast<const char*>(w1_img), static_cast<const char*>(w2_img),
                                      static_cast<const char*>(w3_img), static_cast<const __half*>(q), out);
   return check_launch("sa_group_mlp_max (tcgen05)");
@@ -479,13 +362,7 @@ extern "C" int vnb_linear(int rows, int cin, int cout, const float* in, const fl
   }
   VNB_REQUIRE(precision == 1, "linear: precision must be 0 (fp32) or 1 (tensor cores)");
   VNB_REQUIRE(w_img != nullptr, "linear(tensor cores): packed weight image missing");
-  const int k_pad = round_up(cin, 16), n_pad = round_up(cout, 16);
-  VNB_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
-  dim3 grid((rows + 127) / 128, (n_pad + 127) / 128);
-  linear_tc_kernel<<<grid, LIN_THREADS, LIN_SMEM, st>>>(rows, cin, cout, k_pad, n_pad, in,
-                                                       static_cast<const char*>(w_img), bias, residual, act, out_f32,
-                                                       static_cast<__half*>(out_f16));
-  return check_launch("linear (tcgen05)");
+  return linear_tc(rows, cin, cout, in, w_img, bias, residual, act, out_f32, out_f16, st);
 }
 
 extern "C" int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, const float* xyz, const float* feat,
@@ -513,6 +390,10 @@ extern "C" int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, con
   } else {
     VNB_REQUIRE(q_f16 != nullptr && w1_f32 != nullptr,
                 "sa_group_mlp_max(tensor cores): hoisted layer 1 needs q_f16 and w1_f32 (rows 0..2)");
+    if (g_sa_variant == 1) {  // warp-specialised, pipelined kernel (sa_ws.cu)
+      int rc = sa_ws_dispatch(b, n, m, xyz, new_xyz, idx, c1, c2, c3, w1_f32, b2, b3, w2_img, w3_img, q_f16, out, st);
+      if (rc >= 0) return rc;
+    }
     if (c1 == 128 && c2 == 128 && c3 == 256)
       return launch_sa_tc<128, 128, 256, true>(b, n, c, m, xyz, feat, new_xyz, idx, w1_f32, nullptr, b2, b3, nullptr,
                                                w2_img, w3_img, q_f16, out, st);

@@ -179,45 +179,74 @@ __global__ void __launch_bounds__(256) nms_greedy_kernel(int k, int W, const int
       ++nkept;
     }
   }
-  if (lane == 0) atomicAdd(out_count, nkept);
-  (void)kept_pos;
+  (void)kept_pos; (void)out_count; (void)nkept;
 }
 
-// K4: global order of the survivors: descending score, exact ties by ascending (batch, box).
-__global__ void nms_emit_kernel(int total, int k, const float* __restrict__ scores, const uint8_t* __restrict__ keep,
-                                int* __restrict__ out_idx) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total || !keep[e]) return;
-  const float se = scores[e];
-  int rank = 0;
-  for (int f = 0; f < total; ++f) rank += (keep[f] && (scores[f] > se || (scores[f] == se && f < e))) ? 1 : 0;
-  out_idx[rank * 2 + 0] = e / k;
-  out_idx[rank * 2 + 1] = e % k;
-}
-
-// K4': the same ordering over an all-gathered set of per-rank records (strided fields).
-__global__ void merge_detections_kernel(int world, int per_rank, int k, const char* __restrict__ gathered,
-                                        size_t rank_stride, size_t off_scores, size_t off_keep,
-                                        int* __restrict__ out_idx, int* __restrict__ out_count) {
+// K4: global order of the survivors: descending score, exact ties by ascending (batch, box).  Also used to merge an
+// all-gathered set of per-rank records (strided fields, vnb_merge_detections).  One CTA: compact the kept entries into
+// shared memory in flat-index order (ballot + prefix), then rank each against the others (O(nkept^2), nkept << total).
+__global__ void __launch_bounds__(1024) rank_emit_kernel(int world, int per_rank, int k, const char* __restrict__ sc_base,
+                                                          size_t sc_stride, const char* __restrict__ kp_base,
+                                                          size_t kp_stride, int* __restrict__ out_idx,
+                                                          int* __restrict__ out_count) {
+  extern __shared__ char s_dyn[];
   const int total = world * per_rank;
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  const int re = e / per_rank, le = e % per_rank;
-  const uint8_t ke = *reinterpret_cast<const uint8_t*>(gathered + re * rank_stride + off_keep + le);
-  if (!ke) return;
-  const float se = *reinterpret_cast<const float*>(gathered + re * rank_stride + off_scores + (size_t)le * 4);
-  int rank = 0;
-  for (int r = 0; r < world; ++r) {
-    const float* sc = reinterpret_cast<const float*>(gathered + r * rank_stride + off_scores);
-    const uint8_t* kp = reinterpret_cast<const uint8_t*>(gathered + r * rank_stride + off_keep);
-    for (int f = 0; f < per_rank; ++f) {
-      const int ge = r * per_rank + f;
-      rank += (kp[f] && (sc[f] > se || (sc[f] == se && ge < e))) ? 1 : 0;
+  float* s_sc = reinterpret_cast<float*>(s_dyn);
+  int* s_id = reinterpret_cast<int*>(s_sc + total);
+  __shared__ int s_wcnt[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < total; c0 += 1024) {
+    const int e = c0 + tid;
+    bool kept = false;
+    float sc = 0.f;
+    if (e < total) {
+      const int r = e / per_rank, l = e % per_rank;
+      kept = *reinterpret_cast<const uint8_t*>(kp_base + r * kp_stride + l) != 0;
+      sc = *reinterpret_cast<const float*>(sc_base + r * sc_stride + (size_t)l * 4);
     }
+    const unsigned bm = __ballot_sync(0xffffffffu, kept);
+    if (lane == 0) s_wcnt[warp] = __popc(bm);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_wcnt[w];
+    if (kept) {
+      const int pos = off + __popc(bm & ((1u << lane) - 1u));
+      s_sc[pos] = sc;
+      s_id[pos] = e;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += s_wcnt[w];
+      s_base += t;
+    }
+    __syncthreads();
   }
-  out_idx[rank * 2 + 0] = e / k;
-  out_idx[rank * 2 + 1] = e % k;
-  atomicAdd(out_count, 1);
+  const int nk = s_base;
+  for (int i = tid; i < nk; i += 1024) {
+    const float se = s_sc[i];
+    const int e = s_id[i];
+    int rank = 0;
+    for (int j = 0; j < nk; ++j) rank += (s_sc[j] > se || (s_sc[j] == se && s_id[j] < e)) ? 1 : 0;
+    out_idx[rank * 2 + 0] = e / k;
+    out_idx[rank * 2 + 1] = e % k;
+  }
+  if (tid == 0) *out_count = nk;
+}
+
+static int launch_rank_emit(int world, int per_rank, int k, const char* sc, size_t scs, const char* kp, size_t kps,
+                            int* out_idx, int* out_count, cudaStream_t st) {
+  const size_t smem = (size_t)world * per_rank * 8;
+  if (smem > 200 * 1024) return set_err(VNB_ERR_INVALID, "nms: more than 25600 boxes in one ordering pass");
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rank_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_err(VNB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  rank_emit_kernel<<<1, 1024, smem, st>>>(world, per_rank, k, sc, scs, kp, kps, out_idx, out_count);
+  return check_launch("nms3d order");
 }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -257,19 +286,18 @@ extern "C" int vnb_nms3d(int b, int k, const float* bbox, const float* scores, c
     VNB_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   nms_greedy_kernel<<<b, 256, smem, st>>>(k, W, order, ncand, mask, keep, nullptr, out_count);
   if (int rc = check_launch("nms3d greedy")) return rc;
-  const int total = b * k;
-  nms_emit_kernel<<<(total + 127) / 128, 128, 0, st>>>(total, k, scores, keep, out_idx);
-  return check_launch("nms3d emit");
+  return launch_rank_emit(1, b * k, k, reinterpret_cast<const char*>(scores), 0, reinterpret_cast<const char*>(keep), 0,
+                          out_idx, out_count, st);
 }
 
 extern "C" int vnb_merge_detections(int world, int b, int k, const void* gathered, size_t rank_stride,
                                     size_t off_scores, size_t off_keep, int* out_idx, int* out_count, void* stream) {
   VNB_REQUIRE(world > 0 && b >= 0 && k >= 0, "merge_detections: bad shape");
   cudaStream_t st = as_stream(stream);
-  VNB_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int), st));
-  const int total = world * b * k;
-  if (total == 0) return VNB_OK;
-  merge_detections_kernel<<<(total + 127) / 128, 128, 0, st>>>(world, b * k, k, static_cast<const char*>(gathered),
-                                                             rank_stride, off_scores, off_keep, out_idx, out_count);
-  return check_launch("merge_detections");
+  if (world * b * k == 0) {
+    VNB_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int), st));
+    return VNB_OK;
+  }
+  const char* g = static_cast<const char*>(gathered);
+  return launch_rank_emit(world, b * k, k, g + off_scores, rank_stride, g + off_keep, rank_stride, out_idx, out_count, st);
 }

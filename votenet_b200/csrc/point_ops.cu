@@ -9,6 +9,7 @@ namespace vnb {
 
 static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;
+int g_bq_variant = 1;  // 0: brute-force scan, 1: cell grid + index bitmap (needs the workspace entry point)
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 char* err_buf() { return g_err; }
 int set_err(int code, const char* fmt, ...) {
@@ -270,7 +271,7 @@ __global__ void decode_kernel(int total, const float* __restrict__ pxyz, const f
 }
 
 // Largest float t with sqrtf(t) < radius (host; IEEE sqrt is correctly rounded on both host and device).
-static float ball_d2_max(float radius) {
+float ball_d2_max(float radius) {
   float t = radius * radius;
   while (t > 0.0f && !(sqrtf(t) < radius)) t = nextafterf(t, 0.0f);
   for (;;) {

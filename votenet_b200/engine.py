@@ -62,12 +62,11 @@ class Engine:
         self.store = WeightStore(weights, device=self.device, eps=cfg.bn_eps, precision=precision)
         self.mean_size = torch.as_tensor(CLASS_MEAN_SIZE, device=self.device).contiguous()
         with torch.cuda.device(self.device):
-            self.s_samp = torch.cuda.Stream(device=self.device)
-            self.s_aux = torch.cuda.Stream(device=self.device)
             self._prepare_layers()
             self.slots = [self._make_slot() for _ in range(slots)]
         self._step = 0
         self.launches_per_forward = None
+        self.timeline = None   # debugging: set to [] (with use_graph=False) to collect (step, stage, event) marks
 
     # ------------------------------------------------------------------------------------------------ weights
     def _prepare_layers(self):
@@ -115,6 +114,8 @@ class Engine:
             l.cnt = E((B, sa.npoint), i32)
             l.q = E((B * n, sa.mlp[0]), f16) if self.sa_layers[li][3] is not None else None
             l.feat = E((B, sa.npoint, sa.mlp[-1]))
+            l.bq_ws = (torch.empty((lib.vnb_query_ball_point_workspace_bytes(B, n),), dtype=torch.uint8, device=dev)
+                       if n >= 4096 else None)
             s.lv.append(l)
             n = sa.npoint
         c = cfg.sa[-1].mlp[-1]
@@ -142,7 +143,10 @@ class Engine:
         s.p_h = [E((B * p.npoint, co)) for co in p.mlp2]
         s.rec = DetectionRecord(B, p.npoint, dev)
         s.nms_ws = torch.empty((lib.vnb_nms3d_workspace_bytes(B, p.npoint),), dtype=torch.uint8, device=dev)
+        s.fps_ws = torch.empty((lib.vnb_fps_nested_workspace_bytes(B, max(sa.npoint for sa in cfg.sa)),), dtype=torch.uint8, device=dev)
         s.done = torch.cuda.Event()
+        s.samp = torch.cuda.Stream(device=dev)   # sampling chain (FPS + gathers)
+        s.aux = torch.cuda.Stream(device=dev)    # neighbour searches (ball query, three_nn)
         s.graph = None
         s.used = False
         return s
@@ -168,30 +172,45 @@ class Engine:
     def _enqueue(self, s, main):
         """Enqueue one forward over slot `s`: sampling chain on s_samp, neighbour searches on s_aux, features on main."""
         cfg, B = self.cfg, self.B
-        samp, aux = self.s_samp, self.s_aux
+        samp, aux = s.samp, s.aux
         ev = torch.cuda.Event
+        tl = self.timeline is not None
+
+        def mark(name, stream):
+            if tl:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                self.timeline.append((self._step, name, e))
+        mark("start", main)
         e_in = ev(); e_in.record(main)
         samp.wait_event(e_in); aux.wait_event(e_in)
         # ---- sampling chain (xyz only): FPS -> gather, level after level; then the proposal FPS on the seeds
         e_lv = []
         src = s.xyz
-        for l in s.lv:
-            check(lib.vnb_farthest_point_sample(B, l.n, l.m, dptr(src), dptr(l.fps), _sp(samp)))
+        for li, l in enumerate(s.lv):
+            if li == 0:   # the only real search (raw cloud); deeper levels sample an FPS-ordered set
+                check(lib.vnb_farthest_point_sample(B, l.n, l.m, dptr(src), dptr(l.fps), _sp(samp)))
+            else:
+                check(lib.vnb_farthest_point_sample_nested(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws), _sp(samp)))
             check(lib.vnb_gather_point(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(l.xyz), _sp(samp)))
             e = ev(); e.record(samp); e_lv.append(e)
+            mark(f"fps{li + 1}", samp)
             src = l.xyz
         seeds_xyz = s.lv[1].xyz
         p = cfg.proposal
-        check(lib.vnb_farthest_point_sample(B, s.lv[1].m, p.npoint, dptr(seeds_xyz), dptr(s.p_fps), _sp(samp)))
+        check(lib.vnb_farthest_point_sample_nested(B, s.lv[1].m, p.npoint, dptr(seeds_xyz), dptr(s.p_fps), dptr(s.fps_ws),
+                                                   _sp(samp)))
         e_pf = ev(); e_pf.record(samp)
+        mark("fps_prop", samp)
         # ---- neighbour searches (xyz + centroids only)
         e_bq = []
         src = s.xyz
         for li, l in enumerate(s.lv):
             aux.wait_event(e_lv[li])
-            check(lib.vnb_query_ball_point(B, l.n, l.m, float(cfg.sa[li].radius), 64, dptr(src), dptr(l.xyz), dptr(l.idx),
-                                           dptr(l.cnt), _sp(aux)))
+            check(lib.vnb_query_ball_point_ws(B, l.n, l.m, float(cfg.sa[li].radius), 64, dptr(src), dptr(l.xyz),
+                                              dptr(l.idx), dptr(l.cnt), dptr(l.bq_ws), _sp(aux)))
             e = ev(); e.record(aux); e_bq.append(e)
+            mark(f"bq{li + 1}", aux)
             src = l.xyz
         for f, (u, kx) in zip(s.fp, ((s.lv[2].xyz, s.lv[3].xyz), (s.lv[1].xyz, s.lv[2].xyz))):
             check(lib.vnb_three_nn(B, f.n, f.m, dptr(u), dptr(kx), dptr(f.dist), dptr(f.idx), _sp(aux)))
@@ -200,7 +219,9 @@ class Engine:
         src_xyz, src_feat, c = s.xyz, s.feat, cfg.feature_dim
         for li, l in enumerate(s.lv):
             main.wait_event(e_bq[li])
+            mark(f"sa{li + 1}_begin", main)
             self._sa(li, src_xyz, src_feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, main)
+            mark(f"sa{li + 1}", main)
             src_xyz, src_feat, c = l.xyz, l.feat, cfg.sa[li].mlp[-1]
         main.wait_event(e_nn)
         pts2 = s.lv[3].feat
@@ -212,6 +233,7 @@ class Engine:
                 self._linear(B * f.n, x, self.store.layer(f"{scope}/conv_{i}"), True, f.h[i], None, main)
                 x = f.h[i]
             pts2 = x
+        mark("fp", main)
         ns = s.lv[1].m
         cf = cfg.seed_feat_dim
         check(lib.vnb_concat2(B * ns, 3, cf, dptr(seeds_xyz), dptr(pts2), dptr(s.seeds), _sp(main)))
@@ -222,6 +244,7 @@ class Engine:
                          residual=s.seeds if i == nv - 1 else None)
             x = s.vh[i]
         check(lib.vnb_split2(B * ns, 3, cf, dptr(x), dptr(s.votes_xyz), dptr(s.votes_feat), _sp(main)))
+        mark("vote", main)
         main.wait_event(e_pf)
         check(lib.vnb_gather_point(B, ns, p.npoint, dptr(s.votes_xyz), dptr(s.p_fps), dptr(s.p_xyz), _sp(main)))
         check(lib.vnb_query_ball_point(B, ns, p.npoint, float(p.radius), 64, dptr(s.votes_xyz), dptr(s.p_xyz),
@@ -232,11 +255,13 @@ class Engine:
             self._linear(B * p.npoint, x, self.store.layer(f"proposal/conv_post_{i}"), i < len(p.mlp2) - 1, s.p_h[i], None,
                          main)
             x = s.p_h[i]
+        mark("proposal", main)
         r = s.rec
         check(lib.vnb_decode_boxes(B, p.npoint, dptr(s.p_xyz), dptr(x), dptr(self.mean_size), dptr(r.bboxes),
                                    dptr(r.scores), dptr(r.objectness), dptr(r.class_scores), _sp(main)))
         check(lib.vnb_nms3d(B, p.npoint, dptr(r.bboxes), dptr(r.scores), dptr(r.objectness), float(cfg.nms_iou),
                             dptr(r.keep), dptr(r.nms_idx), dptr(r.nms_count), dptr(s.nms_ws), _sp(main)))
+        mark("nms", main)
         # join the side streams back (all their work has been consumed through events; this keeps capture well-formed)
         e1, e2 = ev(), ev()
         e1.record(samp); e2.record(aux)

@@ -17,8 +17,12 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     m = xyz2.shape[1]
     idx = torch.zeros((b, m, int(nsample)), dtype=torch.int32, device=xyz1.device)
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
-    check(lib.vnb_query_ball_point(b, n, m, float(radius), int(nsample), dptr(xyz1, torch.float32, "xyz1"),
-                                   dptr(xyz2, torch.float32, "xyz2"), dptr(idx), dptr(cnt), stream_ptr()))
+    # large searched sets go through the grid + index-bitmap kernel (bit-identical outputs); it needs scratch memory
+    ws = None
+    if n >= 4096:
+        ws = torch.empty((lib.vnb_query_ball_point_workspace_bytes(b, n),), dtype=torch.uint8, device=xyz1.device)
+    check(lib.vnb_query_ball_point_ws(b, n, m, float(radius), int(nsample), dptr(xyz1, torch.float32, "xyz1"),
+                                      dptr(xyz2, torch.float32, "xyz2"), dptr(idx), dptr(cnt), dptr(ws), stream_ptr()))
     return idx, cnt
 
 

@@ -20,6 +20,18 @@ def farthest_point_sample(npoint, inp):
     return out
 
 
+def farthest_point_sample_nested(npoint, inp):
+    """Bit-identical to farthest_point_sample; fast when `inp` is itself FPS-ordered (nested SA levels): proves in
+    parallel that the answer is the identity prefix and only falls back to the sequential sampler where it is not."""
+    inp = _xyz3(inp, "FarthestPointSample")
+    b, n, _ = inp.shape
+    out = torch.empty((b, int(npoint)), dtype=torch.int32, device=inp.device)
+    ws = torch.empty((lib.vnb_fps_nested_workspace_bytes(b, int(npoint)),), dtype=torch.uint8, device=inp.device)
+    check(lib.vnb_farthest_point_sample_nested(b, n, int(npoint), dptr(inp, torch.float32, "inp"), dptr(out), dptr(ws),
+                                               stream_ptr()))
+    return out
+
+
 def gather_point(inp, idx):
     """inp (B,N,3) f32, idx (B,M) i32 -> (B,M,3) f32.   Reference: tf_sampling.py:29-37 (GatherPoint, tf_sampling.cpp:126-148)."""
     inp = _xyz3(inp, "GatherPoint")

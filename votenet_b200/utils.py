@@ -114,7 +114,11 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
     if len(mlp) != 3:
         raise NotImplementedError("pointnet_sa_module: the fused kernel implements the 3-layer shared MLP VoteNet uses")
     prec = weights.precision
-    fps_idx = tf_sampling.farthest_point_sample(npoint, sample_xyz if sample_xyz is not None else xyz)  # utils.py:42-45
+    # utils.py:42-45.  (the _nested entry point is bit-identical; it is only faster when the input is FPS-ordered,
+    # which is the case for every VoteNet level but the first)
+    fps_in = sample_xyz if sample_xyz is not None else xyz
+    fps = tf_sampling.farthest_point_sample_nested if fps_in.shape[1] <= 4096 else tf_sampling.farthest_point_sample
+    fps_idx = fps(npoint, fps_in)
     new_xyz = tf_sampling.gather_point(xyz, fps_idx)
     idx, _ = tf_grouping.query_ball_point(radius, nsample, xyz, new_xyz)                                 # utils.py:49
     layers = [weights.layer(f"{scope}/conv{i}") for i in range(3)]
