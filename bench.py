@@ -177,7 +177,7 @@ def kernel_table(eng, cfg, peaks, flush):
         byt = B * (l.n * 12 + l.m * 12 + l.m * 256 + l.m * 4)
         rows.append(dict(kernel=f"ball_query_sa{li + 1}", ms=ms, bound="hbm", algo_bytes=byt, achieved=byt / ms / 1e6,
                          peak=peaks["hbm"], unit="GB/s"))
-        ms = t(lambda: eng._sa(li, src, feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, st))
+        ms = t(lambda: eng._sa(li, src, feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, st, s.sa_ws))
         cin = 3 + c
         fl = 0
         for co in sa.mlp:
@@ -200,8 +200,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=int, default=1)
-    ap.add_argument("--inflight", type=int, default=4, help="steps in flight (independent workspaces + streams)")
-    ap.add_argument("--fps-cluster", type=int, default=None, help="tuning: CTAs per FPS cluster")
+    ap.add_argument("--inflight", type=int, default=8, help="steps in flight (independent workspaces + streams)")
+    ap.add_argument("--fps-cluster", type=int, default=4,
+                    help="CTAs per FPS cluster (4 = 32 SMs per batch: best throughput with steps overlapped; 8 = lowest latency)")
     ap.add_argument("--fps-threads", type=int, default=None, help="tuning: threads per FPS CTA (256/512/1024)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -344,7 +345,7 @@ def main():
                            "parallelism": f"dp{world} (clouds sharded, 1 all-gather of detections)" if world > 1 else "single GPU",
                            "l2": f"inputs rotate over {RING} device-resident batches ({RING * h2d / 1e6:.0f} MB > 126 MB L2)",
                            "pipelining": f"{NS} steps in flight ({NS} workspaces, {NS} streams): later steps' FPS chains overlap earlier steps' MLP chains",
-                           "cuda_graph": not args.no_graph},
+                           "cuda_graph": not args.no_graph, "fps_geometry": f"{args.fps_threads or 256} threads x cluster {args.fps_cluster}"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "launches_per_forward": lpf,

@@ -149,7 +149,10 @@ int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, const float* x
                          const float* new_xyz, const int* idx, int c1, int c2, int c3, const float* w1_f32,
                          const float* b1, const float* w2_f32, const float* b2, const float* w3_f32, const float* b3,
                          const void* w1_img, const void* w2_img, const void* w3_img, const void* q_f16, float* out,
-                         int precision, void* stream);
+                         int precision, void* workspace, void* stream);
+/* workspace (optional, may be NULL): vnb_sa_workspace_bytes(b,m,nsample) bytes; the pipelined tensor-core kernel of the
+ * hoisted variant needs it (grouped relative coordinates); without it the single-role kernel runs. */
+size_t vnb_sa_workspace_bytes(int b, int m, int nsample);
 
 /* pointnet_fp_module front half: inverse-distance weights + three_interpolate + concat     utils.py:279-286
  * dist (b,n,3), idx (b,n,3) from vnb_three_nn; points2 (b,m,c2) known features; points1 (b,n,c1) skip features

@@ -38,7 +38,7 @@ def test_argument_validation_needs_no_gpu():
     assert lib.vnb_query_ball_point(1, 8, 4, 0.5, 0, null, null, null, null, null) == 1
     assert lib.vnb_nms3d(1, 4, null, null, null, 1.5, null, null, null, null, null) == 1
     assert b"iou_threshold" in lib.vnb_last_error()
-    assert lib.vnb_sa_group_mlp_max(*([1, 8, 1, 2, 32] + [null] * 4 + [64, 64, 128] + [null] * 11 + [1, null])) == 1
+    assert lib.vnb_sa_group_mlp_max(*([1, 8, 1, 2, 32] + [null] * 4 + [64, 64, 128] + [null] * 11 + [1, null, null])) == 1
     assert lib.vnb_linear(4, 8, 8, null, null, null, null, null, 7, null, null, 1, null) == 1
     # sizes
     assert lib.vnb_weight_image_bytes(128, 128) == 2 * 128 * 128

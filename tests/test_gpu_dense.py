@@ -158,7 +158,8 @@ def test_sa_kernel_variants_agree(cuda):
     from votenet_b200._lib import check, lib
     from votenet_b200.utils import WeightStore, sa_group_mlp_max
 
-    for (b, n, m, c, mlp, r) in [(8, 2048, 1024, 128, (128, 128, 256), 0.2), (3, 1024, 254, 256, (128, 128, 128), 0.3)]:
+    for (b, n, m, c, mlp, r) in [(8, 2048, 1024, 128, (128, 128, 256), 0.2), (3, 1024, 254, 256, (128, 128, 128), 0.3),
+                                 (4, 6000, 2048, 1, (64, 64, 128), 0.15), (1, 3000, 130, 3, (64, 64, 128), 0.2)]:
         xyz, feat, new_xyz, idx, w, ref = _sa_case(b, n, m, c, mlp, r, seed=77 + m)
         store = WeightStore(w, device=cuda, precision=1)
         layers = [store.layer(f"s/conv{i}") for i in range(3)]

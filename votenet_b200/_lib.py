@@ -42,7 +42,8 @@ _SIGS = {
     "vnb_weight_image_bytes": ([_i, _i], _sz),
     "vnb_pack_weight_f16": ([_i, _i, _p, _p, _p], _i),
     "vnb_linear": ([_i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _i, _p], _i),
-    "vnb_sa_group_mlp_max": ([_i] * 5 + [_p] * 4 + [_i] * 3 + [_p] * 11 + [_i, _p], _i),
+    "vnb_sa_group_mlp_max": ([_i] * 5 + [_p] * 4 + [_i] * 3 + [_p] * 11 + [_i, _p, _p], _i),
+    "vnb_sa_workspace_bytes": ([_i, _i, _i], _sz),
     "vnb_fp_interpolate_concat": ([_i] * 5 + [_p] * 6, _i),
     "vnb_concat2": ([_i, _i, _i, _p, _p, _p, _p], _i),
     "vnb_split2": ([_i, _i, _i, _p, _p, _p, _p], _i),

@@ -26,6 +26,7 @@ SOURCES = {
     "mlp_simt.cu": [],
     "mlp_tc.cu": [],
     "sa_ws.cu": [],
+    "sa1_ws.cu": [],
     "linear_tc.cu": [],
 }
 

@@ -137,6 +137,12 @@ __global__ void __launch_bounds__(T) fps_cluster_kernel(int n, int m, int CL, co
     pacc[i] += _t - pt0;                            \
     pt0 = _t;                                       \
   }
+  // destination slots of this CTA's champion in CTA `lane` of the cluster (lanes < CL), both parities
+  uint32_t ra0 = 0, ra1 = 0, rb0 = 0, rb1 = 0;
+  if (CL > 1 && lane < CL) {
+    ra0 = mapa(smem_addr(&s_xa[0][rank]), lane); ra1 = mapa(smem_addr(&s_xa[1][rank]), lane);
+    rb0 = mapa(smem_addr(&s_xb[0][rank]), lane); rb1 = mapa(smem_addr(&s_xb[1][rank]), lane);
+  }
   for (int r = 1; r < m; ++r) {
     const int par = r & 1;
     if (PROF) pt0 = clock64();
@@ -184,9 +190,8 @@ __global__ void __launch_bounds__(T) fps_cluster_kernel(int n, int m, int CL, co
         const int cl = __ffs(cm) - 1;
         sx = __shfl_sync(0xffffffffu, sx, cl); sy = __shfl_sync(0xffffffffu, sy, cl); sz = __shfl_sync(0xffffffffu, sz, cl);
         if (lane < CL) {
-          st_cluster_v4(mapa(smem_addr(&s_xa[par][rank]), lane), chi, (tag << 16) | clo, __float_as_uint(sx),
-                        __float_as_uint(sy));
-          st_cluster_v2(mapa(smem_addr(&s_xb[par][rank]), lane), __float_as_uint(sz), tag);
+          st_cluster_v4(par ? ra1 : ra0, chi, (tag << 16) | clo, __float_as_uint(sx), __float_as_uint(sy));
+          st_cluster_v2(par ? rb1 : rb0, __float_as_uint(sz), tag);
         }
       }
       FPS_TICK(4)  // remote stores issued (only the champion warp does work here)
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(T) fps_cluster_kernel(int n, int m, int CL, co
 // Kernel A: R[j] = T_j[j] for j < m (thread j, loop over i < j; triangular, m^2/2 distance evaluations per cloud).
 // Kernel B: thread k walks i = 0..m-2 keeping its running min and checks round j = i+1 against R[j].
 // Induction over j makes the hypothesis true whenever all checks pass.
-constexpr int VT = 256;
+constexpr int VT = 64;  // small CTAs: (n/64) x b of them spread over all SMs
 __global__ void __launch_bounds__(128) fps_prefix_r_kernel(int n, int m, const float* __restrict__ xyz,
                                                            float* __restrict__ R /* (b,m) */) {
   extern __shared__ float sv[];  // xyz of picks 0 .. jend-1
@@ -254,13 +259,11 @@ __global__ void __launch_bounds__(128) fps_prefix_r_kernel(int n, int m, const f
 __global__ void __launch_bounds__(VT) fps_prefix_verify_kernel(int n, int m, const float* __restrict__ xyz,
                                                                 const float* __restrict__ R,
                                                                 int* __restrict__ fail /* per cloud, pre-zeroed */) {
-  extern __shared__ float sv[];  // [m*3] xyz of the m hypothesised picks, [m] R
-  float* sx = sv;
-  float* sR = sv + (size_t)m * 3;
+  extern __shared__ float4 sq[];  // [m-1]: {xyz of pick i, R[i+1]} -> one broadcast LDS.128 per round
   const int cloud = blockIdx.y;
   const float* pc = xyz + (size_t)cloud * n * 3;
-  for (int t = threadIdx.x; t < m * 3; t += VT) sx[t] = pc[t];
-  for (int t = threadIdx.x; t < m; t += VT) sR[t] = R[(size_t)cloud * m + t];
+  for (int i = threadIdx.x; i + 1 < m; i += VT)
+    sq[i] = make_float4(pc[(size_t)i * 3], pc[(size_t)i * 3 + 1], pc[(size_t)i * 3 + 2], R[(size_t)cloud * m + i + 1]);
   __syncthreads();
   const int k = blockIdx.x * VT + threadIdx.x;
   if (k >= n) return;
@@ -268,11 +271,12 @@ __global__ void __launch_bounds__(VT) fps_prefix_verify_kernel(int n, int m, con
   const uint32_t tk = tie_key(k);
   float t = 1e38f;
   bool bad = false;
+#pragma unroll 4
   for (int i = 0; i + 1 < m; ++i) {  // after this iteration t == T_{i+1}[k]
-    t = fminf(t, d2_ref_gpu(x - sx[i * 3], y - sx[i * 3 + 1], z - sx[i * 3 + 2]));
+    const float4 p = sq[i];
+    t = fminf(t, d2_ref_gpu(x - p.x, y - p.y, z - p.z));
     const int j = i + 1;
-    const float rj = sR[j];
-    if (k != j && (t > rj || (t == rj && tk > tie_key(j)))) bad = true;
+    if (k != j && (t > p.w || (t == p.w && tk > tie_key(j)))) bad = true;
   }
   if (bad) atomicOr(&fail[cloud], 1);
 }
@@ -418,7 +422,7 @@ extern "C" int vnb_farthest_point_sample_nested(int b, int n, int m, const float
   if (int rc = fps_check_args(b, n, m)) return rc;
   if (b == 0) return VNB_OK;
   cudaStream_t st = as_stream(stream);
-  const size_t smem = (size_t)m * 4 * sizeof(float);
+  const size_t smem = (size_t)m * sizeof(float4);
   if (m > n || smem > 200 * 1024)  // the identity prefix needs m <= n; huge m does not fit the proof kernel
     return fps_dispatch(b, n, m, xyz, out_idx, nullptr, st);
   int* fail = static_cast<int*>(workspace);

@@ -29,7 +29,10 @@ int sa_simt(int b, int n, int c, int m, const float* xyz, const float* feat, con
             const float* b3, float* out, cudaStream_t st);
 int sa_ws_dispatch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, int c1, int c2, int c3,
                    const float* w1x, const float* b2, const float* b3, const void* w2_img, const void* w3_img,
-                   const void* q, float* out, cudaStream_t st);
+                   const void* q, float* out, void* workspace, cudaStream_t st);
+int sa1_ws_dispatch(int b, int n, int c, int m, const float* xyz, const float* feat, const float* new_xyz, const int* idx,
+                    int c1, int c2, int c3, const float* b1, const float* b2, const float* b3, const void* w1_img,
+                    const void* w2_img, const void* w3_img, float* out, void* workspace, cudaStream_t st);
 int linear_tc(int rows, int cin, int cout, const float* in, const void* w_img, const float* bias, const float* res,
               int act, float* out_f32, void* out_f16, cudaStream_t st);  // linear_tc.cu
 int g_sa_variant = 1;  // 0: single-role kernel (sa_tc_kernel), 1: warp-specialised pipeline (sa_ws.cu) where available
@@ -332,6 +335,11 @@ static int launch_sa_tc(int b, int n, int c, int m, const float* xyz, const floa
 
 using namespace vnb;
 
+extern "C" size_t vnb_sa_workspace_bytes(int b, int m, int nsample) {
+  if (b <= 0 || m <= 0 || nsample <= 0) return 256;
+  return (size_t)b * m * nsample * 16;
+}
+
 extern "C" size_t vnb_weight_image_bytes(int cin, int cout) {
   if (cin <= 0 || cout <= 0) return 0;
   size_t k_pad = (size_t)round_up(cin, 16), n_pad = (size_t)round_up(cout, 16);
@@ -369,7 +377,7 @@ extern "C" int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, con
                                     const float* new_xyz, const int* idx, int c1, int c2, int c3, const float* w1_f32,
                                     const float* b1, const float* w2_f32, const float* b2, const float* w3_f32,
                                     const float* b3, const void* w1_img, const void* w2_img, const void* w3_img,
-                                    const void* q_f16, float* out, int precision, void* stream) {
+                                    const void* q_f16, float* out, int precision, void* workspace, void* stream) {
   VNB_REQUIRE(nsample == 64, "sa_group_mlp_max: nsample must be 64 (got %d)", nsample);
   VNB_REQUIRE(b >= 0 && n > 0 && c >= 0 && m >= 0 && c1 > 0 && c2 > 0 && c3 > 0, "sa_group_mlp_max: bad shape");
   if (b == 0 || m == 0) return VNB_OK;
@@ -384,6 +392,11 @@ extern "C" int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, con
   const bool hoist = c > 13;
   if (!hoist) {
     VNB_REQUIRE(w1_img != nullptr, "sa_group_mlp_max(tensor cores): w1_img missing");
+    if (g_sa_variant == 1) {  // warp-specialised, pipelined kernel (sa1_ws.cu)
+      int rc = sa1_ws_dispatch(b, n, c, m, xyz, feat, new_xyz, idx, c1, c2, c3, b1, b2, b3, w1_img, w2_img, w3_img, out,
+                               workspace, st);
+      if (rc >= 0) return rc;
+    }
     if (c1 == 64 && c2 == 64 && c3 == 128)
       return launch_sa_tc<64, 64, 128, false>(b, n, c, m, xyz, feat, new_xyz, idx, nullptr, b1, b2, b3, w1_img, w2_img,
                                               w3_img, nullptr, out, st);
@@ -391,7 +404,7 @@ extern "C" int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, con
     VNB_REQUIRE(q_f16 != nullptr && w1_f32 != nullptr,
                 "sa_group_mlp_max(tensor cores): hoisted layer 1 needs q_f16 and w1_f32 (rows 0..2)");
     if (g_sa_variant == 1) {  // warp-specialised, pipelined kernel (sa_ws.cu)
-      int rc = sa_ws_dispatch(b, n, m, xyz, new_xyz, idx, c1, c2, c3, w1_f32, b2, b3, w2_img, w3_img, q_f16, out, st);
+      int rc = sa_ws_dispatch(b, n, m, xyz, new_xyz, idx, c1, c2, c3, w1_f32, b2, b3, w2_img, w3_img, q_f16, out, workspace, st);
       if (rc >= 0) return rc;
     }
     if (c1 == 128 && c2 == 128 && c3 == 256)

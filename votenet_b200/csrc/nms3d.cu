@@ -183,9 +183,10 @@ __global__ void __launch_bounds__(256) nms_greedy_kernel(int k, int W, const int
 }
 
 // K4: global order of the survivors: descending score, exact ties by ascending (batch, box).  Also used to merge an
-// all-gathered set of per-rank records (strided fields, vnb_merge_detections).  One CTA: compact the kept entries into
-// shared memory in flat-index order (ballot + prefix), then rank each against the others (O(nkept^2), nkept << total).
-__global__ void __launch_bounds__(1024) rank_emit_kernel(int world, int per_rank, int k, const char* __restrict__ sc_base,
+// all-gathered set of per-rank records (strided fields, vnb_merge_detections).  Every CTA compacts the kept entries into
+// its shared memory in flat-index order (ballot + prefix; cheap and redundant), then the CTAs split the O(nkept^2)
+// ranking: CTA c ranks compacted entries c*256+tid, (c+G)*256+tid, ...
+__global__ void __launch_bounds__(256) rank_emit_kernel(int world, int per_rank, int k, const char* __restrict__ sc_base,
                                                           size_t sc_stride, const char* __restrict__ kp_base,
                                                           size_t kp_stride, int* __restrict__ out_idx,
                                                           int* __restrict__ out_count) {
@@ -193,12 +194,12 @@ __global__ void __launch_bounds__(1024) rank_emit_kernel(int world, int per_rank
   const int total = world * per_rank;
   float* s_sc = reinterpret_cast<float*>(s_dyn);
   int* s_id = reinterpret_cast<int*>(s_sc + total);
-  __shared__ int s_wcnt[32];
+  __shared__ int s_wcnt[8];
   __shared__ int s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_base = 0;
   __syncthreads();
-  for (int c0 = 0; c0 < total; c0 += 1024) {
+  for (int c0 = 0; c0 < total; c0 += 256) {
     const int e = c0 + tid;
     bool kept = false;
     float sc = 0.f;
@@ -220,13 +221,13 @@ __global__ void __launch_bounds__(1024) rank_emit_kernel(int world, int per_rank
     __syncthreads();
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < 32; ++w) t += s_wcnt[w];
+      for (int w = 0; w < 8; ++w) t += s_wcnt[w];
       s_base += t;
     }
     __syncthreads();
   }
   const int nk = s_base;
-  for (int i = tid; i < nk; i += 1024) {
+  for (int i = (int)blockIdx.x * 256 + tid; i < nk; i += (int)gridDim.x * 256) {
     const float se = s_sc[i];
     const int e = s_id[i];
     int rank = 0;
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(1024) rank_emit_kernel(int world, int per_rank
     out_idx[rank * 2 + 0] = e / k;
     out_idx[rank * 2 + 1] = e % k;
   }
-  if (tid == 0) *out_count = nk;
+  if (tid == 0 && blockIdx.x == 0) *out_count = nk;
 }
 
 static int launch_rank_emit(int world, int per_rank, int k, const char* sc, size_t scs, const char* kp, size_t kps,
@@ -245,7 +246,9 @@ static int launch_rank_emit(int world, int per_rank, int k, const char* sc, size
     cudaError_t e = cudaFuncSetAttribute(rank_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_err(VNB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  rank_emit_kernel<<<1, 1024, smem, st>>>(world, per_rank, k, sc, scs, kp, kps, out_idx, out_count);
+  int grid = (world * per_rank + 255) / 256;
+  if (grid > 32) grid = 32;
+  rank_emit_kernel<<<grid, 256, smem, st>>>(world, per_rank, k, sc, scs, kp, kps, out_idx, out_count);
   return check_launch("nms3d order");
 }
 

@@ -4,9 +4,11 @@
 // (reference utils.py:49-55,120-132) — but the four stages of a 128-row tile run on different warps and overlap with
 // the tensor core across tiles:
 //
-//   warps 8-11  PRODUCER   gather q rows (16 threads per row, 16-byte coalesced chunks), add the rank-3 relative-xyz term,
-//                          ReLU, fp16, write the swizzled A operand H1[t%2]                        -> h1_full[t%2]
-//   warp  12    MMA        one elected thread issues  M2(t): D2[t%2] = H1[t%2] . W2^T            -> m2_done[t%2] (commit)
+//   warps 8-15  PRODUCER   gather q rows (16 threads per row, 16-byte coalesced chunks, 8 independent loads in flight per
+//                          thread), add the rank-3 relative-xyz term, ReLU, fp16, write the swizzled A operand H1[t%2]
+//                          -> h1_full[t%2].  The relative coordinates + q-row index of every grouped row come from a
+//                          tiny helper kernel (group_rel_kernel) so the gather addresses carry no dependent-load chain.
+//   warp  16    MMA        one elected thread issues  M2(t): D2[t%2] = H1[t%2] . W2^T            -> m2_done[t%2] (commit)
 //                                                      M3(t): D3 = W3^T . H2^T  (transposed)      -> m3_done     (commit)
 //   warps 0-3   EPILOGUE2  D2[t%2] (TMEM) -> +bias, ReLU, fp16 -> H2 (B operand of M3)            -> d2_empty[t%2], h2_full
 //   warps 4-7   EPILOGUE3  D3 (TMEM, channel per lane) -> max over each centroid's 64 samples, +bias, ReLU -> out; d3_empty
@@ -40,8 +42,8 @@ struct WsCfg {
   static constexpr int OFF_W3 = OFF_W2 + W2_BYTES;
   static constexpr int OFF_H1 = OFF_W3 + W3_BYTES;          // two buffers
   static constexpr int OFF_H2 = OFF_H1 + 2 * H1_BYTES;
-  static constexpr int OFF_REL = OFF_H2 + H2_BYTES;          // float4[128]: rel xyz + q row index of each tile row
-  static constexpr int OFF_F = OFF_REL + 128 * 16;           // floats: b2[C2] | b3[C3]
+  static constexpr int OFF_REL = OFF_H2 + H2_BYTES;          // float4[2][128]: rel xyz + q row index of each tile row
+  static constexpr int OFF_F = OFF_REL + 2 * 128 * 16;           // floats: b2[C2] | b3[C3]
   static constexpr int OFF_BAR = OFF_F + (C2 + C3) * 4;
   static constexpr int SMEM = OFF_BAR + 16 * 8 + 16 + 1024;
   static constexpr int TM_D2 = 0;                            // two buffers of C2 columns
@@ -52,13 +54,26 @@ struct WsCfg {
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-constexpr int WS_THREADS = 13 * 32;
+constexpr int WS_THREADS = 17 * 32;
+constexpr int WS_PRODUCERS = 256;
+
+// relative coordinates (utils.py:51) and flat source-row index of every grouped row: rel[(g*64+s)] = {xyz[idx]-c, row}
+__global__ void group_rel_kernel(int n, int m, long long total_rows, const float* __restrict__ xyz,
+                                 const float* __restrict__ new_xyz, const int* __restrict__ idx,
+                                 float4* __restrict__ rel) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_rows) return;
+  const int g = (int)(t >> 6);
+  const int bi = g / m;
+  const int pid = idx[t];
+  const float* pp = xyz + ((size_t)bi * n + pid) * 3;
+  const float* cc = new_xyz + (size_t)g * 3;
+  rel[t] = make_float4(pp[0] - cc[0], pp[1] - cc[1], pp[2] - cc[2], __int_as_float(bi * n + pid));
+}
 
 template <int C1, int C2, int C3>
 __global__ void __launch_bounds__(WS_THREADS, 1) sa_ws_kernel(int n, int m, int total_centroids, int tiles_per_cta,
-                                                              const float* __restrict__ xyz,
-                                                              const float* __restrict__ new_xyz,
-                                                              const int* __restrict__ idx,
+                                                              const float4* __restrict__ rel,
                                                               const float* __restrict__ w1x /* (3,C1) */,
                                                               const float* __restrict__ b2, const float* __restrict__ b3,
                                                               const char* __restrict__ w2_img,
@@ -76,7 +91,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sa_ws_kernel(int n, int m, int 
   float* sB3 = sB2 + C2;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* bar_w = bars + 0;
-  uint64_t* h1_full = bars + 1;    // [2] 128 producer arrivals
+  uint64_t* h1_full = bars + 1;    // [2] 256 producer arrivals
   uint64_t* m2_done = bars + 3;    // [2] tcgen05.commit
   uint64_t* d2_empty = bars + 5;   // [2] 128 epilogue-2 arrivals
   uint64_t* h2_full = bars + 7;    //     128 epilogue-2 arrivals
@@ -88,7 +103,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sa_ws_kernel(int n, int m, int 
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&h1_full[s], 128); mbar_init(&m2_done[s], 1); mbar_init(&d2_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&h1_full[s], WS_PRODUCERS); mbar_init(&m2_done[s], 1); mbar_init(&d2_empty[s], 128); }
     mbar_init(h2_full, 128); mbar_init(m3_done, 1); mbar_init(d3_empty, 128);
     fence_barrier_init();
     mbar_arrive_expect_tx(bar_w, (uint32_t)(Cfg::W2_BYTES + Cfg::W3_BYTES));
@@ -109,37 +124,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sa_ws_kernel(int n, int m, int 
   const int first_tile = (int)blockIdx.x * tiles_per_cta;
   const int my_tiles = min(tiles_per_cta, ntiles - first_tile);
 
-  if (warp >= 8 && warp < 12) {
-    // ================================================================ PRODUCER (128 threads)
-    const int pt = tid - 256;          // 0..127
+  if (warp >= 8 && warp < 16) {
+    // ================================================================ PRODUCER (256 threads)
+    const int pt = tid - 256;          // 0..255
     const int chunk = pt & 15;         // 8 channels [8*chunk, 8*chunk+8)
-    const int rsub = pt >> 4;          // rows rsub, rsub+8, ...
+    const int rsub = pt >> 4;          // rows rsub, rsub+16, ...
     float wx[8], wy[8], wz[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       wx[i] = w1x[chunk * 8 + i]; wy[i] = w1x[C1 + chunk * 8 + i]; wz[i] = w1x[2 * C1 + chunk * 8 + i];
     }
+    float4 relreg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pt < 128 && my_tiles > 0) relreg = __ldg(rel + (size_t)first_tile * 128 + pt);
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = first_tile + t;
       const int s = t & 1;
-      {  // relative xyz and q-row index of this thread's tile row (row = pt)
-        const int g = tile * 2 + (pt >> 6);
-        const int bi = g / m;
-        const int pid = idx[(size_t)g * 64 + (pt & 63)];
-        const float* pp = xyz + ((size_t)bi * n + pid) * 3;
-        const float* cc = new_xyz + (size_t)g * 3;
-        named_bar_sync(1, 128);  // previous tile's readers of sRel are done
-        sRel[pt] = make_float4(pp[0] - cc[0], pp[1] - cc[1], pp[2] - cc[2], __int_as_float(bi * n + pid));  // utils.py:51
-        named_bar_sync(1, 128);
+      if (pt < 128) {
+        sRel[s * 128 + pt] = relreg;                                                    // this tile
+        if (t + 1 < my_tiles) relreg = __ldg(rel + (size_t)(tile + 1) * 128 + pt);      // prefetch the next
       }
+      named_bar_sync(1, WS_PRODUCERS);  // sRel[s] visible; its previous readers (tile t-2) passed the barrier of tile t-1
       if (t >= 2) mbar_wait(&m2_done[s], (uint32_t)(((t >> 1) - 1) & 1));  // M2(t-2) finished reading H1[s]
       uint8_t* h1 = sH1 + s * Cfg::H1_BYTES;
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int r = rsub + 8 * i;
-        const float4 rl = sRel[r];
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(q + (size_t)__float_as_int(rl.w) * C1) + chunk);
-        const __half2* hh = reinterpret_cast<const __half2*>(&raw);
+      const float4* srel = sRel + s * 128;
+      uint4 raw[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)  // all gathers first: 8 independent 16-byte loads in flight per thread
+        raw[i] = __ldg(reinterpret_cast<const uint4*>(q + (size_t)__float_as_int(srel[rsub + 16 * i].w) * C1) + chunk);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 16 * i;
+        const float4 rl = srel[r];
+        const __half2* hh = reinterpret_cast<const __half2*>(&raw[i]);
         float o[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -160,7 +176,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sa_ws_kernel(int n, int m, int 
       fence_proxy_async_smem();
       mbar_arrive(&h1_full[s]);
     }
-  } else if (warp == 12) {
+  } else if (warp == 16) {
     // ================================================================ MMA issuer (one thread)
     if (lane == 0 && my_tiles > 0) {
       mbar_wait(bar_w, 0);
@@ -238,32 +254,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sa_ws_kernel(int n, int m, int 
       const int tile = first_tile + t;
       mbar_wait(m3_done, (uint32_t)(t & 1));
       tc_fence_after_sync();
-      float res[C3 / 128][2];
+      // one (channel half, centroid) at a time, not unrolled: keeps a single 32-register TMEM load live
+#pragma unroll 1
+      for (int part = 0; part < (C3 / 128) * 2; ++part) {
+        const int hh = part >> 1, gq = part & 1;
+        float mval = -INFINITY;
+#pragma unroll 1
+        for (int cb = 0; cb < 64; cb += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem + lane_base + Cfg::TM_D3 + hh * 128 + gq * 64 + cb, v);
+          tmem_ld_wait();
 #pragma unroll
-      for (int hh = 0; hh < C3 / 128; ++hh) {
-#pragma unroll
-        for (int gq = 0; gq < 2; ++gq) {
-          float mval = -INFINITY;
-#pragma unroll
-          for (int cb = 0; cb < 64; cb += 32) {
-            uint32_t v[32];
-            tmem_ld_x32(tmem + lane_base + Cfg::TM_D3 + hh * 128 + gq * 64 + cb, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mval = fmaxf(mval, __uint_as_float(v[i]));
-          }
-          res[hh][gq] = mval;
+          for (int i = 0; i < 32; ++i) mval = fmaxf(mval, __uint_as_float(v[i]));
         }
+        const int ch = hh * 128 + et;
+        // bias + ReLU commute with the max (both monotone)
+        out[((size_t)tile * 2 + gq) * C3 + ch] = fmaxf(mval + sB3[ch], 0.f);
       }
       tc_fence_before_sync();
-      mbar_arrive(d3_empty);  // D3 is free for M3(t+1) before the global stores
-#pragma unroll
-      for (int hh = 0; hh < C3 / 128; ++hh) {
-        const int ch = hh * 128 + et;
-        const float bb = sB3[ch];  // bias + ReLU commute with the max (both monotone)
-        out[((size_t)tile * 2 + 0) * C3 + ch] = fmaxf(res[hh][0] + bb, 0.f);
-        out[((size_t)tile * 2 + 1) * C3 + ch] = fmaxf(res[hh][1] + bb, 0.f);
-      }
+      mbar_arrive(d3_empty);  // D3 is free for M3(t+1)
     }
   }
   tc_fence_before_sync();
@@ -271,10 +280,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sa_ws_kernel(int n, int m, int 
   if (warp == 0) tmem_dealloc(tmem, Cfg::TM_COLS);
 }
 
+void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx, void* rel,
+                      cudaStream_t st) {
+  group_rel_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(n, m, rows, xyz, new_xyz, idx, static_cast<float4*>(rel));
+}
+
 template <int C1, int C2, int C3>
 static int launch_ws(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, const float* w1x,
                      const float* b2, const float* b3, const void* w2_img, const void* w3_img, const void* q, float* out,
-                     cudaStream_t st) {
+                     void* workspace, cudaStream_t st) {
   using Cfg = WsCfg<C1, C2, C3>;
   auto kern = sa_ws_kernel<C1, C2, C3>;
   VNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -282,10 +296,14 @@ static int launch_ws(int b, int n, int m, const float* xyz, const float* new_xyz
   VNB_CUDA(cudaGetDevice(&dev));
   VNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int ntiles = b * m / 2;
+  float4* rel = static_cast<float4*>(workspace);
+  const long long rows = (long long)b * m * 64;
+  group_rel_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(n, m, rows, xyz, new_xyz, idx, rel);
+  if (int rc = check_launch("sa_group_mlp_max: grouped relative coordinates")) return rc;
   int tpc = ntiles / (2 * sms);
   tpc = tpc < 2 ? 2 : (tpc > 16 ? 16 : tpc);
   const int grid = (ntiles + tpc - 1) / tpc;
-  kern<<<grid, WS_THREADS, Cfg::SMEM, st>>>(n, m, b * m, tpc, xyz, new_xyz, idx, w1x, b2, b3, static_cast<const char*>(w2_img),
+  kern<<<grid, WS_THREADS, Cfg::SMEM, st>>>(n, m, b * m, tpc, rel, w1x, b2, b3, static_cast<const char*>(w2_img),
                                             static_cast<const char*>(w3_img), static_cast<const __half*>(q), out);
   return check_launch("sa_group_mlp_max (tcgen05, warp-specialised)");
 }
@@ -293,11 +311,12 @@ static int launch_ws(int b, int n, int m, const float* xyz, const float* new_xyz
 // returns -1 when no instance matches
 int sa_ws_dispatch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, int c1, int c2, int c3,
                    const float* w1x, const float* b2, const float* b3, const void* w2_img, const void* w3_img,
-                   const void* q, float* out, cudaStream_t st) {
+                   const void* q, float* out, void* workspace, cudaStream_t st) {
+  if (workspace == nullptr) return -1;
   if (c1 == 128 && c2 == 128 && c3 == 256)
-    return launch_ws<128, 128, 256>(b, n, m, xyz, new_xyz, idx, w1x, b2, b3, w2_img, w3_img, q, out, st);
+    return launch_ws<128, 128, 256>(b, n, m, xyz, new_xyz, idx, w1x, b2, b3, w2_img, w3_img, q, out, workspace, st);
   if (c1 == 128 && c2 == 128 && c3 == 128)
-    return launch_ws<128, 128, 128>(b, n, m, xyz, new_xyz, idx, w1x, b2, b3, w2_img, w3_img, q, out, st);
+    return launch_ws<128, 128, 128>(b, n, m, xyz, new_xyz, idx, w1x, b2, b3, w2_img, w3_img, q, out, workspace, st);
   return -1;
 }
 

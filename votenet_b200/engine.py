@@ -143,6 +143,8 @@ class Engine:
         s.p_h = [E((B * p.npoint, co)) for co in p.mlp2]
         s.rec = DetectionRecord(B, p.npoint, dev)
         s.nms_ws = torch.empty((lib.vnb_nms3d_workspace_bytes(B, p.npoint),), dtype=torch.uint8, device=dev)
+        mmax = max(max(sa.npoint for sa in cfg.sa), cfg.proposal.npoint)
+        s.sa_ws = torch.empty((lib.vnb_sa_workspace_bytes(B, mmax, 64),), dtype=torch.uint8, device=dev)
         s.fps_ws = torch.empty((lib.vnb_fps_nested_workspace_bytes(B, max(sa.npoint for sa in cfg.sa)),), dtype=torch.uint8, device=dev)
         s.done = torch.cuda.Event()
         s.samp = torch.cuda.Stream(device=dev)   # sampling chain (FPS + gathers)
@@ -157,7 +159,7 @@ class Engine:
                              dptr(layer.img) if self.precision == PRECISION_TENSOR else None, dptr(layer.b),
                              dptr(residual), 1 if act else 0, dptr(out32), dptr(out16), int(self.precision), _sp(st)))
 
-    def _sa(self, li, xyz, feat, n, c, new_xyz, idx, m, q, out, st):
+    def _sa(self, li, xyz, feat, n, c, new_xyz, idx, m, q, out, st, ws=None):
         l1, l2, l3, lf, _ = self.sa_layers[li]
         B = self.B
         tc = self.precision == PRECISION_TENSOR
@@ -167,7 +169,7 @@ class Engine:
                                        l3.cout, dptr(l1.W), dptr(l1.b), dptr(l2.W), dptr(l2.b), dptr(l3.W), dptr(l3.b),
                                        dptr(l1.img) if (tc and lf is None) else None, dptr(l2.img) if tc else None,
                                        dptr(l3.img) if tc else None, dptr(q) if lf is not None else None, dptr(out),
-                                       int(self.precision), _sp(st)))
+                                       int(self.precision), dptr(ws), _sp(st)))
 
     def _enqueue(self, s, main):
         """Enqueue one forward over slot `s`: sampling chain on s_samp, neighbour searches on s_aux, features on main."""
@@ -220,7 +222,7 @@ class Engine:
         for li, l in enumerate(s.lv):
             main.wait_event(e_bq[li])
             mark(f"sa{li + 1}_begin", main)
-            self._sa(li, src_xyz, src_feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, main)
+            self._sa(li, src_xyz, src_feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, main, s.sa_ws)
             mark(f"sa{li + 1}", main)
             src_xyz, src_feat, c = l.xyz, l.feat, cfg.sa[li].mlp[-1]
         main.wait_event(e_nn)
@@ -249,7 +251,7 @@ class Engine:
         check(lib.vnb_gather_point(B, ns, p.npoint, dptr(s.votes_xyz), dptr(s.p_fps), dptr(s.p_xyz), _sp(main)))
         check(lib.vnb_query_ball_point(B, ns, p.npoint, float(p.radius), 64, dptr(s.votes_xyz), dptr(s.p_xyz),
                                        dptr(s.p_idx), dptr(s.p_cnt), _sp(main)))
-        self._sa(len(cfg.sa), s.votes_xyz, s.votes_feat, ns, cf, s.p_xyz, s.p_idx, p.npoint, s.p_q, s.p_feat, main)
+        self._sa(len(cfg.sa), s.votes_xyz, s.votes_feat, ns, cf, s.p_xyz, s.p_idx, p.npoint, s.p_q, s.p_feat, main, s.sa_ws)
         x = s.p_feat
         for i in range(len(p.mlp2)):
             self._linear(B * p.npoint, x, self.store.layer(f"proposal/conv_post_{i}"), i < len(p.mlp2) - 1, s.p_h[i], None,

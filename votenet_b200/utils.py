@@ -88,7 +88,9 @@ def sa_group_mlp_max(xyz, points, new_xyz, idx, layers, precision, store=None, s
     out = torch.empty((b, m, l3.cout), dtype=torch.float32, device=xyz.device)
     q = None
     w1_img = w2_img = w3_img = None
+    ws = None
     if precision == PRECISION_TENSOR:
+        ws = torch.empty((lib.vnb_sa_workspace_bytes(b, m, ns),), dtype=torch.uint8, device=xyz.device)
         w2_img, w3_img = l2.img, l3.img
         if c >= HOIST_MIN_C:
             # layer 1 hoisted through the gather: q = feat @ W1[3:] + b1, once per source point, fp16
@@ -100,7 +102,7 @@ def sa_group_mlp_max(xyz, points, new_xyz, idx, layers, precision, store=None, s
                                    dptr(new_xyz, torch.float32, "new_xyz"), dptr(idx, torch.int32, "idx"), l1.cout,
                                    l2.cout, l3.cout, dptr(l1.W), dptr(l1.b), dptr(l2.W), dptr(l2.b), dptr(l3.W),
                                    dptr(l3.b), dptr(w1_img), dptr(w2_img), dptr(w3_img), dptr(q), dptr(out),
-                                   int(precision), stream_ptr()))
+                                   int(precision), dptr(ws), stream_ptr()))
     return out
 
 
