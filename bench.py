@@ -172,8 +172,8 @@ def kernel_table(eng, cfg, peaks, flush):
         byt = B * (l.m - 1) * l.n * 16
         rows.append(dict(kernel=f"fps_sa{li + 1}", ms=ms, bound="hbm(streaming-equivalent; on-chip kernel)", algo_bytes=byt,
                          achieved=byt / ms / 1e6, peak=peaks["hbm"], unit="GB/s"))
-        ms = t(lambda: check(lib.vnb_query_ball_point(B, l.n, l.m, float(sa.radius), 64, dptr(src), dptr(l.xyz), dptr(l.idx),
-                                                      dptr(l.cnt), stream_ptr())))
+        ms = t(lambda: check(lib.vnb_query_ball_point_ws(B, l.n, l.m, float(sa.radius), 64, dptr(src), dptr(l.xyz), dptr(l.idx),
+                                                         dptr(l.cnt), dptr(l.bq_ws), stream_ptr())))
         byt = B * (l.n * 12 + l.m * 12 + l.m * 256 + l.m * 4)
         rows.append(dict(kernel=f"ball_query_sa{li + 1}", ms=ms, bound="hbm", algo_bytes=byt, achieved=byt / ms / 1e6,
                          peak=peaks["hbm"], unit="GB/s"))
@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=8, help="steps in flight (independent workspaces + streams)")
     ap.add_argument("--fps-cluster", type=int, default=4,
                     help="CTAs per FPS cluster (4 = 32 SMs per batch: best throughput with steps overlapped; 8 = lowest latency)")
+    ap.add_argument("--fps-variant", type=int, default=None, help="0: register/cluster FPS kernel, 1: bucket-pruned (default)")
     ap.add_argument("--fps-threads", type=int, default=None, help="tuning: threads per FPS CTA (256/512/1024)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -233,6 +234,8 @@ def main():
         _check(lib.vnb_set_tuning(b"fps_cluster", args.fps_cluster))
     if args.fps_threads is not None:
         _check(lib.vnb_set_tuning(b"fps_threads", args.fps_threads))
+    if args.fps_variant is not None:
+        _check(lib.vnb_set_tuning(b"fps_variant", args.fps_variant))
     peaks = _peaks()
     cfg = VoteNetConfig()  # BASELINE.json: 20 000 points, (xyz + height)
     B, N = CLOUDS_PER_RANK, cfg.num_points

@@ -1,0 +1,114 @@
+"""GPU parity tests (`-m gpu`) of the bucket-pruned FPS kernel (csrc/fps_pruned.cu) through the C ABI: the index
+sequence must be bit-identical to the CPU oracle (oracle/oracle.c restating tf_sampling_g.cu:105-170) and to the
+register/cluster kernel for every input — random, clustered, tie-laden, duplicated, padded, m > n."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a, dev):
+    return torch.as_tensor(np.ascontiguousarray(a), device=dev)
+
+
+@pytest.fixture()
+def variant():
+    """Sets the FPS variant for one test and restores the default afterwards."""
+    from votenet_b200._lib import check, lib
+
+    def set_variant(v):
+        check(lib.vnb_set_tuning(b"fps_variant", int(v)))
+
+    yield set_variant
+    set_variant(1)
+
+
+def fps(m, x, dev):
+    from votenet_b200.tf_sampling import farthest_point_sample
+
+    return farthest_point_sample(m, T(x, dev)).cpu().numpy()
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (2, 2), (3, 5), (31, 31), (33, 7), (160, 160), (161, 50), (512, 128), (513, 64),
+                                 (1024, 256), (2048, 1024), (2561, 300), (3000, 64), (4096, 300), (5000, 200),
+                                 (8192, 64), (16384, 333), (20000, 256), (20479, 100), (20480, 128)])
+def test_pruned_matches_oracle_uniform(cuda, variant, n, m):
+    variant(2)  # pruned kernel for every n
+    rng = np.random.default_rng(n * 31 + m)
+    x = rng.random((3, n, 3), dtype=np.float32) * 4 - 2
+    got = fps(m, x, cuda)
+    assert got.dtype == np.int32 and got.shape == (3, m)
+    assert np.array_equal(got, O.farthest_point_sample(m, x))
+
+
+def test_pruned_ties_duplicates_lattice(cuda, variant):
+    variant(2)
+    x = np.zeros((2, 700, 3), np.float32)
+    x[0, 600] = (1, 0, 0); x[0, 100] = (1, 0, 0)          # 600 mod 512 = 88 < 100 -> 600 wins
+    x[1, 612] = (1, 0, 0); x[1, 100] = (1, 0, 0)          # same slot -> lower k wins
+    got = fps(5, x, cuda)
+    assert np.array_equal(got, O.farthest_point_sample(5, x))
+    assert got[0, 1] == 600 and got[1, 1] == 100
+    rng = np.random.default_rng(0)
+    # lattice clouds: massive exact ties in every round, at several sizes (ties inside a lane, a warp, across warps)
+    for n, m, levels in ((3000, 400, 6), (20000, 700, 12), (8000, 500, 3), (640, 640, 4)):
+        lat = (rng.integers(0, levels, (2, n, 3)) / 4).astype(np.float32)
+        assert np.array_equal(fps(m, lat, cuda), O.farthest_point_sample(m, lat)), (n, m, levels)
+    # every point identical; and more samples than points
+    same = np.full((2, 5000, 3), 0.25, np.float32)
+    assert np.array_equal(fps(64, same, cuda), O.farthest_point_sample(64, same))
+    few = rng.random((2, 40, 3), dtype=np.float32)
+    assert np.array_equal(fps(100, few, cuda), O.farthest_point_sample(100, few))
+    # planar / collinear clouds (degenerate bounding boxes: zero extent along one or two axes)
+    flat = rng.random((2, 6000, 3), dtype=np.float32); flat[:, :, 1] = 1.2
+    assert np.array_equal(fps(300, flat, cuda), O.farthest_point_sample(300, flat))
+    line = np.zeros((2, 4000, 3), np.float32); line[:, :, 2] = rng.random((2, 4000), dtype=np.float32)
+    assert np.array_equal(fps(300, line, cuda), O.farthest_point_sample(300, line))
+
+
+def test_pruned_clustered_and_far_outliers(cuda, variant):
+    variant(2)
+    rng = np.random.default_rng(7)
+    # tight clusters + a few far outliers: most sub-buckets skip from the very first rounds
+    c = rng.normal(0, 0.01, (2, 12000, 3)).astype(np.float32) + rng.integers(0, 3, (2, 12000, 3)).astype(np.float32) * 5
+    c[:, :7] = rng.uniform(-100, 100, (2, 7, 3)).astype(np.float32)
+    assert np.array_equal(fps(512, c, cuda), O.farthest_point_sample(512, c))
+    # negative / large magnitude coordinates
+    big = (rng.random((2, 9000, 3), dtype=np.float32) - 0.5) * 2000
+    assert np.array_equal(fps(256, big, cuda), O.farthest_point_sample(256, big))
+
+
+def test_pruned_full_size_equals_oracle_and_cluster_kernel(cuda, variant):
+    """BASELINE shape: 8 clouds x 20000 -> 2048 (and the reference's POINT_NUM 20480) on SUN-RGB-D-shaped clouds."""
+    from votenet_b200 import synth
+
+    xyz = synth.synthetic_batch(0, 8, 20000)
+    variant(1)
+    a = fps(2048, xyz, cuda)          # default path (pruned for n > 2048)
+    variant(0)
+    b = fps(2048, xyz, cuda)          # register/cluster kernel
+    assert np.array_equal(a, b)
+    assert np.array_equal(a[:3], O.farthest_point_sample(2048, xyz[:3]))
+    for row in a:
+        assert len(set(row.tolist())) == 2048 and row[0] == 0  # a permutation prefix starting at 0
+    xyz2 = synth.synthetic_batch(100, 2, 20480)
+    variant(1)
+    assert np.array_equal(fps(2048, xyz2, cuda), O.farthest_point_sample(2048, xyz2))
+
+
+def test_pruned_nested_fallback_flags(cuda, variant):
+    """vnb_farthest_point_sample_nested falls back to the sequential sampler (with per-cloud done flags) when the
+    identity-prefix proof fails: exercise that path with the pruned kernel."""
+    from votenet_b200.tf_sampling import farthest_point_sample_nested
+
+    variant(2)
+    rng = np.random.default_rng(3)
+    x = rng.random((4, 3000, 3), dtype=np.float32)          # not FPS-ordered: the proof fails for every cloud
+    ordered = O.gather_point(x, O.farthest_point_sample(3000, x))[:2]   # FPS-ordered: the proof succeeds
+    mix = np.concatenate([ordered, x[2:]], 0)
+    got = farthest_point_sample_nested(500, T(mix, cuda)).cpu().numpy()
+    assert np.array_equal(got, O.farthest_point_sample(500, mix))
+    assert np.array_equal(got[0], np.arange(500))

@@ -21,6 +21,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 SOURCES = {
     "point_ops.cu": [],
     "fps.cu": [],
+    "fps_pruned.cu": [],
     "ball_query_grid.cu": [],
     "nms3d.cu": ["-fmad=false"],
     "mlp_simt.cu": [],

@@ -27,7 +27,7 @@
 // 0..m-1 unless exact float ties reorder it.  vnb_farthest_point_sample_nested proves that per cloud
 // with a fully PARALLEL check (every round's arg-max condition is independent once the picks are hypothesised) and
 // only falls back to the sequential kernel for clouds where the proof fails — the output is always bit-identical.
-#include "common.cuh"
+#include "fps_common.cuh"
 
 #include <string_view>
 
@@ -38,49 +38,11 @@ extern int g_sa_variant;
 int g_fps_mode = 1;   // 0: cluster barrier per round, 1: CTA champions in tagged slots + polling (default)
 int g_fps_cl = 0;     // 0: automatic cluster size, else forced (power of two <= 16)
 int g_fps_threads = 256;  // threads per CTA of the cluster kernel (256 / 512 / 1024)
+int g_fps_variant = 1;    // 0: register/cluster kernel only; 1: bucket-pruned single-CTA kernel for 2048 < n <= 20480;
+                          // 2: bucket-pruned kernel for every n <= 20480
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void st_cluster_v2(uint32_t raddr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(raddr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
-  uint4 v;
-  asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint2 ld_volatile_v2(const void* p) {
-  uint2 v;
-  asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_addr(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t redux_max(uint32_t v) {
-  uint32_t r;
-  asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
-  return r;
-}
-
-// 16-bit tie key: bit 15 = valid, low 15 bits = 0x7FFF - (((k & 511) << 6) | (k >> 9)); larger wins.
-__device__ __forceinline__ uint32_t tie_key(int k) { return 0x8000u | (0x7FFFu - ((((uint32_t)k & 511u) << 6) | ((uint32_t)k >> 9))); }
-__device__ __forceinline__ int tie_key_to_index(uint32_t key) {
-  uint32_t t = 0x7FFFu - (key & 0x7FFFu);
-  return (int)((t >> 6) | ((t & 63u) << 9));
-}
+int fps_pruned_capacity();
+int launch_fps_pruned(int b, int n, int m, const float* xyz, int* out, const int* flags, cudaStream_t st);
 
 // T threads per CTA, P points per thread, CL CTAs per cluster (launch attribute, CL*T % 512 == 0); W = T/32 warps.
 // MODE 0: cluster barrier per round; MODE 1: tagged slots, receivers poll their own shared memory.
@@ -360,6 +322,8 @@ static int fps_dispatch_t(int b, int n, int m, int CL, const float* xyz, int* ou
 // CTAs minimise the SM footprint of one call (better throughput when several calls overlap); many small CTAs minimise
 // the latency of one call.  CL*T must be a multiple of 512 (per-thread tie rule, see the header comment).
 static int fps_dispatch(int b, int n, int m, const float* xyz, int* out, const int* flags, cudaStream_t st) {
+  if (n <= fps_pruned_capacity() && ((g_fps_variant == 1 && n > 2048) || g_fps_variant == 2))
+    return launch_fps_pruned(b, n, m, xyz, out, flags, st);
   int T = g_fps_threads;
   int CL = g_fps_cl;
   if (n <= 2048 && CL <= 1) {  // small clouds: one CTA of 512 threads
@@ -388,6 +352,7 @@ extern "C" int vnb_set_tuning(const char* key, int value) {
   if (k == "fps_mode") g_fps_mode = value;
   else if (k == "fps_cluster") g_fps_cl = value;
   else if (k == "fps_threads") g_fps_threads = value;
+  else if (k == "fps_variant") g_fps_variant = value;
   else if (k == "ball_query_variant") vnb::g_bq_variant = value;
   else if (k == "sa_variant") vnb::g_sa_variant = value;
   else return set_err(VNB_ERR_INVALID, "set_tuning: unknown key %s", key);
