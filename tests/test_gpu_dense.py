@@ -153,8 +153,9 @@ def test_decode_boxes(cuda):
 
 
 def test_sa_kernel_variants_agree(cuda):
-    """The warp-specialised pipelined kernel (sa_ws.cu) and the single-role kernel perform the same arithmetic in the same
-    order: bit-identical outputs.  Also exercises many tiles per CTA (ring of barriers wraps many times)."""
+    """The warp-specialised pipelined kernels (first generation sa_ws.cu / sa1_ws.cu, second generation sa_ws2.cu /
+    sa1_ws2.cu) and the single-role kernel perform the same arithmetic in the same order: bit-identical outputs.  Also
+    exercises many tiles per CTA (rings of barriers wrap many times) and CTAs with ragged tile counts."""
     from votenet_b200._lib import check, lib
     from votenet_b200.utils import WeightStore, sa_group_mlp_max
 
@@ -166,11 +167,12 @@ def test_sa_kernel_variants_agree(cuda):
         args = (T(xyz, cuda), T(feat, cuda), T(new_xyz, cuda), T(idx, cuda), layers, 1, store, "s")
         outs = []
         try:
-            for v in (0, 1):
+            for v in (0, 1, 2):
                 check(lib.vnb_set_tuning(b"sa_variant", v))
                 outs.append(sa_group_mlp_max(*args))
                 torch.cuda.synchronize()
         finally:
-            check(lib.vnb_set_tuning(b"sa_variant", 1))
+            check(lib.vnb_set_tuning(b"sa_variant", 2))
         assert torch.equal(outs[0], outs[1])
-        assert rel_err(outs[1].cpu().numpy(), ref.numpy()) < TOL_TC
+        assert torch.equal(outs[0], outs[2])
+        assert rel_err(outs[2].cpu().numpy(), ref.numpy()) < TOL_TC

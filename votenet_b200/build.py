@@ -27,7 +27,9 @@ SOURCES = {
     "mlp_simt.cu": [],
     "mlp_tc.cu": [],
     "sa_ws.cu": [],
+    "sa_ws2.cu": [],
     "sa1_ws.cu": [],
+    "sa1_ws2.cu": [],
     "linear_tc.cu": [],
 }
 

@@ -33,9 +33,16 @@ int sa_ws_dispatch(int b, int n, int m, const float* xyz, const float* new_xyz, 
 int sa1_ws_dispatch(int b, int n, int c, int m, const float* xyz, const float* feat, const float* new_xyz, const int* idx,
                     int c1, int c2, int c3, const float* b1, const float* b2, const float* b3, const void* w1_img,
                     const void* w2_img, const void* w3_img, float* out, void* workspace, cudaStream_t st);
+int sa_ws2_dispatch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, int c1, int c2, int c3,
+                    const float* w1x, const float* b2, const float* b3, const void* w2_img, const void* w3_img,
+                    const void* q, float* out, void* workspace, cudaStream_t st);  // sa_ws2.cu
+int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* feat, const float* new_xyz, const int* idx,
+                     int c1, int c2, int c3, const float* b1, const float* b2, const float* b3, const void* w1_img,
+                     const void* w2_img, const void* w3_img, float* out, void* workspace, cudaStream_t st);  // sa1_ws2.cu
 int linear_tc(int rows, int cin, int cout, const float* in, const void* w_img, const float* bias, const float* res,
               int act, float* out_f32, void* out_f16, cudaStream_t st);  // linear_tc.cu
-int g_sa_variant = 1;  // 0: single-role kernel (sa_tc_kernel), 1: warp-specialised pipeline (sa_ws.cu) where available
+int g_sa_variant = 2;  // 0: single-role kernel (sa_tc_kernel), 1: warp-specialised pipeline, first generation,
+                       // 2: second generation (one MMA issuer per layer, one wave) where available
 
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(int cin, int cout, int k_pad, int n_pad, const float* __restrict__ w,
@@ -392,7 +399,12 @@ extern "C" int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, con
   const bool hoist = c > 13;
   if (!hoist) {
     VNB_REQUIRE(w1_img != nullptr, "sa_group_mlp_max(tensor cores): w1_img missing");
-    if (g_sa_variant == 1) {  // warp-specialised, pipelined kernel (sa1_ws.cu)
+    if (g_sa_variant >= 2) {  // second-generation pipeline (sa1_ws2.cu)
+      int rc = sa1_ws2_dispatch(b, n, c, m, xyz, feat, new_xyz, idx, c1, c2, c3, b1, b2, b3, w1_img, w2_img, w3_img, out,
+                                workspace, st);
+      if (rc >= 0) return rc;
+    }
+    if (g_sa_variant >= 1) {  // warp-specialised, pipelined kernel (sa1_ws.cu)
       int rc = sa1_ws_dispatch(b, n, c, m, xyz, feat, new_xyz, idx, c1, c2, c3, b1, b2, b3, w1_img, w2_img, w3_img, out,
                                workspace, st);
       if (rc >= 0) return rc;
@@ -403,7 +415,11 @@ extern "C" int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, con
   } else {
     VNB_REQUIRE(q_f16 != nullptr && w1_f32 != nullptr,
                 "sa_group_mlp_max(tensor cores): hoisted layer 1 needs q_f16 and w1_f32 (rows 0..2)");
-    if (g_sa_variant == 1) {  // warp-specialised, pipelined kernel (sa_ws.cu)
+    if (g_sa_variant >= 2) {  // second-generation pipeline (sa_ws2.cu)
+      int rc = sa_ws2_dispatch(b, n, m, xyz, new_xyz, idx, c1, c2, c3, w1_f32, b2, b3, w2_img, w3_img, q_f16, out, workspace, st);
+      if (rc >= 0) return rc;
+    }
+    if (g_sa_variant >= 1) {  // warp-specialised, pipelined kernel (sa_ws.cu)
       int rc = sa_ws_dispatch(b, n, m, xyz, new_xyz, idx, c1, c2, c3, w1_f32, b2, b3, w2_img, w3_img, q_f16, out, workspace, st);
       if (rc >= 0) return rc;
     }

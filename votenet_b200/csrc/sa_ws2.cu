@@ -1,0 +1,331 @@
+// Fused set-abstraction kernel with hoisted layer 1 (sa2..sa4, proposal), second generation.
+//
+// Same arithmetic as sa_ws_kernel (sa_ws.cu) — group -> relu(q[idx] + W1x^T rel_xyz) -> L2 -> L3 -> max-pool
+// (reference utils.py:49-55,120-132) — with the serialisations of the first generation removed:
+//   * layer 3 is issued K-CHUNK-MAJOR (k-steps of chunk 0 for both channel halves, then chunk 1, ...) and H2 is handed
+//     over in four 32-column chunks, each with its own full/free mbarrier pair: the tensor pipe starts M3(t) when the
+//     first quarter of H2(t) exists and EPILOGUE2(t+1) refills a chunk as soon as M3(t) has consumed it, so E2 and M3
+//     overlap although H2 is single-buffered (shared memory is full);
+//   * layers 2 and 3 have separate issuing warps: M2(t+1) never waits behind M3(t)'s operands or vice versa;
+//   * EPILOGUE3 uses two warps per TMEM lane quadrant (a warp pulls at most 64 B/cycle out of TMEM) and drains D3 in
+//     ~350 cycles, hidden behind M2 on the tensor pipe;
+//   * all TMEM loads of a stage are in flight before the first wait; packed fp32x2 math (FFMA2 / FADD2) and fp16x2 ReLU;
+//   * one wave: one CTA per SM, contiguous chunks of tiles (one prologue, one pipeline fill per SM).
+//
+//   warps 0-3    EPILOGUE2  D2[t%2] -> +b2, ReLU, fp16 -> H2 chunk by chunk
+//   warps 4-11   EPILOGUE3  D3 (channel per lane) -> max over a centroid's 64 samples, +b3, ReLU -> out
+//   warps 12-19  PRODUCER   gather q rows (16 threads per row, 8 independent 16-byte loads in flight per thread, issued
+//                           BEFORE the wait for the H1 buffer), + rank-3 relative-xyz term, ReLU, fp16 -> H1[t%2]
+//   warp  20     MMA2       D2[t%2] = H1[t%2] . W2^T
+//   warp  21     MMA3       D3 = W3^T . H2^T   (transposed; chunk-major)
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace vnb {
+
+using namespace umma;
+
+namespace s2v2 {
+
+template <int C1, int C2, int C3>
+struct Cfg {
+  static_assert(C1 == 128 && C2 == 128 && (C3 == 128 || C3 == 256), "instances: (128,128,256) and (128,128,128)");
+  static constexpr int P1 = C1 / 64, P2 = C2 / 64;
+  static constexpr int W2_BYTES = P1 * C2 * 128;
+  static constexpr int W3_BYTES = P2 * C3 * 128;
+  static constexpr int H1_BYTES = P1 * 128 * 128;   // per buffer
+  static constexpr int H2_BYTES = P2 * 128 * 128;
+  static constexpr int OFF_W2 = 0;
+  static constexpr int OFF_W3 = OFF_W2 + W2_BYTES;
+  static constexpr int OFF_H1 = OFF_W3 + W3_BYTES;          // two buffers
+  static constexpr int OFF_H2 = OFF_H1 + 2 * H1_BYTES;
+  static constexpr int OFF_REL = OFF_H2 + H2_BYTES;          // float4[2][128]: rel xyz + q row index of each tile row
+  static constexpr int OFF_F = OFF_REL + 2 * 128 * 16;       // floats: b2[C2] | b3[C3]
+  static constexpr int OFF_BAR = OFF_F + (C2 + C3) * 4;
+  static constexpr int SMEM = OFF_BAR + 32 * 8 + 16 + 1024;
+  static constexpr int TM_D2 = 0;                            // two buffers of C2 columns
+  static constexpr int TM_D3 = 2 * C2;
+  static constexpr int TM_COLS = 512;
+  static_assert(TM_D3 + C3 <= 512, "TMEM budget");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static constexpr int NCHUNK = C2 / 32;                     // H2 hand-over granularity: 32 columns = 2 k-steps
+};
+
+constexpr int THREADS = 22 * 32;
+constexpr int PRODUCERS = 256;
+
+__device__ __forceinline__ uint32_t pack_relu(float2 v) {  // fp16x2(max(v, 0)): rounding is monotone, so relu commutes
+  __half2 h = __hmax2(__float22half2_rn(v), __float2half2_rn(0.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int C1, int C2, int C3>
+__global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids, int tiles_per_cta,
+                                                            const float4* __restrict__ rel,
+                                                            const float* __restrict__ w1x /* (3,C1) */,
+                                                            const float* __restrict__ b2, const float* __restrict__ b3,
+                                                            const char* __restrict__ w2_img,
+                                                            const char* __restrict__ w3_img,
+                                                            const __half* __restrict__ q, float* __restrict__ out) {
+  using K = Cfg<C1, C2, C3>;
+  constexpr int NCH = K::NCHUNK;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW2 = smem + K::OFF_W2;
+  uint8_t* sW3 = smem + K::OFF_W3;
+  uint8_t* sH1 = smem + K::OFF_H1;
+  uint8_t* sH2 = smem + K::OFF_H2;
+  float4* sRel = reinterpret_cast<float4*>(smem + K::OFF_REL);
+  float* sB2 = reinterpret_cast<float*>(smem + K::OFF_F);
+  float* sB3 = sB2 + C2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);
+  uint64_t* bar_w = bars + 0;
+  uint64_t* h1_full = bars + 1;     // [2]   256 producer arrivals
+  uint64_t* m2_done = bars + 3;     // [2]   tcgen05.commit
+  uint64_t* d2_empty = bars + 5;    // [2]   128 epilogue-2 arrivals
+  uint64_t* h2c_full = bars + 7;    // [NCH] 128 epilogue-2 arrivals: chunk c of H2(t) written
+  uint64_t* m3c_done = bars + 11;   // [NCH] tcgen05.commit: M3(t) has consumed chunk c (the last one == D3(t) complete)
+  uint64_t* d3_empty = bars + 15;   //       256 epilogue-3 arrivals
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 32);
+  static_assert(NCH == 4, "barrier table laid out for 4 chunks");
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&h1_full[s], PRODUCERS); mbar_init(&m2_done[s], 1); mbar_init(&d2_empty[s], 128); }
+    for (int c = 0; c < NCH; ++c) { mbar_init(&h2c_full[c], 128); mbar_init(&m3c_done[c], 1); }
+    mbar_init(d3_empty, 256);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bar_w, (uint32_t)(K::W2_BYTES + K::W3_BYTES));
+    bulk_g2s(sW2, w2_img, K::W2_BYTES, bar_w);
+    bulk_g2s(sW3, w3_img, K::W3_BYTES, bar_w);
+  }
+  for (int i = tid; i < C2; i += THREADS) sB2[i] = b2[i];
+  for (int i = tid; i < C3; i += THREADS) sB3[i] = b3[i];
+  if (warp == 0) tmem_alloc(tmem_ptr, K::TM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_ptr;
+
+  const int ntiles = total_centroids / 2;
+  const int first_tile = (int)blockIdx.x * tiles_per_cta;
+  const int my_tiles = max(0, min(tiles_per_cta, ntiles - first_tile));
+
+  if (warp >= 12 && warp < 20) {
+    // ================================================================ PRODUCER (256 threads)
+    const int pt = tid - 384;          // 0..255
+    const int chunk = pt & 15;         // 8 channels [8*chunk, 8*chunk+8)
+    const int rsub = pt >> 4;          // rows rsub, rsub+16, ...
+    float2 wx[4], wy[4], wz[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      wx[i] = make_float2(w1x[chunk * 8 + 2 * i], w1x[chunk * 8 + 2 * i + 1]);
+      wy[i] = make_float2(w1x[C1 + chunk * 8 + 2 * i], w1x[C1 + chunk * 8 + 2 * i + 1]);
+      wz[i] = make_float2(w1x[2 * C1 + chunk * 8 + 2 * i], w1x[2 * C1 + chunk * 8 + 2 * i + 1]);
+    }
+    float4 relreg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pt < 128 && my_tiles > 0) relreg = __ldg(rel + (size_t)first_tile * 128 + pt);
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = first_tile + t;
+      const int s = t & 1;
+      if (pt < 128) {
+        sRel[s * 128 + pt] = relreg;                                                    // this tile
+        if (t + 1 < my_tiles) relreg = __ldg(rel + (size_t)(tile + 1) * 128 + pt);      // prefetch the next
+      }
+      named_bar(1, PRODUCERS);  // sRel[s] visible; its previous readers (tile t-2) passed the barrier of tile t-1
+      const float4* srel = sRel + s * 128;
+      uint4 raw[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)  // all gathers first: 8 independent 16-byte loads in flight per thread
+        raw[i] = __ldg(reinterpret_cast<const uint4*>(q + (size_t)__float_as_int(srel[rsub + 16 * i].w) * C1) + chunk);
+      if (t >= 2) mbar_wait(&m2_done[s], (uint32_t)(((t >> 1) - 1) & 1));  // M2(t-2) finished reading H1[s]
+      uint8_t* h1 = sH1 + s * K::H1_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 16 * i;
+        const float4 rl = srel[r];
+        const float2 rx = make_float2(rl.x, rl.x), ry = make_float2(rl.y, rl.y), rz = make_float2(rl.z, rl.z);
+        const __half2* hh = reinterpret_cast<const __half2*>(&raw[i]);
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 a = __ffma2_rn(wx[j], rx, __half22float2(hh[j]));
+          a = __ffma2_rn(wy[j], ry, a);
+          a = __ffma2_rn(wz[j], rz, a);
+          pk[j] = pack_relu(a);
+        }
+        const uint32_t kk = (uint32_t)chunk * 8;
+        *reinterpret_cast<uint4*>(h1 + (kk >> 6) * (128 * 128) + sw128_offset((uint32_t)r, kk)) =
+            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&h1_full[s]);
+    }
+  } else if (warp == 20) {
+    // ================================================================ MMA2: D2[s] = H1[s] . W2^T
+    if (lane == 0 && my_tiles > 0) {
+      mbar_wait(bar_w, 0);
+      const uint32_t idesc2 = make_idesc_f16_f32(128, C2);
+      for (int t = 0; t < my_tiles; ++t) {
+        const int s = t & 1;
+        mbar_wait(&h1_full[s], (uint32_t)((t >> 1) & 1));
+        if (t >= 2) mbar_wait(&d2_empty[s], (uint32_t)(((t >> 1) - 1) & 1));  // E2(t-2) drained D2[s]
+        tc_fence_after_sync();
+        const uint32_t a0 = smem_u32(sH1 + s * K::H1_BYTES), b0 = smem_u32(sW2);
+#pragma unroll
+        for (int ks = 0; ks < C1 / 16; ++ks) {
+          const uint32_t pan = (uint32_t)ks >> 2, kin = (uint32_t)ks & 3;
+          mma_f16_ss(tmem + K::TM_D2 + s * C2, make_desc_sw128(a0 + pan * (128 * 128) + kin * 32),
+                     make_desc_sw128(b0 + pan * (C2 * 128) + kin * 32), idesc2, ks > 0 ? 1u : 0u);
+        }
+        mma_commit(&m2_done[s]);
+      }
+    }
+  } else if (warp == 21) {
+    // ================================================================ MMA3: D3 = W3^T . H2^T, chunk-major
+    if (lane == 0 && my_tiles > 0) {
+      mbar_wait(bar_w, 0);
+      const uint32_t idesc3 = make_idesc_f16_f32(128, 128);
+      const uint32_t a0 = smem_u32(sW3), b0 = smem_u32(sH2);
+      for (int t = 0; t < my_tiles; ++t) {
+        const uint32_t par = (uint32_t)(t & 1);
+        if (t >= 1) mbar_wait(d3_empty, (uint32_t)((t - 1) & 1));  // E3(t-1) drained D3
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          mbar_wait(&h2c_full[c], par);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) {
+            const uint32_t ks = (uint32_t)(2 * c + k2), pan = ks >> 2, kin = ks & 3;
+#pragma unroll
+            for (int hh = 0; hh < C3 / 128; ++hh)
+              mma_f16_ss(tmem + K::TM_D3 + hh * 128, make_desc_sw128(a0 + pan * (C3 * 128) + hh * (128 * 128) + kin * 32),
+                         make_desc_sw128(b0 + pan * (128 * 128) + kin * 32), idesc3, ks > 0 ? 1u : 0u);
+          }
+          mma_commit(&m3c_done[c]);
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ================================================================ EPILOGUE 2: D2 -> H2   (thread = tile row)
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int s = t & 1;
+      mbar_wait(&m2_done[s], (uint32_t)((t >> 1) & 1));
+      tc_fence_after_sync();
+      uint32_t v[2][32];
+      tmem_ld_x32(tmem + lane_base + K::TM_D2 + s * C2, v[0]);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        tmem_ld_wait();  // chunk c is in registers
+        if (c + 1 < NCH) {
+          tmem_ld_x32(tmem + lane_base + K::TM_D2 + s * C2 + (c + 1) * 32, v[(c + 1) & 1]);  // in flight during the math
+        } else {
+          tc_fence_before_sync();
+          mbar_arrive(&d2_empty[s]);  // the whole accumulator has been read
+        }
+        if (t >= 1) mbar_wait(&m3c_done[c], (uint32_t)((t - 1) & 1));  // M3(t-1) has consumed chunk c of H2
+        const uint32_t* vc = v[c & 1];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const float4 ba = *reinterpret_cast<const float4*>(sB2 + c * 32 + ch * 8);
+          const float4 bb = *reinterpret_cast<const float4*>(sB2 + c * 32 + ch * 8 + 4);
+          const uint32_t* vv = vc + ch * 8;
+          const uint4 pk = make_uint4(
+              pack_relu(__fadd2_rn(make_float2(__uint_as_float(vv[0]), __uint_as_float(vv[1])), make_float2(ba.x, ba.y))),
+              pack_relu(__fadd2_rn(make_float2(__uint_as_float(vv[2]), __uint_as_float(vv[3])), make_float2(ba.z, ba.w))),
+              pack_relu(__fadd2_rn(make_float2(__uint_as_float(vv[4]), __uint_as_float(vv[5])), make_float2(bb.x, bb.y))),
+              pack_relu(__fadd2_rn(make_float2(__uint_as_float(vv[6]), __uint_as_float(vv[7])), make_float2(bb.z, bb.w))));
+          const uint32_t kk = (uint32_t)(c * 32 + ch * 8);
+          *reinterpret_cast<uint4*>(sH2 + (kk >> 6) * (128 * 128) + sw128_offset((uint32_t)tid, kk)) = pk;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&h2c_full[c]);
+      }
+    }
+  } else if (warp < 12) {
+    // ================================================================ EPILOGUE 3: D3 -> max-pool -> out
+    // warp (4 + 4*g + qd): TMEM lane quadrant qd (channels hh*128 + 32qd..+31), centroid g of the tile (columns 64g..64g+63)
+    const int qd = warp & 3, g = (warp - 4) >> 2;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    float bias3[C3 / 128];
+#pragma unroll
+    for (int hh = 0; hh < C3 / 128; ++hh) bias3[hh] = sB3[hh * 128 + qd * 32 + lane];
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = first_tile + t;
+      mbar_wait(&m3c_done[NCH - 1], (uint32_t)(t & 1));  // the last chunk's commit == D3(t) complete
+      tc_fence_after_sync();
+#pragma unroll
+      for (int hh = 0; hh < C3 / 128; ++hh) {
+        uint32_t v[2][32];
+        tmem_ld_x32(tmem + lane_base + K::TM_D3 + hh * 128 + g * 64, v[0]);
+        tmem_ld_x32(tmem + lane_base + K::TM_D3 + hh * 128 + g * 64 + 32, v[1]);
+        tmem_ld_wait();
+        if (hh == C3 / 128 - 1) {
+          tc_fence_before_sync();
+          mbar_arrive(d3_empty);  // D3 has been read: free for M3(t+1)
+        }
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // four independent chains
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          m0 = fmaxf(fmaxf(m0, __uint_as_float(v[0][i])), __uint_as_float(v[1][i]));
+          m1 = fmaxf(fmaxf(m1, __uint_as_float(v[0][i + 1])), __uint_as_float(v[1][i + 1]));
+          m2 = fmaxf(fmaxf(m2, __uint_as_float(v[0][i + 2])), __uint_as_float(v[1][i + 2]));
+          m3 = fmaxf(fmaxf(m3, __uint_as_float(v[0][i + 3])), __uint_as_float(v[1][i + 3]));
+        }
+        const float mval = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        // bias + ReLU commute with the max (both monotone)
+        out[((size_t)tile * 2 + g) * C3 + hh * 128 + qd * 32 + lane] = fmaxf(mval + bias3[hh], 0.f);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, K::TM_COLS);
+}
+
+}  // namespace s2v2
+
+void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx, void* rel,
+                      cudaStream_t st);  // sa_ws.cu
+
+template <int C1, int C2, int C3>
+static int s2v2_launch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, const float* w1x,
+                       const float* b2, const float* b3, const void* w2_img, const void* w3_img, const void* q, float* out,
+                       void* workspace, cudaStream_t st) {
+  using K = s2v2::Cfg<C1, C2, C3>;
+  auto kern = s2v2::sa_ws2_kernel<C1, C2, C3>;
+  VNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+  int dev = 0, sms = 148;
+  VNB_CUDA(cudaGetDevice(&dev));
+  VNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int ntiles = b * m / 2;
+  const long long rows = (long long)b * m * 64;
+  launch_group_rel(n, m, rows, xyz, new_xyz, idx, workspace, st);
+  if (int rc = check_launch("sa_group_mlp_max: grouped relative coordinates")) return rc;
+  const int tpc = (ntiles + sms - 1) / sms;          // one wave: one CTA per SM, contiguous chunks
+  const int grid = (ntiles + tpc - 1) / tpc;
+  kern<<<grid, s2v2::THREADS, K::SMEM, st>>>(b * m, tpc, static_cast<const float4*>(workspace), w1x, b2, b3,
+                                             static_cast<const char*>(w2_img), static_cast<const char*>(w3_img),
+                                             static_cast<const __half*>(q), out);
+  return check_launch("sa_group_mlp_max (tcgen05, warp-specialised v2)");
+}
+
+// returns -1 when no instance matches
+int sa_ws2_dispatch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, int c1, int c2, int c3,
+                    const float* w1x, const float* b2, const float* b3, const void* w2_img, const void* w3_img,
+                    const void* q, float* out, void* workspace, cudaStream_t st) {
+  if (workspace == nullptr) return -1;
+  if (c1 == 128 && c2 == 128 && c3 == 256)
+    return s2v2_launch<128, 128, 256>(b, n, m, xyz, new_xyz, idx, w1x, b2, b3, w2_img, w3_img, q, out, workspace, st);
+  if (c1 == 128 && c2 == 128 && c3 == 128)
+    return s2v2_launch<128, 128, 128>(b, n, m, xyz, new_xyz, idx, w1x, b2, b3, w2_img, w3_img, q, out, workspace, st);
+  return -1;
+}
+
+}  // namespace vnb
