@@ -38,6 +38,9 @@ int vnb_set_tuning(const char* key, int value);
 /* Debugging aid: when given a device buffer of 16 x 8 int64, the next cluster-FPS launches (256 threads x 10 points)
  * accumulate per-phase cycle counts of warp 0 of every CTA of cloud 0 into it; NULL switches it off. */
 int vnb_debug_fps_profile(void* device_buffer_16x8_i64);
+/* Debugging aid: when given a device buffer of 8 x 64 x 2 int64, CTA 0 of the next fused-SA launches stamps clock64() at
+ * the start / end of every pipeline stage (roles P, M1, M2, M3, E1, E2, E3a, E3b) of its first 64 tiles; NULL = off. */
+int vnb_debug_sa_trace(void* device_buffer_8x64x2_i64);
 
 /* ------------------------------------------------------------------ tf_ops/sampling ------------------- */
 

@@ -57,5 +57,6 @@ for li, sa in enumerate(cfg.sa):
         ms = timeit(lambda: sa_group_mlp_max(src_xyz, src_feat, nx, idx, L, 1, store, f"sa{li + 1}"))
         outs[v] = sa_group_mlp_max(src_xyz, src_feat, nx, idx, L, 1, store, f"sa{li + 1}")
         print(f"sa{li + 1} variant={v}: {ms * 1e3:8.1f} us   {gf / ms:7.1f} TFLOP/s (nominal flops, incl. helper kernels)", flush=True)
-    print(f"   bit-identical: {torch.equal(outs[1], outs[2])}", flush=True)
+    d = (outs[1] - outs[2]).abs().max().item() / outs[1].abs().max().item()
+    print(f"   v1 vs v2: bit-identical {torch.equal(outs[1], outs[2])}, max rel diff {d:.2e}", flush=True)
     src_xyz, src_feat = nx, outs[2]

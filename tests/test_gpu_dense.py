@@ -174,5 +174,8 @@ def test_sa_kernel_variants_agree(cuda):
         finally:
             check(lib.vnb_set_tuning(b"sa_variant", 2))
         assert torch.equal(outs[0], outs[1])
-        assert torch.equal(outs[0], outs[2])
-        assert rel_err(outs[2].cpu().numpy(), ref.numpy()) < TOL_TC
+        # second generation: same operands and accumulation order; the narrow-input kernel carries the layer-1/2 biases
+        # on the tensor cores as fp16 values, so it agrees to rounding of the biases rather than bit for bit
+        assert rel_err(outs[2].cpu().numpy(), outs[0].cpu().numpy()) < 2e-4
+        for o in outs:
+            assert rel_err(o.cpu().numpy(), ref.numpy()) < TOL_TC

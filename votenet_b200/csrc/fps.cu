@@ -360,6 +360,13 @@ extern "C" int vnb_set_tuning(const char* key, int value) {
 }
 
 // debugging aid (not part of the drop-in boundary): per-phase cycle counters of the cluster FPS kernel
+namespace vnb { extern long long* g_sa_trace; }
+// debugging aid (not part of the drop-in boundary): stage timeline of CTA 0 of the fused SA kernels
+extern "C" int vnb_debug_sa_trace(void* device_buffer_8x64x2_i64) {
+  vnb::g_sa_trace = static_cast<long long*>(device_buffer_8x64x2_i64);
+  return VNB_OK;
+}
+
 extern "C" int vnb_debug_fps_profile(void* device_buffer_16x8_i64) {
   vnb::g_fps_prof = static_cast<long long*>(device_buffer_16x8_i64);
   return VNB_OK;

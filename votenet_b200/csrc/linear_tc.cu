@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(int rows, int 
                                                                   float* __restrict__ out_f32,
                                                                   __half* __restrict__ out_f16) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* sA[2] = {smem, smem + LT_A_STAGE};
   uint8_t* sB[2] = {smem + 2 * LT_A_STAGE, smem + 2 * LT_A_STAGE + LT_B_STAGE};
   float* sBias = reinterpret_cast<float*>(smem + 2 * (LT_A_STAGE + LT_B_STAGE));

@@ -1,21 +1,28 @@
 // Fused set-abstraction kernel for NARROW inputs (sa1: 3 + c <= 16 input channels), second generation:
-// all three layers on the tensor cores, every stage double-buffered, every stage with its OWN issuing warp.
+// all three layers on the tensor cores, every stage double-buffered, every stage with its OWN issuing warp, and TWO
+// warp groups per epilogue stage that alternate tiles.
 //
 //   group -> [rel_xyz, feat] (K padded to 16) -> L1 -> L2 -> L3 -> max over the 64 samples        (utils.py:49-55,120-132)
 //
-//   warps 0-3    EPILOGUE1  D1 -> +b1, ReLU, fp16 -> H1[t%2]               (thread = tile row = TMEM lane)
-//   warps 4-7    EPILOGUE2  D2 -> +b2, ReLU, fp16 -> H2[t%2]
-//   warps 8-15   EPILOGUE3  D3 (channel per lane) -> max over a centroid's 64 samples, +b3, ReLU -> out;
-//                           two warps per TMEM lane quadrant, one per centroid of the tile (a warp can pull only 64 B per
-//                           cycle out of TMEM, measured: scripts/micro/tmem.cu)
-//   warps 16-19  PRODUCER   one grouped row per thread: {rel_xyz, source row} from the helper kernel's table, c feature
-//                           floats; table rows prefetched two tiles ahead and features one tile ahead so no global
-//                           latency is exposed; fp16, swizzled 32-byte row of A0[t%2]
-//   warp  20/21/22  MMA1/2/3   one thread each: M1(t): D1 = A0 . W1^T, M2(t): D2 = H1 . W2^T, M3(t): D3 = W3^T . H2^T
-//                           (transposed: channels on TMEM lanes, so the 64-sample max-pool is a register reduction).
-//                           Separate issuers: a layer never waits behind another layer's operands (the first generation's
-//                           single in-order issuer kept only ~2 tiles in flight over 7 stages).
-// TMEM: D1[2] (2 x 64) | D2[2] (2 x 64) | D3[2] (2 x 128) columns.  All hand-offs are mbarriers.  One CTA per SM, one wave:
+//   warps 0-3 / 4-7      EPILOGUE1 (even / odd tiles)  D1[s] -> ReLU, fp16 -> H1[t%4]        (thread = tile row = TMEM lane)
+//   warps 8-11 / 12-15   EPILOGUE2 (even / odd tiles)  D2[s] -> ReLU, fp16 -> H2[t%4]        (biases b1, b2 ride on the MMAs)
+//   warps 16-19 / 20-23  EPILOGUE3 (even / odd tiles)  D3[s] (channel per lane) -> max over each centroid's 64 samples,
+//                        +b3, ReLU -> out
+//   warps 24-27          PRODUCER   one grouped row per thread: {rel_xyz, source row} from the helper kernel's table, c
+//                        feature floats; table rows prefetched two tiles ahead and features one tile ahead so no global
+//                        latency is exposed; fp16, swizzled 32-byte row of A0[s]
+//   warps 28 / 29 / 30   MMA1/2/3   one thread each: M1(t): D1 = A0 . W1^T, M2(t): D2 = H1 . W2^T, M3(t): D3 = W3^T . H2^T
+//                        (transposed: channels on TMEM lanes, so the 64-sample max-pool is a register reduction).
+// Why this shape (stage timeline measured with vnb_debug_sa_trace, profiles/):
+//   * one in-order MMA issuer kept only ~2 tiles in flight over 7 stages -> one issuer per layer;
+//   * an epilogue pass over one tile is a chain of fixed latencies in ONE warp per TMEM lane quadrant (mbarrier try_wait
+//     ~90 cycles even when complete, tcgen05.ld ~100, fence + arrive ~100, ...): ~1100 cycles however little math is
+//     left -> two warp groups per stage, each owning one of the two buffers (s = tile parity), halve the period;
+//   * a warp pulls at most 64 B/cycle out of TMEM (scripts/micro/tmem.cu): the max-pool needs 8 warps;
+//   * shared-memory pointers must stay in the shared address space (umma.cuh: smem_align_1024) and loads must be issued
+//     before earlier stores in program order (the compiler never hoists LDS over STS).
+// TMEM: D1[2] (2 x 64) | D2[2] (2 x 64) | D3[2] (2 x 128) columns; shared memory: A0[2], H1[4], H2[4].  All hand-offs are
+// mbarriers (MMA issuers poll, everything else parks).  One CTA per SM, one wave:
 // CTA i owns a contiguous chunk of tiles.
 #include "common.cuh"
 #include "umma.cuh"
@@ -37,18 +44,25 @@ constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
 constexpr int OFF_W3 = OFF_W2 + W2_BYTES;
 constexpr int OFF_A0 = OFF_W3 + W3_BYTES;
 constexpr int OFF_H1 = OFF_A0 + 2 * A0_BYTES;
-constexpr int OFF_H2 = OFF_H1 + 2 * H_BYTES;
-constexpr int OFF_F = OFF_H2 + 2 * H_BYTES;          // floats b1 | b2 | b3
-constexpr int OFF_BAR = OFF_F + (C1 + C2 + C3) * 4;
-constexpr int SMEM = OFF_BAR + 32 * 8 + 16 + 1024;
+constexpr int NH = 4;                      // H1 / H2 buffers (shared memory is plentiful here; TMEM allows only 2 x D)
+constexpr int OFF_H2 = OFF_H1 + NH * H_BYTES;
+constexpr int OFF_ONES = OFF_H2 + NH * H_BYTES;      // A panel [128 rows][k 0..15]: column 0 = 1.0, rest 0  (bias k-step of M2)
+constexpr int OFF_B2P = OFF_ONES + 128 * 128;        // B panel [C2 rows][k 0..15]: column 0 = b2[n], rest 0
+constexpr int OFF_F = OFF_B2P + C2 * 128;            // floats b3
+constexpr int OFF_BAR = OFF_F + C3 * 4;
+constexpr int SMEM = OFF_BAR + 40 * 8 + 16 + 1024;
+static_assert(SMEM <= 227 * 1024, "shared memory budget");
 constexpr int TM_D1 = 0, TM_D2 = 2 * C1, TM_D3 = 2 * C1 + 2 * C2;
 constexpr int TM_COLS = 512;
 static_assert(TM_D3 + 2 * C3 <= 512, "TMEM budget");
-constexpr int THREADS = 23 * 32;
+constexpr int THREADS = 31 * 32;
+constexpr int TRACE_T = 64;
 
-__device__ __forceinline__ uint32_t pack_relu(float2 v) {  // fp16x2(max(v, 0)): rounding is monotone, so relu commutes
-  __half2 h = __hmax2(__float22half2_rn(v), __float2half2_rn(0.f));
-  return *reinterpret_cast<uint32_t*>(&h);
+// fp16x2{lo, hi} = relu(round(.)) in ONE instruction (F2FP.RELU.F16.F32.PACK_AB); rounding is monotone, so relu commutes
+__device__ __forceinline__ uint32_t pack_relu2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -61,39 +75,47 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
                                                              const float* __restrict__ b1, const float* __restrict__ b2,
                                                              const float* __restrict__ b3, const char* __restrict__ w1_img,
                                                              const char* __restrict__ w2_img,
-                                                             const char* __restrict__ w3_img, float* __restrict__ out) {
+                                                             const char* __restrict__ w3_img, float* __restrict__ out,
+                                                             long long* __restrict__ trace) {
+  // debugging aid: CTA 0 stamps clock64() at the start (after its input wait) and the end of every stage of its first
+  // TRACE_T tiles: trace[(role * TRACE_T + t) * 2 + {0,1}], roles P, M1, M2, M3, E1, E2, E3(g=0), E3(g=1)
+  const bool tr = trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
+#define S1_STAMP(role, t, ph) \
+  if (tr && (t) < TRACE_T) trace[((role) * TRACE_T + (t)) * 2 + (ph)] = clock64();
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* sW1 = smem + OFF_W1;
   uint8_t* sW2 = smem + OFF_W2;
   uint8_t* sW3 = smem + OFF_W3;
   uint8_t* sA0 = smem + OFF_A0;
   uint8_t* sH1 = smem + OFF_H1;
   uint8_t* sH2 = smem + OFF_H2;
-  float* sB1 = reinterpret_cast<float*>(smem + OFF_F);
-  float* sB2 = sB1 + C1;
-  float* sB3 = sB2 + C2;
+  uint8_t* sOnes = smem + OFF_ONES;
+  uint8_t* sB2P = smem + OFF_B2P;
+  float* sB3 = reinterpret_cast<float*>(smem + OFF_F);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* bar_w = bars;          // weights landed
-  uint64_t* a0_full = bars + 1;    // [2] 128 producer arrivals
-  uint64_t* m1_done = bars + 3;    // [2] commit
-  uint64_t* h1_full = bars + 5;    // [2] 128 E1 arrivals
-  uint64_t* d1_empty = bars + 7;   // [2] 128 E1 arrivals
-  uint64_t* m2_done = bars + 9;    // [2] commit
-  uint64_t* h2_full = bars + 11;   // [2] 128 E2 arrivals
-  uint64_t* d2_empty = bars + 13;  // [2] 128 E2 arrivals
-  uint64_t* m3_done = bars + 15;   // [2] commit
-  uint64_t* d3_empty = bars + 17;  // [2] 256 E3 arrivals
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 32);
+  uint64_t* a0_full = bars + 1;    // [2]  128 producer arrivals                        (slot t&1, parity (t>>1)&1)
+  uint64_t* m1_done = bars + 3;    // [2]  commit
+  uint64_t* d1_empty = bars + 5;   // [2]  128 E1 arrivals
+  uint64_t* d2_empty = bars + 7;   // [2]  128 E2 arrivals
+  uint64_t* d3_empty = bars + 9;   // [2]  128 E3 arrivals
+  uint64_t* h1_full = bars + 11;   // [NH] 128 E1 arrivals                              (slot t&3, parity (t>>2)&1)
+  uint64_t* m2_done = bars + 15;   // [NH] commit: D2[t&1] ready, H1[t&3] free again
+  uint64_t* h2_full = bars + 19;   // [NH] 128 E2 arrivals
+  uint64_t* m3_done = bars + 23;   // [NH] commit: D3[t&1] ready, H2[t&3] free again
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 36);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&a0_full[s], 128); mbar_init(&m1_done[s], 1); mbar_init(&h1_full[s], 128); mbar_init(&d1_empty[s], 128);
-      mbar_init(&m2_done[s], 1); mbar_init(&h2_full[s], 128); mbar_init(&d2_empty[s], 128);
-      mbar_init(&m3_done[s], 1); mbar_init(&d3_empty[s], 256);
+      mbar_init(&a0_full[s], 128); mbar_init(&m1_done[s], 1); mbar_init(&d1_empty[s], 128); mbar_init(&d2_empty[s], 128);
+      mbar_init(&d3_empty[s], 128);
+    }
+    for (int k = 0; k < NH; ++k) {
+      mbar_init(&h1_full[k], 128); mbar_init(&m2_done[k], 1); mbar_init(&h2_full[k], 128); mbar_init(&m3_done[k], 1);
     }
     fence_barrier_init();
     mbar_arrive_expect_tx(bar_w, (uint32_t)(W1_BYTES + W2_BYTES + W3_BYTES));
@@ -101,12 +123,31 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
     bulk_g2s(sW2, w2_img, W2_BYTES, bar_w);
     bulk_g2s(sW3, w3_img, W3_BYTES, bar_w);
   }
-  for (int i = tid; i < C1; i += THREADS) sB1[i] = b1[i];
-  for (int i = tid; i < C2; i += THREADS) sB2[i] = b2[i];
   for (int i = tid; i < C3; i += THREADS) sB3[i] = b3[i];
-  // A0 padding columns (k >= 16 of the 64-column panel are never read; k in [3+c,16) must be finite): zero both buffers
+  // A0 padding columns (k >= 16 of the 64-column panel are never read; k in [3+c,14) must be finite): zero both buffers;
+  // zero the two bias panels
   for (int i = tid; i < 2 * A0_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA0)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (128 * 128 + C2 * 128) / 16; i += THREADS) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0) tmem_alloc(tmem_ptr, TM_COLS);
+  mbar_wait(bar_w, 0);  // weight images have landed (every thread observes the barrier: the patch below follows the copy)
+  __syncthreads();
+  // Biases of layers 1 and 2 ride on the tensor cores (an epilogue pass is ALU-pipe bound, profiles/micro_thr.txt):
+  //   layer 1: A0 columns 14, 15 are the constant 1 (written by the producer), rows k = 14, 15 of the W1 image are b1;
+  //   layer 2: one extra k-step multiplies the constant panel sOnes (columns 0, 1 = 1) with sB2P (columns 0, 1 = b2).
+  // fp16 biases, fp32 accumulation.  Layer 3's bias is added after the max-pool (one add per output).
+  // Each bias is split into fp16 hi + lo parts on two columns (~22 significant bits).
+  if (tid < 128)
+    *reinterpret_cast<__half2*>(sOnes + sw128_offset((uint32_t)tid, 0)) = __floats2half2_rn(1.f, 1.f);
+  if (tid < C2) {
+    const float bv = b2[tid];
+    const __half hi = __float2half_rn(bv);
+    *reinterpret_cast<__half2*>(sB2P + sw128_offset((uint32_t)tid, 0)) = __halves2half2(hi, __float2half_rn(bv - __half2float(hi)));
+  }
+  if (tid < C1) {
+    const float bv = b1[tid];
+    const __half hi = __float2half_rn(bv);
+    *reinterpret_cast<__half2*>(sW1 + sw128_offset((uint32_t)tid, 14)) = __halves2half2(hi, __float2half_rn(bv - __half2float(hi)));
+  }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -116,23 +157,24 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
   const int ntiles = total_centroids / 2;
   const int first_tile = (int)blockIdx.x * tiles_per_cta;
   const int my_tiles = max(0, min(tiles_per_cta, ntiles - first_tile));
-  // use u = t>>1 of a [2]-slotted barrier -> parity u&1
+  // use number t>>1 of a [2]-slotted barrier -> parity (t>>1)&1; use number t>>2 of an [NH]-slotted one -> (t>>2)&1
   auto par_of = [](int t) { return (uint32_t)((t >> 1) & 1); };
+  auto par4 = [](int t) { return (uint32_t)((t >> 2) & 1); };
 
-  if (warp >= 16 && warp < 20) {
+  if (warp >= 24 && warp < 28) {
     // ================================================================ PRODUCER: one grouped row per thread
-    const int pt = tid - 512;
+    const int pt = tid - 768;
     const float4* rp = rel + (size_t)first_tile * 128 + pt;
     float4 r_cur = make_float4(0.f, 0.f, 0.f, 0.f), r_nxt = r_cur;   // table rows of tiles t, t+1
     if (my_tiles > 0) r_cur = __ldg(rp);
     if (my_tiles > 1) r_nxt = __ldg(rp + 128);
-    float f_cur[13], f_nxt[13];
+    float f_cur[11], f_nxt[11];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) f_cur[i] = f_nxt[i] = 0.f;
+    for (int i = 0; i < 11; ++i) f_cur[i] = f_nxt[i] = 0.f;
     if (my_tiles > 0) {
       const float* f = feat + (size_t)__float_as_int(r_cur.w) * c;
 #pragma unroll
-      for (int i = 0; i < 13; ++i)
+      for (int i = 0; i < 11; ++i)
         if (i < c) f_cur[i] = __ldg(f + i);
     }
     for (int t = 0; t < my_tiles; ++t) {
@@ -142,152 +184,184 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
       if (t + 1 < my_tiles) {
         const float* f = feat + (size_t)__float_as_int(r_nxt.w) * c;
 #pragma unroll
-        for (int i = 0; i < 13; ++i)
+        for (int i = 0; i < 11; ++i)
           if (i < c) f_nxt[i] = __ldg(f + i);
       }
       if (t + 2 < my_tiles) r_nn = __ldg(rp + (size_t)(t + 2) * 128);
       if (t >= 2) mbar_wait(&m1_done[s], par_of(t - 2));  // M1(t-2) finished reading A0[s]
+      if (warp == 24) { S1_STAMP(0, t, 0) }
       uint8_t* a0 = sA0 + s * A0_BYTES;
       *reinterpret_cast<uint4*>(a0 + sw128_offset((uint32_t)pt, 0)) =
           make_uint4(pack2(r_cur.x, r_cur.y), pack2(r_cur.z, f_cur[0]), pack2(f_cur[1], f_cur[2]), pack2(f_cur[3], f_cur[4]));
       *reinterpret_cast<uint4*>(a0 + sw128_offset((uint32_t)pt, 8)) =
           make_uint4(pack2(f_cur[5], f_cur[6]), pack2(f_cur[7], f_cur[8]), pack2(f_cur[9], f_cur[10]),
-                     pack2(f_cur[11], f_cur[12]));
+                     pack2(1.f, 1.f));  // k = 14, 15: the constant 1 that multiplies b1 (hi, lo); needs c <= 11
       fence_proxy_async_smem();
       mbar_arrive(&a0_full[s]);
+      if (warp == 24) { S1_STAMP(0, t, 1) }
       r_cur = r_nxt; r_nxt = r_nn;
 #pragma unroll
-      for (int i = 0; i < 13; ++i) f_cur[i] = f_nxt[i];
+      for (int i = 0; i < 11; ++i) f_cur[i] = f_nxt[i];
     }
-  } else if (warp == 20) {
+  } else if (warp == 28) {
     // ================================================================ MMA1: D1[s] = A0[s] . W1^T  (single K = 16 step)
-    if (lane == 0 && my_tiles > 0) {
-      mbar_wait(bar_w, 0);
+    // (all 32 lanes run the loop; one elected lane issues — see umma.cuh: elect_one)
+    if (my_tiles > 0) {
       const uint32_t id1 = make_idesc_f16_f32(128, C1);
+      const uint64_t bd = make_desc_sw128(smem_u32(sW1));
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t & 1;
-        mbar_wait(&a0_full[s], par_of(t));
-        if (t >= 2) mbar_wait(&d1_empty[s], par_of(t - 2));
+        mbar_wait_spin(&a0_full[s], par_of(t));
+        if (t >= 2) mbar_wait_spin(&d1_empty[s], par_of(t - 2));
         tc_fence_after_sync();
-        mma_f16_ss(tmem + TM_D1 + s * C1, make_desc_sw128(smem_u32(sA0 + s * A0_BYTES)), make_desc_sw128(smem_u32(sW1)),
-                   id1, 0u);
-        mma_commit(&m1_done[s]);
+        S1_STAMP(1, t, 0)
+        if (elect_one()) {
+          mma_f16_ss(tmem + TM_D1 + s * C1, make_desc_sw128(smem_u32(sA0 + s * A0_BYTES)), bd, id1, 0u);
+          mma_commit(&m1_done[s]);
+        }
+        __syncwarp();
+        S1_STAMP(1, t, 1)
       }
     }
-  } else if (warp == 21) {
-    // ================================================================ MMA2: D2[s] = H1[s] . W2^T
-    if (lane == 0 && my_tiles > 0) {
-      mbar_wait(bar_w, 0);
+  } else if (warp == 29) {
+    // ================================================================ MMA2: D2[s] = H1[t%4] . W2^T  (+ b2)
+    if (my_tiles > 0) {
       const uint32_t id2 = make_idesc_f16_f32(128, C2);
+      const uint64_t bd = make_desc_sw128(smem_u32(sW2));
+      const uint64_t ones = make_desc_sw128(smem_u32(sOnes)), bias = make_desc_sw128(smem_u32(sB2P));
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t & 1;
-        mbar_wait(&h1_full[s], par_of(t));
-        if (t >= 2) mbar_wait(&d2_empty[s], par_of(t - 2));
+        mbar_wait_spin(&h1_full[t & 3], par4(t));
+        if (t >= 2) mbar_wait_spin(&d2_empty[s], par_of(t - 2));
         tc_fence_after_sync();
-        const uint32_t a0 = smem_u32(sH1 + s * H_BYTES), b0 = smem_u32(sW2);
+        S1_STAMP(2, t, 0)
+        if (elect_one()) {
+          const uint64_t ad = make_desc_sw128(smem_u32(sH1 + (t & 3) * H_BYTES));
 #pragma unroll
-        for (int ks = 0; ks < C1 / 16; ++ks)
-          mma_f16_ss(tmem + TM_D2 + s * C2, make_desc_sw128(a0 + ks * 32), make_desc_sw128(b0 + ks * 32), id2,
-                     ks > 0 ? 1u : 0u);
-        mma_commit(&m2_done[s]);
+          for (int ks = 0; ks < C1 / 16; ++ks)  // +32 bytes per k-step == +2 in the descriptor's address field
+            mma_f16_ss(tmem + TM_D2 + s * C2, ad + (uint64_t)(2 * ks), bd + (uint64_t)(2 * ks), id2, ks > 0 ? 1u : 0u);
+          mma_f16_ss(tmem + TM_D2 + s * C2, ones, bias, id2, 1u);  // + b2
+          mma_commit(&m2_done[t & 3]);
+        }
+        __syncwarp();
+        S1_STAMP(2, t, 1)
       }
     }
-  } else if (warp == 22) {
-    // ================================================================ MMA3: D3[s] = W3^T . H2[s]^T
-    if (lane == 0 && my_tiles > 0) {
-      mbar_wait(bar_w, 0);
+  } else if (warp == 30) {
+    // ================================================================ MMA3: D3[s] = W3^T . H2[t%4]^T
+    if (my_tiles > 0) {
       const uint32_t id3 = make_idesc_f16_f32(128, 128);
+      const uint64_t ad = make_desc_sw128(smem_u32(sW3));
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t & 1;
-        mbar_wait(&h2_full[s], par_of(t));
-        if (t >= 2) mbar_wait(&d3_empty[s], par_of(t - 2));
+        mbar_wait_spin(&h2_full[t & 3], par4(t));
+        if (t >= 2) mbar_wait_spin(&d3_empty[s], par_of(t - 2));
         tc_fence_after_sync();
-        const uint32_t a0 = smem_u32(sW3), b0 = smem_u32(sH2 + s * H_BYTES);
+        S1_STAMP(3, t, 0)
+        if (elect_one()) {
+          const uint64_t bd = make_desc_sw128(smem_u32(sH2 + (t & 3) * H_BYTES));
 #pragma unroll
-        for (int ks = 0; ks < C2 / 16; ++ks)
-          mma_f16_ss(tmem + TM_D3 + s * C3, make_desc_sw128(a0 + ks * 32), make_desc_sw128(b0 + ks * 32), id3,
-                     ks > 0 ? 1u : 0u);
-        mma_commit(&m3_done[s]);
+          for (int ks = 0; ks < C2 / 16; ++ks)
+            mma_f16_ss(tmem + TM_D3 + s * C3, ad + (uint64_t)(2 * ks), bd + (uint64_t)(2 * ks), id3, ks > 0 ? 1u : 0u);
+          mma_commit(&m3_done[t & 3]);
+        }
+        __syncwarp();
+        S1_STAMP(3, t, 1)
       }
     }
-  } else if (warp < 8) {
-    // ================================================================ EPILOGUE 1 (warps 0-3) / EPILOGUE 2 (warps 4-7)
-    const bool e2 = warp >= 4;
+  } else if (warp < 16) {
+    // ================================================================ EPILOGUE 1 (warps 0-7) / EPILOGUE 2 (warps 8-15)
+    // warp group (warp >> 2) & 1 owns the tiles of that parity, i.e. buffer s of every stage
+    const bool e2 = warp >= 8;
+    const int s = (warp >> 2) & 1;
     const int et = tid & 127;  // tile row == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint64_t* in_done = e2 ? m2_done : m1_done;      // accumulator ready
-    uint64_t* out_free = e2 ? m3_done : m2_done;     // MMA that read our output buffer two tiles ago
-    uint64_t* d_empty = e2 ? d2_empty : d1_empty;
-    uint64_t* h_full = e2 ? h2_full : h1_full;
-    const uint32_t tm = e2 ? TM_D2 : TM_D1;
-    uint8_t* hbase = e2 ? sH2 : sH1;
-    const float* bias = e2 ? sB2 : sB1;
-    for (int t = 0; t < my_tiles; ++t) {
-      const int s = t & 1;
-      mbar_wait(&in_done[s], par_of(t));
+    uint64_t* d_empty = (e2 ? d2_empty : d1_empty) + s;
+    const uint32_t tacc = tmem + lane_base + (e2 ? TM_D2 : TM_D1) + s * 64;
+    uint8_t* hbase = sH1 + (e2 ? NH * H_BYTES : 0);   // sH2 follows sH1; pointers stay provably shared-memory
+    const bool stamp = (warp & 3) == 0;
+    const int role = e2 ? (s ? 9 : 5) : (s ? 8 : 4);  // trace roles: E1 even 4 / odd 8, E2 even 5 / odd 9
+    for (int t = s; t < my_tiles; t += 2) {
+      // accumulator ready: E1 <- m1_done[s], E2 <- m2_done[t&3]
+      if (e2) mbar_wait(&m2_done[t & 3], par4(t)); else mbar_wait(&m1_done[s], par_of(t));
       tc_fence_after_sync();
-      uint32_t v[2][32];
-      tmem_ld_x32(tmem + lane_base + tm + s * 64, v[0]);       // both halves of the 64-column accumulator in flight
-      tmem_ld_x32(tmem + lane_base + tm + s * 64 + 32, v[1]);
-      if (t >= 2) mbar_wait(&out_free[s], par_of(t - 2));
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      mbar_arrive(&d_empty[s]);                                 // accumulator drained into registers
-      uint8_t* h = hbase + s * H_BYTES;
+      if (stamp) { S1_STAMP(role, t, 0) }
+      uint8_t* h = hbase + (t & 3) * H_BYTES;
+      // the MMA that read our output buffer NH tiles ago: E1 <- m2_done, E2 <- m3_done
+      uint64_t* out_free = (e2 ? m3_done : m2_done) + (t & 3);
+      uint64_t* h_full = (e2 ? h2_full : h1_full) + (t & 3);
 #pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {
+      for (int qq = 0; qq < 4; ++qq) {  // four 16-column quarters (ptxas hoists the next load; x32 loads overflow 64 registers)
+        uint32_t v[16];
+        tmem_ld_x16(tacc + qq * 16, v);
+        if (qq == 0 && t >= NH) mbar_wait(out_free, par4(t - NH));
+        tmem_ld_wait();
+        if (qq == 3) {
+          tc_fence_before_sync();
+          mbar_arrive(d_empty);  // accumulator drained into registers
+        }
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const float4 ba = *reinterpret_cast<const float4*>(bias + hb * 32 + ch * 8);
-          const float4 bb = *reinterpret_cast<const float4*>(bias + hb * 32 + ch * 8 + 4);
-          const uint32_t* vv = &v[hb][ch * 8];
-          const uint4 pk = make_uint4(
-              pack_relu(__fadd2_rn(make_float2(__uint_as_float(vv[0]), __uint_as_float(vv[1])), make_float2(ba.x, ba.y))),
-              pack_relu(__fadd2_rn(make_float2(__uint_as_float(vv[2]), __uint_as_float(vv[3])), make_float2(ba.z, ba.w))),
-              pack_relu(__fadd2_rn(make_float2(__uint_as_float(vv[4]), __uint_as_float(vv[5])), make_float2(bb.x, bb.y))),
-              pack_relu(__fadd2_rn(make_float2(__uint_as_float(vv[6]), __uint_as_float(vv[7])), make_float2(bb.z, bb.w))));
-          *reinterpret_cast<uint4*>(h + sw128_offset((uint32_t)et, (uint32_t)(hb * 32 + ch * 8))) = pk;
+        for (int gi = 0; gi < 2; ++gi) {  // bias already in the accumulator: relu + fp16 pack is one instruction per pair
+          const uint4 pk = make_uint4(pack_relu2(__uint_as_float(v[gi * 8 + 0]), __uint_as_float(v[gi * 8 + 1])),
+                                      pack_relu2(__uint_as_float(v[gi * 8 + 2]), __uint_as_float(v[gi * 8 + 3])),
+                                      pack_relu2(__uint_as_float(v[gi * 8 + 4]), __uint_as_float(v[gi * 8 + 5])),
+                                      pack_relu2(__uint_as_float(v[gi * 8 + 6]), __uint_as_float(v[gi * 8 + 7])));
+          *reinterpret_cast<uint4*>(h + sw128_offset((uint32_t)et, (uint32_t)(qq * 16 + gi * 8))) = pk;
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(&h_full[s]);
+      mbar_arrive(h_full);
+      if (stamp) { S1_STAMP(role, t, 1) }
     }
-  } else if (warp < 16) {
+  } else if (warp < 24) {
     // ================================================================ EPILOGUE 3: D3 -> max-pool -> out
-    // warp (8 + 4*g + q): TMEM lane quadrant q (channels 32q..32q+31), centroid g of the tile (columns 64g..64g+63)
-    const int q = warp & 3, g = (warp - 8) >> 2;
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    // warp (16 + 4*s + q): tiles of parity s, TMEM lane quadrant q (channels 32q..32q+31), both centroids of the tile
+    const int q = warp & 3, s = (warp >> 2) & 1;
+    const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + TM_D3 + s * C3;
     const int ch = q * 32 + lane;
     const float bias3 = sB3[ch];
-    for (int t = 0; t < my_tiles; ++t) {
+    for (int t = s; t < my_tiles; t += 2) {
       const int tile = first_tile + t;
-      const int s = t & 1;
-      mbar_wait(&m3_done[s], par_of(t));
+      mbar_wait(&m3_done[t & 3], par4(t));
       tc_fence_after_sync();
-      uint32_t v[2][32];
-      tmem_ld_x32(tmem + lane_base + TM_D3 + s * C3 + g * 64, v[0]);
-      tmem_ld_x32(tmem + lane_base + TM_D3 + s * C3 + g * 64 + 32, v[1]);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      mbar_arrive(&d3_empty[s]);
-      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // four independent chains
+      if (q == 0) { S1_STAMP(6 + s, t, 0) }
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        m0 = fmaxf(fmaxf(m0, __uint_as_float(v[0][i])), __uint_as_float(v[1][i]));
-        m1 = fmaxf(fmaxf(m1, __uint_as_float(v[0][i + 1])), __uint_as_float(v[1][i + 1]));
-        m2 = fmaxf(fmaxf(m2, __uint_as_float(v[0][i + 2])), __uint_as_float(v[1][i + 2]));
-        m3 = fmaxf(fmaxf(m3, __uint_as_float(v[0][i + 3])), __uint_as_float(v[1][i + 3]));
+      for (int g = 0; g < 2; ++g) {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // four independent chains
+        // 16-column loads: ptxas hoists the next load over the current reduction, and two x32 loads do not fit the
+        // 64-register budget of this 992-thread CTA (it spilled a whole load)
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          uint32_t v[16];
+          tmem_ld_x16(tacc + g * 64 + qq * 16, v);
+          tmem_ld_wait();
+          if (g == 1 && qq == 3) {
+            tc_fence_before_sync();
+            mbar_arrive(&d3_empty[s]);  // D3[s] has been read
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i += 8) {
+            m0 = fmaxf(fmaxf(m0, __uint_as_float(v[i])), __uint_as_float(v[i + 4]));
+            m1 = fmaxf(fmaxf(m1, __uint_as_float(v[i + 1])), __uint_as_float(v[i + 5]));
+            m2 = fmaxf(fmaxf(m2, __uint_as_float(v[i + 2])), __uint_as_float(v[i + 6]));
+            m3 = fmaxf(fmaxf(m3, __uint_as_float(v[i + 3])), __uint_as_float(v[i + 7]));
+          }
+        }
+        const float mval = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        out[((size_t)tile * 2 + g) * C3 + ch] = fmaxf(mval + bias3, 0.f);  // bias + ReLU commute with the max
       }
-      const float mval = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      out[((size_t)tile * 2 + g) * C3 + ch] = fmaxf(mval + bias3, 0.f);  // bias + ReLU commute with the max
+      if (q == 0) { S1_STAMP(6 + s, t, 1) }
     }
   }
+#undef S1_STAMP
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TM_COLS);
 }
 
 }  // namespace s1v2
+
+long long* g_sa_trace = nullptr;  // debugging: device buffer of 12 x 64 x 2 int64 (vnb_debug_sa_trace)
 
 void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx, void* rel,
                       cudaStream_t st);  // sa_ws.cu
@@ -296,7 +370,7 @@ void launch_group_rel(int n, int m, long long rows, const float* xyz, const floa
 int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* feat, const float* new_xyz, const int* idx,
                      int c1, int c2, int c3, const float* b1, const float* b2, const float* b3, const void* w1_img,
                      const void* w2_img, const void* w3_img, float* out, void* workspace, cudaStream_t st) {
-  if (workspace == nullptr || !(c1 == 64 && c2 == 64 && c3 == 128) || c > 13) return -1;
+  if (workspace == nullptr || !(c1 == 64 && c2 == 64 && c3 == 128) || c > 11) return -1;  // k = 14, 15 carry the bias
   auto kern = s1v2::sa1_ws2_kernel;
   VNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, s1v2::SMEM));
   int dev = 0, sms = 148;
@@ -310,7 +384,7 @@ int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* 
   const int grid = (ntiles + tpc - 1) / tpc;
   kern<<<grid, s1v2::THREADS, s1v2::SMEM, st>>>(c, b * m, tpc, static_cast<const float4*>(workspace), feat, b1, b2, b3,
                                                 static_cast<const char*>(w1_img), static_cast<const char*>(w2_img),
-                                                static_cast<const char*>(w3_img), out);
+                                                static_cast<const char*>(w3_img), out, g_sa_trace);
   return check_launch("sa_group_mlp_max (tcgen05, warp-specialised v2, narrow input)");
 }
 

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sa_ws_kernel(int n, int m, int 
                                                               const __half* __restrict__ q, float* __restrict__ out) {
   using Cfg = WsCfg<C1, C2, C3>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* sW2 = smem + Cfg::OFF_W2;
   uint8_t* sW3 = smem + Cfg::OFF_W3;
   uint8_t* sH1 = smem + Cfg::OFF_H1;

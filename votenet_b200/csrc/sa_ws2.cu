@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
   using K = Cfg<C1, C2, C3>;
   constexpr int NCH = K::NCHUNK;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* sW2 = smem + K::OFF_W2;
   uint8_t* sW3 = smem + K::OFF_W3;
   uint8_t* sH1 = smem + K::OFF_H1;
@@ -145,10 +145,12 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
         raw[i] = __ldg(reinterpret_cast<const uint4*>(q + (size_t)__float_as_int(srel[rsub + 16 * i].w) * C1) + chunk);
       if (t >= 2) mbar_wait(&m2_done[s], (uint32_t)(((t >> 1) - 1) & 1));  // M2(t-2) finished reading H1[s]
       uint8_t* h1 = sH1 + s * K::H1_BYTES;
+      float4 rl_next = srel[rsub];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rsub + 16 * i;
-        const float4 rl = srel[r];
+        const float4 rl = rl_next;
+        if (i + 1 < 8) rl_next = srel[r + 16];  // before this row's store: shared loads are kept behind earlier shared stores
         const float2 rx = make_float2(rl.x, rl.x), ry = make_float2(rl.y, rl.y), rz = make_float2(rl.z, rl.z);
         const __half2* hh = reinterpret_cast<const __half2*>(&raw[i]);
         uint32_t pk[4];
@@ -231,10 +233,15 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
         }
         if (t >= 1) mbar_wait(&m3c_done[c], (uint32_t)((t - 1) & 1));  // M3(t-1) has consumed chunk c of H2
         const uint32_t* vc = v[c & 1];
+        // bias of group ch+1 is loaded BEFORE group ch is stored (shared loads are kept behind earlier shared stores)
+        float4 ba = *reinterpret_cast<const float4*>(sB2 + c * 32), bb = *reinterpret_cast<const float4*>(sB2 + c * 32 + 4);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const float4 ba = *reinterpret_cast<const float4*>(sB2 + c * 32 + ch * 8);
-          const float4 bb = *reinterpret_cast<const float4*>(sB2 + c * 32 + ch * 8 + 4);
+          float4 na = ba, nb = bb;
+          if (ch + 1 < 4) {
+            na = *reinterpret_cast<const float4*>(sB2 + c * 32 + (ch + 1) * 8);
+            nb = *reinterpret_cast<const float4*>(sB2 + c * 32 + (ch + 1) * 8 + 4);
+          }
           const uint32_t* vv = vc + ch * 8;
           const uint4 pk = make_uint4(
               pack_relu(__fadd2_rn(make_float2(__uint_as_float(vv[0]), __uint_as_float(vv[1])), make_float2(ba.x, ba.y))),
@@ -243,6 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
               pack_relu(__fadd2_rn(make_float2(__uint_as_float(vv[6]), __uint_as_float(vv[7])), make_float2(bb.z, bb.w))));
           const uint32_t kk = (uint32_t)(c * 32 + ch * 8);
           *reinterpret_cast<uint4*>(sH2 + (kk >> 6) * (128 * 128) + sw128_offset((uint32_t)tid, kk)) = pk;
+          ba = na; bb = nb;
         }
         fence_proxy_async_smem();
         mbar_arrive(&h2c_full[c]);

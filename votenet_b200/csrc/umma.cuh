@@ -9,6 +9,14 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// First 1024-byte-aligned address of the dynamic shared-memory window (SW128 atoms must be 1024-B aligned).  Computed as
+// base + offset so the result is still provably a SHARED-memory pointer: rounding the address through an integer makes it
+// a generic pointer and every access LD.E / ST.E — which the compiler may not reorder (measured: the epilogues of
+// sa1_ws2_kernel ran 4x slower on that alone).
+__device__ __forceinline__ uint8_t* smem_align_1024(uint8_t* raw) {
+  return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -31,8 +39,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the thread (no issue slots consumed) until the phase completes
+// or `ns` nanoseconds elapse.  Measured on sa1_ws2_kernel: with the un-hinted form a waiting warp re-polled every ~40
+// cycles and HALF of all issued instructions of the kernel were polling loops.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  for (uint32_t spin = 0; !mbar_try_wait_hint(bar, parity, 20000u); ++spin)
+    if (spin > (1u << 20)) __trap();
+}
+
+// Tight polling wait for the single-thread MMA issuers: the parked form above wakes ~300 cycles after the arrive
+// (measured, vnb_debug_sa_trace), which sits on the critical path of every tile; one polling thread costs next to nothing.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
     if (spin > (1u << 26)) __trap();
 }
@@ -61,6 +91,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// One elected lane of a CONVERGED warp.  The MMA issuers run their loop with all 32 lanes (uniform control flow) and issue
+// tcgen05.mma / tcgen05.commit under this predicate: ptxas then emits the UTCHMMAs back to back.  Issuing from inside an
+// `if (lane == 0)` region instead wraps EVERY tcgen05 instruction in an elect / BRA.U.ANY retry loop (~100 cycles each).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows at 128 B pitch inside an 8-row / 1024 B
