@@ -76,12 +76,14 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
                                                              const float* __restrict__ b3, const char* __restrict__ w1_img,
                                                              const char* __restrict__ w2_img,
                                                              const char* __restrict__ w3_img, float* __restrict__ out,
-                                                             long long* __restrict__ trace) {
+                                                             long long* __restrict__ trace, int mma_spin) {
   // debugging aid: CTA 0 stamps clock64() at the start (after its input wait) and the end of every stage of its first
   // TRACE_T tiles: trace[(role * TRACE_T + t) * 2 + {0,1}], roles P, M1, M2, M3, E1, E2, E3(g=0), E3(g=1)
   const bool tr = trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
 #define S1_STAMP(role, t, ph) \
   if (tr && (t) < TRACE_T) trace[((role) * TRACE_T + (t)) * 2 + (ph)] = clock64();
+#define MMA_WAIT(bar, par) \
+  do { if (mma_spin) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* sW1 = smem + OFF_W1;
@@ -211,8 +213,8 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
       const uint64_t bd = make_desc_sw128(smem_u32(sW1));
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t & 1;
-        mbar_wait_spin(&a0_full[s], par_of(t));
-        if (t >= 2) mbar_wait_spin(&d1_empty[s], par_of(t - 2));
+        MMA_WAIT(&a0_full[s], par_of(t));
+        if (t >= 2) MMA_WAIT(&d1_empty[s], par_of(t - 2));
         tc_fence_after_sync();
         S1_STAMP(1, t, 0)
         if (elect_one()) {
@@ -231,8 +233,8 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
       const uint64_t ones = make_desc_sw128(smem_u32(sOnes)), bias = make_desc_sw128(smem_u32(sB2P));
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t & 1;
-        mbar_wait_spin(&h1_full[t & 3], par4(t));
-        if (t >= 2) mbar_wait_spin(&d2_empty[s], par_of(t - 2));
+        MMA_WAIT(&h1_full[t & 3], par4(t));
+        if (t >= 2) MMA_WAIT(&d2_empty[s], par_of(t - 2));
         tc_fence_after_sync();
         S1_STAMP(2, t, 0)
         if (elect_one()) {
@@ -254,8 +256,8 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
       const uint64_t ad = make_desc_sw128(smem_u32(sW3));
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t & 1;
-        mbar_wait_spin(&h2_full[t & 3], par4(t));
-        if (t >= 2) mbar_wait_spin(&d3_empty[s], par_of(t - 2));
+        MMA_WAIT(&h2_full[t & 3], par4(t));
+        if (t >= 2) MMA_WAIT(&d3_empty[s], par_of(t - 2));
         tc_fence_after_sync();
         S1_STAMP(3, t, 0)
         if (elect_one()) {
@@ -361,6 +363,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
 
 }  // namespace s1v2
 
+extern int g_sa_variant;  // mlp_tc.cu
 long long* g_sa_trace = nullptr;  // debugging: device buffer of 12 x 64 x 2 int64 (vnb_debug_sa_trace)
 
 void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx, void* rel,
@@ -384,7 +387,7 @@ int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* 
   const int grid = (ntiles + tpc - 1) / tpc;
   kern<<<grid, s1v2::THREADS, s1v2::SMEM, st>>>(c, b * m, tpc, static_cast<const float4*>(workspace), feat, b1, b2, b3,
                                                 static_cast<const char*>(w1_img), static_cast<const char*>(w2_img),
-                                                static_cast<const char*>(w3_img), out, g_sa_trace);
+                                                static_cast<const char*>(w3_img), out, g_sa_trace, g_sa_variant == 3 ? 1 : 0);  // MMA issuers park (default) or poll (sa_variant 3)
   return check_launch("sa_group_mlp_max (tcgen05, warp-specialised v2, narrow input)");
 }
 

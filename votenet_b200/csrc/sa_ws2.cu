@@ -11,6 +11,12 @@
 //     ~350 cycles, hidden behind M2 on the tensor pipe;
 //   * all TMEM loads of a stage are in flight before the first wait; packed fp32x2 math (FFMA2 / FADD2) and fp16x2 ReLU;
 //   * one wave: one CTA per SM, contiguous chunks of tiles (one prologue, one pipeline fill per SM).
+// Measured (vnb_debug_sa_trace + ncu, profiles/): the kernel is SHARED-MEMORY-BANDWIDTH bound, not tensor- or ALU-bound —
+// both operands of every tcgen05.mma stream from shared memory (192 KB per tile = 1536 cycles at 128 B/cycle, exactly the
+// tensor time) while the producer / epilogue stores and the broadcast loads add ~1500 wavefronts per tile on the same
+// banks; period ~2900 cycles per tile.  Variants that ADD shared-memory traffic or fixed latencies lost: cp.async gathers
+// transformed in place (+512 wavefronts), two alternating EPILOGUE2 groups, one polling lane per warp.  The next step is
+// structural: layer-2's A operand (H1) in TMEM via tcgen05.st (TS-mode MMA), which removes a third of the traffic.
 //
 //   warps 0-3    EPILOGUE2  D2[t%2] -> +b2, ReLU, fp16 -> H2 chunk by chunk
 //   warps 4-11   EPILOGUE3  D3 (channel per lane) -> max over a centroid's 64 samples, +b3, ReLU -> out
@@ -54,9 +60,11 @@ struct Cfg {
 constexpr int THREADS = 22 * 32;
 constexpr int PRODUCERS = 256;
 
-__device__ __forceinline__ uint32_t pack_relu(float2 v) {  // fp16x2(max(v, 0)): rounding is monotone, so relu commutes
-  __half2 h = __hmax2(__float22half2_rn(v), __float2half2_rn(0.f));
-  return *reinterpret_cast<uint32_t*>(&h);
+// fp16x2{v.x, v.y} = relu(round(.)) in ONE instruction (F2FP.RELU.F16.F32.PACK_AB); rounding is monotone, so relu commutes
+__device__ __forceinline__ uint32_t pack_relu(float2 v) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(v.y), "f"(v.x));
+  return d;
 }
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

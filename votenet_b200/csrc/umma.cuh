@@ -66,6 +66,8 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
     if (spin > (1u << 26)) __trap();
 }
+// (Tried and rejected, measured on both SA kernels: polling / arriving with ONE lane per warp + __syncwarp instead of all
+// lanes — 35-45 % slower; the hardware try_wait of a full warp is cheaper than the divergent region around one lane.)
 
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma / bulk copies read through it)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
