@@ -205,6 +205,8 @@ def main():
                     help="CTAs per FPS cluster (4 = 32 SMs per batch: best throughput with steps overlapped; 8 = lowest latency)")
     ap.add_argument("--fps-variant", type=int, default=None, help="0: register/cluster FPS kernel, 1: bucket-pruned (default)")
     ap.add_argument("--fps-threads", type=int, default=None, help="tuning: threads per FPS CTA (256/512/1024)")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE", help="vnb_set_tuning knob (repeatable)")
+    ap.add_argument("--debug-skip-fps1", action="store_true", help="experiment only: reuse the warm-up step's SA1 FPS result")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -236,11 +238,19 @@ def main():
         _check(lib.vnb_set_tuning(b"fps_threads", args.fps_threads))
     if args.fps_variant is not None:
         _check(lib.vnb_set_tuning(b"fps_variant", args.fps_variant))
+    trap_buf = torch.zeros(8, dtype=torch.int32).pin_memory()  # filled by a device-side bounded wait that gives up
+    _check(lib.vnb_debug_trap_buffer(trap_buf.data_ptr()))
+    global TRAP_BUF
+    TRAP_BUF = trap_buf
+    for kv in args.tune:
+        k, v = kv.split("=")
+        _check(lib.vnb_set_tuning(k.encode(), int(v)))
     peaks = _peaks()
     cfg = VoteNetConfig()  # BASELINE.json: 20 000 points, (xyz + height)
     B, N = CLOUDS_PER_RANK, cfg.num_points
     w = make_synthetic_weights(cfg, 0)
     eng = Engine(cfg, w, B, device=dev, precision=args.precision, use_graph=not args.no_graph, slots=args.inflight)
+    eng.debug_skip_fps1 = args.debug_skip_fps1
 
     # ---- synthetic inputs: this rank's clouds; a ring of RING device-resident batches (164 MB > the 126 MB L2) so that
     #      a step's inputs are never L2-resident from an earlier step
@@ -361,5 +371,13 @@ def main():
         dist.destroy_process_group()
 
 
+TRAP_BUF = None
+
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception:
+        if TRAP_BUF is not None:
+            print("device-side trap record {line, blockDim, blockIdx, threadIdx, gridDim}:", TRAP_BUF[:5].tolist(),
+                  file=sys.stderr, flush=True)
+        raise

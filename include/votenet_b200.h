@@ -41,6 +41,9 @@ int vnb_debug_fps_profile(void* device_buffer_16x8_i64);
 /* Debugging aid: when given a device buffer of 8 x 64 x 2 int64, CTA 0 of the next fused-SA launches stamps clock64() at
  * the start / end of every pipeline stage (roles P, M1, M2, M3, E1, E2, E3a, E3b) of its first 64 tiles; NULL = off. */
 int vnb_debug_sa_trace(void* device_buffer_8x64x2_i64);
+/* debugging aid: host-mapped int[8]; a bounded device-side wait that gives up stores {source line, blockDim.x,
+ * blockIdx.x, threadIdx.x, gridDim.x} there before it traps */
+int vnb_debug_trap_buffer(void* host_mapped_int8);
 
 /* ------------------------------------------------------------------ tf_ops/sampling ------------------- */
 

@@ -27,6 +27,7 @@ _SIGS = {
     "vnb_set_tuning": ([C.c_char_p, _i], _i),
     "vnb_debug_fps_profile": ([_p], _i),
     "vnb_debug_sa_trace": ([_p], _i),
+    "vnb_debug_trap_buffer": ([_p], _i),
     "vnb_fps_nested_workspace_bytes": ([_i, _i], _sz),
     "vnb_farthest_point_sample_nested": ([_i, _i, _i, _p, _p, _p, _p], _i),
     "vnb_query_ball_point_workspace_bytes": ([_i, _i], _sz),

@@ -35,6 +35,28 @@ static inline int check_launch(const char* what) {
     if (_e != cudaSuccess) return ::vnb::set_err(VNB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
   } while (0)
 
+// Debugging aid: where did a bounded wait give up?  vnb_debug_trap_buffer(p) hands every translation unit a pointer to
+// host-mapped memory; a trap site stores {line, blockDim.x, blockIdx.x, threadIdx.x, gridDim.x} there before __trap().
+void register_trap_setter(void (*fn)(int*));
+#ifdef __CUDACC__
+static __device__ int* g_trap_slot = nullptr;  // one copy per translation unit
+__device__ __noinline__ static void trap_at(int line) {
+  if (g_trap_slot != nullptr) {
+    volatile int* t = g_trap_slot;
+    t[1] = (int)blockDim.x; t[2] = (int)blockIdx.x; t[3] = (int)threadIdx.x; t[4] = (int)gridDim.x; t[0] = line;
+    __threadfence_system();
+  }
+  __trap();
+}
+namespace {
+struct TrapRegistration {
+  TrapRegistration() {
+    register_trap_setter([](int* p) { cudaMemcpyToSymbol(g_trap_slot, &p, sizeof(p)); });
+  }
+} g_trap_registration;
+}  // namespace
+#endif
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

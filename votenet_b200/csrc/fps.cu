@@ -35,6 +35,8 @@ namespace vnb {
 
 extern int g_bq_variant;
 extern int g_sa_variant;
+extern int g_sa_sms;
+extern int g_sa_split;
 int g_fps_mode = 1;   // 0: cluster barrier per round, 1: CTA champions in tagged slots + polling (default)
 int g_fps_cl = 0;     // 0: automatic cluster size, else forced (power of two <= 16)
 int g_fps_threads = 256;  // threads per CTA of the cluster kernel (256 / 512 / 1024)
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(T) fps_cluster_kernel(int n, int m, int CL, co
           do {
             a = ld_volatile_v4(&s_xa[par][lane]);
             bq = ld_volatile_v2(&s_xb[par][lane]);
-            if (++spin > (1u << 22)) __trap();  // protocol bug: trap instead of hanging the GPU
+            if (++spin > (1u << 22)) trap_at(__LINE__);  // protocol bug: trap instead of hanging the GPU
           } while ((a.y >> 16) != tag || bq.y != tag);
         }
         __syncwarp();
@@ -355,6 +357,8 @@ extern "C" int vnb_set_tuning(const char* key, int value) {
   else if (k == "fps_variant") g_fps_variant = value;
   else if (k == "ball_query_variant") vnb::g_bq_variant = value;
   else if (k == "sa_variant") vnb::g_sa_variant = value;
+  else if (k == "sa_sms") vnb::g_sa_sms = value;
+  else if (k == "sa_split") vnb::g_sa_split = value < 1 ? 1 : value;
   else return set_err(VNB_ERR_INVALID, "set_tuning: unknown key %s", key);
   return VNB_OK;
 }

@@ -41,6 +41,8 @@ int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* 
                      const void* w2_img, const void* w3_img, float* out, void* workspace, cudaStream_t st);  // sa1_ws2.cu
 int linear_tc(int rows, int cin, int cout, const float* in, const void* w_img, const float* bias, const float* res,
               int act, float* out_f32, void* out_f16, cudaStream_t st);  // linear_tc.cu
+int g_sa_sms = 0;    // tuning: SMs the fused SA kernels size their grid for (0 = all)
+int g_sa_split = 1;  // tuning: CTAs (chunks of tiles) per SM
 int g_sa_variant = 2;  // 0: single-role kernel (sa_tc_kernel), 1: warp-specialised pipeline, first generation,
                        // 2: second generation (one MMA issuer per layer, one wave) where available
 

@@ -5,6 +5,8 @@
 
 #include <math.h>
 
+#include <vector>
+
 namespace vnb {
 
 static thread_local char g_err[512] = "";
@@ -12,6 +14,11 @@ static unsigned long long g_launches = 0;
 int g_bq_variant = 1;  // 0: brute-force scan, 1: cell grid + index bitmap (needs the workspace entry point)
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 char* err_buf() { return g_err; }
+static std::vector<void (*)(int*)>& trap_setters() {
+  static std::vector<void (*)(int*)> v;
+  return v;
+}
+void register_trap_setter(void (*fn)(int*)) { trap_setters().push_back(fn); }
 int set_err(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -290,6 +297,11 @@ extern "C" {
 
 int vnb_abi_version(void) { return VNB_ABI_VERSION; }
 const char* vnb_last_error(void) { return err_buf(); }
+// debugging aid (not part of the drop-in boundary): host-mapped int[8] that a bounded wait fills in before it traps
+int vnb_debug_trap_buffer(void* host_mapped_int8) {
+  for (auto fn : vnb::trap_setters()) fn(static_cast<int*>(host_mapped_int8));
+  return VNB_OK;
+}
 unsigned long long vnb_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int vnb_gather_point(int b, int n, int m, const float* inp, const int* idx, float* out, void* stream) {

@@ -131,6 +131,10 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
   for (int i = tid; i < 2 * A0_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA0)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < (128 * 128 + C2 * 128) / 16; i += THREADS) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0) tmem_alloc(tmem_ptr, TM_COLS);
+  // No thread may touch an mbarrier before thread 0 has initialised it: the previous CTA on this SM (possibly another
+  // kernel) leaves arbitrary bytes there, and re-initialising a barrier other threads are parked on is undefined — seen
+  // as sporadic launch failures when different fused kernels alternate on an SM (scripts/gpu_stress.py, mix "sa_all").
+  __syncthreads();
   mbar_wait(bar_w, 0);  // weight images have landed (every thread observes the barrier: the patch below follows the copy)
   __syncthreads();
   // Biases of layers 1 and 2 ride on the tensor cores (an epilogue pass is ALU-pipe bound, profiles/micro_thr.txt):
@@ -366,6 +370,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
 extern int g_sa_variant;  // mlp_tc.cu
 long long* g_sa_trace = nullptr;  // debugging: device buffer of 12 x 64 x 2 int64 (vnb_debug_sa_trace)
 
+extern int g_sa_sms, g_sa_split;  // mlp_tc.cu
 void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx, void* rel,
                       cudaStream_t st);  // sa_ws.cu
 
@@ -383,6 +388,8 @@ int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* 
   launch_group_rel(n, m, rows, xyz, new_xyz, idx, workspace, st);
   if (int rc = check_launch("sa_group_mlp_max: grouped relative coordinates")) return rc;
   const int ntiles = b * m / 2;
+  if (g_sa_sms > 0 && g_sa_sms < sms) sms = g_sa_sms;  // leave room for concurrently running FPS CTAs
+  sms *= g_sa_split;
   const int tpc = (ntiles + sms - 1) / sms;          // one wave: one CTA per SM, contiguous chunks
   const int grid = (ntiles + tpc - 1) / tpc;
   kern<<<grid, s1v2::THREADS, s1v2::SMEM, st>>>(c, b * m, tpc, static_cast<const float4*>(workspace), feat, b1, b2, b3,

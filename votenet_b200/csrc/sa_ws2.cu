@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
 
 }  // namespace s2v2
 
+extern int g_sa_sms, g_sa_split;  // mlp_tc.cu
 void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx, void* rel,
                       cudaStream_t st);  // sa_ws.cu
 
@@ -324,6 +325,8 @@ static int s2v2_launch(int b, int n, int m, const float* xyz, const float* new_x
   const long long rows = (long long)b * m * 64;
   launch_group_rel(n, m, rows, xyz, new_xyz, idx, workspace, st);
   if (int rc = check_launch("sa_group_mlp_max: grouped relative coordinates")) return rc;
+  if (g_sa_sms > 0 && g_sa_sms < sms) sms = g_sa_sms;  // leave room for concurrently running FPS CTAs
+  sms *= g_sa_split;
   const int tpc = (ntiles + sms - 1) / sms;          // one wave: one CTA per SM, contiguous chunks
   const int grid = (ntiles + tpc - 1) / tpc;
   kern<<<grid, s2v2::THREADS, K::SMEM, st>>>(b * m, tpc, static_cast<const float4*>(workspace), w1x, b2, b3,

@@ -54,18 +54,20 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_at(uint64_t* bar, uint32_t parity, int line) {
   if (mbar_try_wait(bar, parity)) return;
   for (uint32_t spin = 0; !mbar_try_wait_hint(bar, parity, 20000u); ++spin)
-    if (spin > (1u << 20)) __trap();
+    if (spin > (1u << 20)) vnb::trap_at(line);
 }
+#define mbar_wait(bar, parity) mbar_wait_at(bar, parity, __LINE__)
 
 // Tight polling wait for the single-thread MMA issuers: the parked form above wakes ~300 cycles after the arrive
 // (measured, vnb_debug_sa_trace), which sits on the critical path of every tile; one polling thread costs next to nothing.
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_spin_at(uint64_t* bar, uint32_t parity, int line) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-    if (spin > (1u << 26)) __trap();
+    if (spin > (1u << 26)) vnb::trap_at(line);
 }
+#define mbar_wait_spin(bar, parity) mbar_wait_spin_at(bar, parity, __LINE__)
 // (Tried and rejected, measured on both SA kernels: polling / arriving with ONE lane per warp + __syncwarp instead of all
 // lanes — 35-45 % slower; the hardware try_wait of a full warp is cheaper than the divergent region around one lane.)
 

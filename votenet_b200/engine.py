@@ -66,6 +66,7 @@ class Engine:
             self.slots = [self._make_slot() for _ in range(slots)]
         self._step = 0
         self.launches_per_forward = None
+        self.debug_skip_fps1 = False  # experiment only: capture the graph without the SA1 FPS launch
         self.timeline = None   # debugging: set to [] (with use_graph=False) to collect (step, stage, event) marks
 
     # ------------------------------------------------------------------------------------------------ weights
@@ -191,7 +192,8 @@ class Engine:
         src = s.xyz
         for li, l in enumerate(s.lv):
             if li == 0:   # the only real search (raw cloud); deeper levels sample an FPS-ordered set
-                check(lib.vnb_farthest_point_sample(B, l.n, l.m, dptr(src), dptr(l.fps), _sp(samp)))
+                if not (self.debug_skip_fps1 and s.used):
+                    check(lib.vnb_farthest_point_sample(B, l.n, l.m, dptr(src), dptr(l.fps), _sp(samp)))
             else:
                 check(lib.vnb_farthest_point_sample_nested(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws), _sp(samp)))
             check(lib.vnb_gather_point(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(l.xyz), _sp(samp)))
@@ -287,10 +289,12 @@ class Engine:
             n0 = lib.vnb_launch_count()
             self._enqueue(s, main)
             self.launches_per_forward = int(lib.vnb_launch_count() - n0)
+            s.used = True
         else:
             if s.graph is None:
                 # warm-up outside capture (sets function attributes, packs nothing new), then capture
                 self._enqueue(s, main)
+                s.used = True
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
                 cap = torch.cuda.Stream(device=self.device)
