@@ -40,34 +40,71 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML every 5 ms (pynvml), with
+    `nvidia-smi --query-gpu` polling as the fallback when NVML cannot be loaded."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+        self.index, self.stop_flag, self.rows, self.max_mhz, self.source = index, threading.Event(), [], None, "nvml"
+        self.h = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except ValueError:
+                    phys = index
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h, self.source = None, "nvidia-smi"
+
+    def _sample_nvml(self):
+        nv = self.nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+        self.rows.append((mhz, [bool(r & b) for b in bits]))
+
+    def _sample_smi(self):
+        o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=5).stdout.strip()
+        if o:
+            f = [x.strip() for x in o.split(",")]
+            self.max_mhz = float(f[1])
+            self.rows.append((float(f[0]), [x.lower().startswith("active") for x in f[2:6]]))
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag.is_set():
             try:
-                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                if self.h is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.005 if self.h is not None else 0.2)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0, "source": self.source}
+        sm = [r[0] for r in self.rows]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[1][i] for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.rows), "source": self.source}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -144,13 +181,14 @@ def cpu_baseline(cfg, w, budget_s=20.0):
 
 
 def kernel_table(eng, cfg, peaks, flush):
-    """Per-kernel device time (CUDA events on the launching stream, L2 flushed before each launch) and roofline
-    fraction from ALGORITHMIC bytes / flops (SURVEY.md §8(d) per-cloud figures x batch)."""
+    """Per-stage device time (CUDA events on the launching stream, L2 flushed before each launch, each stage launched
+    alone) and roofline fraction from ALGORITHMIC bytes / flops (SURVEY.md §8(d) per-cloud figures x batch)."""
     from votenet_b200._lib import check, dptr, lib, stream_ptr
 
     B = eng.B
     s = eng.slots[0]
     st = torch.cuda.current_stream()
+    sp = stream_ptr
 
     def t(fn, it=5):
         fn(); torch.cuda.synchronize()
@@ -163,31 +201,107 @@ def kernel_table(eng, cfg, peaks, flush):
         return float(np.mean(ts))
 
     rows = []
-    src = s.xyz
-    c = cfg.feature_dim
-    feat = s.feat
+
+    def hbm(name, ms, byt, note=None):
+        r = dict(kernel=name, ms=ms, bound="hbm", algo_bytes=byt, achieved=byt / ms / 1e6, peak=peaks["hbm"], unit="GB/s")
+        if note:
+            r["note"] = note
+        rows.append(r)
+
+    def tensor(name, ms, fl):
+        rows.append(dict(kernel=name, ms=ms, bound="tensor", algo_flops=fl, achieved=fl / ms / 1e9, peak=peaks["tc_burst"],
+                         unit="TFLOP/s"))
+
+    def mlp_flops(rows_, cin, widths):
+        fl = 0
+        for co in widths:
+            fl += cin * co; cin = co
+        return 2.0 * rows_ * fl
+
+    onchip = "on-chip kernel: achieved = streaming-equivalent bytes (m-1)*n*16 B per cloud / time (may exceed the HBM peak)"
+    src, c, feat = s.xyz, cfg.feature_dim, s.feat
     for li, l in enumerate(s.lv):
         sa = cfg.sa[li]
-        ms = t(lambda: check(lib.vnb_farthest_point_sample(B, l.n, l.m, dptr(src), dptr(l.fps), stream_ptr())))
-        byt = B * (l.m - 1) * l.n * 16
-        rows.append(dict(kernel=f"fps_sa{li + 1}", ms=ms, bound="hbm(streaming-equivalent; on-chip kernel)", algo_bytes=byt,
-                         achieved=byt / ms / 1e6, peak=peaks["hbm"], unit="GB/s"))
+        if li == 0:
+            ms = t(lambda: check(lib.vnb_farthest_point_sample(B, l.n, l.m, dptr(src), dptr(l.fps), sp())))
+            hbm("fps_sa1", ms, B * (l.m - 1) * l.n * 16, onchip)
+        else:  # FPS of an FPS-ordered set: parallel proof of the identity prefix (sequential kernel only on failure)
+            ms = t(lambda: check(lib.vnb_farthest_point_sample_nested(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws), sp())))
+            hbm(f"fps_sa{li + 1}_nested", ms, B * (l.m - 1) * l.n * 16, onchip)
         ms = t(lambda: check(lib.vnb_query_ball_point_ws(B, l.n, l.m, float(sa.radius), 64, dptr(src), dptr(l.xyz), dptr(l.idx),
-                                                         dptr(l.cnt), dptr(l.bq_ws), stream_ptr())))
-        byt = B * (l.n * 12 + l.m * 12 + l.m * 256 + l.m * 4)
-        rows.append(dict(kernel=f"ball_query_sa{li + 1}", ms=ms, bound="hbm", algo_bytes=byt, achieved=byt / ms / 1e6,
-                         peak=peaks["hbm"], unit="GB/s"))
+                                                         dptr(l.cnt), dptr(l.bq_ws), sp())))
+        hbm(f"ball_query_sa{li + 1}", ms, B * (l.n * 12 + l.m * 12 + l.m * 256 + l.m * 4), "latency-bound (compulsory bytes only)")
         ms = t(lambda: eng._sa(li, src, feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, st, s.sa_ws))
-        cin = 3 + c
-        fl = 0
-        for co in sa.mlp:
-            fl += cin * co; cin = co
-        fl = 2.0 * B * l.m * 64 * fl
-        rows.append(dict(kernel=f"sa{li + 1}_group_mlp_max", ms=ms, bound="tensor", algo_flops=fl, achieved=fl / ms / 1e9,
-                         peak=peaks["tc_burst"], unit="TFLOP/s"))
+        tensor(f"sa{li + 1}_group_mlp_max", ms, mlp_flops(B * l.m * 64, 3 + c, sa.mlp))
         src, feat, c = l.xyz, l.feat, sa.mlp[-1]
-    for r in rows:
-        r["frac"] = r["achieved"] / r["peak"]
+    # feature propagation: three_nn + (interpolate/concat + 2 x (1x1 conv + BN + ReLU)); voting module
+    from votenet_b200.utils import fp_module_fused
+    ns, cf = s.lv[1].m, cfg.seed_feat_dim
+    for f, scope, u, kx in zip(s.fp, ("fp1", "fp2"), (s.lv[2].xyz, s.lv[1].xyz), (s.lv[3].xyz, s.lv[2].xyz)):
+        ms = t(lambda: check(lib.vnb_three_nn(B, f.n, f.m, dptr(u), dptr(kx), dptr(f.dist), dptr(f.idx), sp())))
+        hbm(f"three_nn_{scope}", ms, B * (f.n * 12 + f.m * 12 + f.n * 24), "latency-bound (compulsory bytes only)")
+    f1, f2 = s.fp
+    fl_fp1 = mlp_flops(B * f1.n, f1.c1 + f1.c2, cfg.fp_mlp)
+    fl_fp2 = mlp_flops(B * f2.n, f2.c1 + f2.c2, cfg.fp_mlp)
+    fl_vote = mlp_flops(B * ns, 3 + cf, cfg.vote_units)
+    if eng.fuse_fp:
+        ms = t(lambda: fp_module_fused(f1.dist, f1.idx, s.lv[2].feat, s.lv[3].feat,
+                                       [eng.store.layer(f"fp1/conv_{i}") for i in range(2)], f1.h[-1], stream=st))
+        tensor("fp1_interpolate_mlp_fused", ms, fl_fp1)
+        ms = t(lambda: fp_module_fused(f2.dist, f2.idx, s.lv[1].feat, f1.h[-1].view(B, f1.n, -1),
+                                       [eng.store.layer(f"fp2/conv_{i}") for i in range(2)], f2.h[-1],
+                                       vote=(eng.vote_fused, eng.vote_x0, s.lv[1].xyz, s.votes_xyz, s.votes_feat), stream=st))
+        tensor("fp2_interpolate_mlp_vote_fused", ms, fl_fp2 + fl_vote)
+    else:
+        pts2 = s.lv[3].feat
+        for f, skip, scope, fl in zip(s.fp, (s.lv[2].feat, s.lv[1].feat), ("fp1", "fp2"), (fl_fp1, fl_fp2)):
+            def fp_fn(f=f, skip=skip, scope=scope, pts2=pts2):
+                check(lib.vnb_fp_interpolate_concat(B, f.n, f.m, f.c1, f.c2, dptr(f.dist), dptr(f.idx), dptr(skip), dptr(pts2),
+                                                    dptr(f.cat), sp()))
+                x = f.cat
+                for i in range(len(cfg.fp_mlp)):
+                    eng._linear(B * f.n, x, eng.store.layer(f"{scope}/conv_{i}"), True, f.h[i], None, st)
+                    x = f.h[i]
+            ms = t(fp_fn)
+            tensor(f"{scope}_interpolate_mlp", ms, fl)
+            pts2 = f.h[-1]
+
+        def vote_fn():
+            check(lib.vnb_concat2(B * ns, 3, cf, dptr(s.lv[1].xyz), dptr(pts2), dptr(s.seeds), sp()))
+            x = s.seeds
+            nv = len(cfg.vote_units)
+            for i in range(nv):
+                eng._linear(B * ns, x, eng.store.layer(f"voting{i}"), i < nv - 1, s.vh[i], None, st,
+                            residual=s.seeds if i == nv - 1 else None)
+                x = s.vh[i]
+            check(lib.vnb_split2(B * ns, 3, cf, dptr(x), dptr(s.votes_xyz), dptr(s.votes_feat), sp()))
+        ms = t(vote_fn)
+        tensor("vote_mlp", ms, fl_vote)
+    p = cfg.proposal
+
+    def prop_fn():
+        check(lib.vnb_farthest_point_sample_nested(B, ns, p.npoint, dptr(s.lv[1].xyz), dptr(s.p_fps), dptr(s.fps_ws), sp()))
+        check(lib.vnb_gather_point(B, ns, p.npoint, dptr(s.votes_xyz), dptr(s.p_fps), dptr(s.p_xyz), sp()))
+        check(lib.vnb_query_ball_point(B, ns, p.npoint, float(p.radius), 64, dptr(s.votes_xyz), dptr(s.p_xyz), dptr(s.p_idx),
+                                       dptr(s.p_cnt), sp()))
+        eng._sa(len(cfg.sa), s.votes_xyz, s.votes_feat, ns, cf, s.p_xyz, s.p_idx, p.npoint, s.p_q, s.p_feat, st, s.sa_ws)
+        x = s.p_feat
+        for i in range(len(p.mlp2)):
+            eng._linear(B * p.npoint, x, eng.store.layer(f"proposal/conv_post_{i}"), i < len(p.mlp2) - 1, s.p_h[i], None, st)
+            x = s.p_h[i]
+    ms = t(prop_fn)
+    tensor("proposal_fps_ballquery_group_mlp", ms, mlp_flops(B * p.npoint * 64, 3 + cf, p.mlp) + mlp_flops(B * p.npoint, p.mlp[-1], p.mlp2))
+    r = s.rec
+
+    def nms_fn():
+        check(lib.vnb_decode_boxes(B, p.npoint, dptr(s.p_xyz), dptr(s.p_h[-1]), dptr(eng.mean_size), dptr(r.bboxes),
+                                   dptr(r.scores), dptr(r.objectness), dptr(r.class_scores), sp()))
+        check(lib.vnb_nms3d(B, p.npoint, dptr(r.bboxes), dptr(r.scores), dptr(r.objectness), float(cfg.nms_iou), dptr(r.keep),
+                            dptr(r.nms_idx), dptr(r.nms_count), dptr(s.nms_ws), sp()))
+    ms = t(nms_fn)
+    hbm("decode_nms3d", ms, B * (p.npoint * (79 + 3) * 4 + eng.record_nbytes // B), "latency-bound (compulsory bytes only)")
+    for r_ in rows:
+        r_["frac"] = r_["achieved"] / r_["peak"]
     return rows
 
 
@@ -309,6 +423,7 @@ def main():
             st.wait_event(e0)
         for i in range(K):
             step_fn(W + i)
+        enq = time.time() - t0
         for st in streams:
             ctl.wait_stream(st)
         e1.record(ctl)
@@ -322,13 +437,13 @@ def main():
             tt = torch.tensor([ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
-        return ms, wall, int(lib.vnb_launch_count() - n0)
+        return ms, wall, enq
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms_dev, wall_dev, _ = timed(step_device, args.steps, args.warmup)
+    ms_dev, wall_dev, enq_dev = timed(step_device, args.steps, args.warmup)
     sampler.stop_flag.set()
-    ms_e2e, wall_e2e, _ = timed(step_host, args.steps, args.warmup)
+    ms_e2e, wall_e2e, enq_e2e = timed(step_host, args.steps, args.warmup)
     lpf = eng.launches_per_forward or 0
     launches = lpf * args.steps + (args.steps if world > 1 else 0)
 
@@ -346,8 +461,7 @@ def main():
         roof = {"kernel": dom["kernel"], "bound": "hbm" if dom["unit"] == "GB/s" else "tensor", "achieved": dom["achieved"],
                 "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic,
                 "peak_source": peaks["src"], "ms_per_launch": dom["ms"],
-                "note": "FPS is an on-chip (register/DSMEM) kernel: achieved = streaming-equivalent bytes (m-1)*n*16 B per "
-                        "cloud / time, so it may exceed the HBM peak" if dom["kernel"].startswith("fps") else ""}
+                "note": dom.get("note", "")}
         cpu = None if args.no_cpu_baseline else cpu_baseline(cfg, w)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -364,7 +478,8 @@ def main():
                 "gpu_launches": launches, "launches_per_forward": lpf,
                 "roofline": roof, "kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in ktab],
                 "cpu_baseline": cpu, "clocks": sampler.summary(),
-                "wall_s": {"device_loop": wall_dev, "e2e_loop": wall_e2e}}
+                "wall_s": {"device_loop": wall_dev, "e2e_loop": wall_e2e},
+                "host_enqueue_ms_per_step": {"device_loop": 1e3 * enq_dev / args.steps, "e2e_loop": 1e3 * enq_e2e / args.steps}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -166,6 +166,24 @@ size_t vnb_sa_workspace_bytes(int b, int m, int nsample);
 int vnb_fp_interpolate_concat(int b, int n, int m, int c1, int c2, const float* dist, const int* idx,
                               const float* points1, const float* points2, float* out, void* stream);
 
+/* pointnet_fp_module (utils.py:266-294) as ONE tensor-core kernel, optionally followed by the voting module
+ * (model.py:53-61) in the same kernel: a CTA walks 128 rows through every layer, activations stay on the SM
+ * (csrc/fp_chain.cu).  dist / idx from vnb_three_nn; points1 (b,n,256) skip features; points2 (b,m,256) known features.
+ *   fp layers (n_fp_layers == 2, widths [256,256]): packed images (vnb_pack_weight_f16) of the BN-folded weights
+ *     (512,256) and (256,256), biases; fp_out (b*n,256) f32 receives the module's output (the seed features).
+ *   vote layers (n_vote_layers == 0 or 3, widths [256,256,259]): vote_w_img[0] = image of rows 3.. of the first FC weight
+ *     (K = 256; its xyz rows 0..2 are passed as vote_w0_xyz_f32 (3,256) f32 and applied as an fp32 rank-3 update);
+ *     vote_w_img[2] / vote_bias[2] = last FC with its 259 output columns permuted [3..258, 0..2];
+ *     seeds_xyz (b*n,3) -> votes_xyz (b*n,3) = seeds_xyz + offset[:, :3], votes_feat (b*n,256) = fp_out + offset[:, 3:].
+ * The pointer arrays are HOST arrays of device pointers (read during the call).  Tensor-core path only (fp16
+ * operands, fp32 accumulation); other widths return VNB_ERR_INVALID (use the unfused entry points). */
+int vnb_fp_module_fused(int b, int n, int m, int c1, int c2, const float* dist, const int* idx, const float* points1,
+                        const float* points2, int n_fp_layers, const void* const* fp_w_img,
+                        const float* const* fp_bias, const int* fp_cout, float* fp_out, int n_vote_layers,
+                        const void* const* vote_w_img, const float* const* vote_bias, const int* vote_cout,
+                        const float* vote_w0_xyz_f32, const float* seeds_xyz, float* votes_xyz, float* votes_feat,
+                        void* stream);
+
 /* row-wise concat / split helpers: out (rows, ca+cb) = [a (rows,ca), b (rows,cb)]  and the inverse */
 int vnb_concat2(int rows, int ca, int cb, const float* a, const float* b, float* out, void* stream);
 int vnb_split2(int rows, int ca, int cb, const float* in, float* a, float* b, void* stream);

@@ -135,6 +135,59 @@ def test_fp_module_and_helpers(cuda):
     assert torch.equal(a2, a) and torch.equal(b2, bb)
 
 
+@pytest.mark.parametrize("b,n,m", [(2, 512, 256), (3, 200, 77), (8, 1024, 512)])
+def test_fp_vote_fused(cuda, b, n, m):
+    """vnb_fp_module_fused (fp module + voting module in one tensor-core kernel) against the dense oracle
+    (utils.py:266-294 + model.py:53-61), and against the unfused kernels; ragged row counts included."""
+    from votenet_b200 import utils as U
+    from votenet_b200.tf_interpolate import three_nn
+
+    rng = np.random.default_rng(1234 + n)
+    xyz1 = rng.random((b, n, 3), dtype=np.float32); xyz2 = rng.random((b, m, 3), dtype=np.float32)
+    p1 = rng.standard_normal((b, n, 256)).astype(np.float32); p2 = rng.standard_normal((b, m, 256)).astype(np.float32)
+    g = torch.Generator().manual_seed(9)
+    w = {}
+    for name, cin, cout, bn in (("fp2/conv_0", 512, 256, True), ("fp2/conv_1", 256, 256, True), ("voting0", 259, 256, True),
+                                ("voting1", 256, 256, True), ("voting2", 256, 259, False)):
+        w[f"{name}/W"] = torch.randn(cin, cout, generator=g) * (2.0 / cin) ** 0.5
+        w[f"{name}/b"] = torch.randn(cout, generator=g) * 0.05
+        if bn:
+            w[f"{name}/bn/gamma"] = torch.rand(cout, generator=g) * 0.4 + 0.8
+            w[f"{name}/bn/beta"] = torch.randn(cout, generator=g) * 0.05
+            w[f"{name}/bn/mean/EMA"] = torch.randn(cout, generator=g) * 0.05
+            w[f"{name}/bn/variance/EMA"] = torch.rand(cout, generator=g) * 0.4 + 0.8
+    seeds_feat, _ = D.pointnet_fp_module(torch.as_tensor(xyz1), torch.as_tensor(xyz2), torch.as_tensor(p1),
+                                         torch.as_tensor(p2), (256, 256), "fp2", w)
+    seeds = torch.cat([torch.as_tensor(xyz1), seeds_feat], 2)
+    off = seeds.reshape(-1, 259)
+    for i in range(3):
+        off = D.dense_layer(off, w, f"voting{i}")
+    votes = (seeds + off.reshape(seeds.shape)).numpy()
+
+    store = U.WeightStore(w, device=cuda, precision=1)
+    txyz1, txyz2, tp1, tp2 = T(xyz1, cuda), T(xyz2, cuda), T(p1, cuda), T(p2, cuda)
+    dist, idx = three_nn(txyz1, txyz2)
+    fp_out = torch.empty((b, n, 256), device=cuda)
+    vx = torch.empty((b, n, 3), device=cuda); vf = torch.empty((b, n, 256), device=cuda)
+    vl, x0 = U.vote_layers_fused(store, ["voting0", "voting1", "voting2"])
+    U.fp_module_fused(dist, idx, tp1, tp2, [store.layer("fp2/conv_0"), store.layer("fp2/conv_1")], fp_out,
+                      vote=(vl, x0, txyz1, vx, vf))
+    torch.cuda.synchronize()
+    assert rel_err(fp_out.cpu().numpy(), seeds_feat.numpy()) < TOL_TC
+    assert rel_err(vf.cpu().numpy(), votes[..., 3:]) < TOL_TC
+    assert np.abs(vx.cpu().numpy() - votes[..., :3]).max() < TOL_TC * max(1.0, np.abs(votes[..., :3]).max())
+    # fp-only form of the same kernel == what pointnet_fp_module dispatches to; and the unfused kernels agree to 1e-3
+    a = U.pointnet_fp_module(txyz1, txyz2, tp1, tp2, [256, 256], "fp2", weights=store)
+    U.FUSE_FP = False
+    try:
+        c = U.pointnet_fp_module(txyz1, txyz2, tp1, tp2, [256, 256], "fp2", weights=store)
+    finally:
+        U.FUSE_FP = True
+    torch.cuda.synchronize()
+    assert torch.equal(a, fp_out)
+    assert rel_err(a.cpu().numpy(), c.cpu().numpy()) < TOL_TC
+
+
 def test_decode_boxes(cuda):
     from votenet_b200 import synth
     from votenet_b200.model import decode_boxes

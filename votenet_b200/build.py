@@ -31,6 +31,7 @@ SOURCES = {
     "sa1_ws.cu": [],
     "sa1_ws2.cu": [],
     "linear_tc.cu": [],
+    "fp_chain.cu": [],
 }
 
 

@@ -2,12 +2,16 @@
 // (FullyConnected / 1x1 Conv2D + folded BN + ReLU of the reference: utils.py:291-292, model.py:53-57, utils.py:149-155;
 //  also the hoisted layer-1 pre-GEMM of the fused SA kernels, see mlp_tc.cu.)
 //
-// One CTA (256 threads) per 128-row x <=128-column output tile.  K is streamed in 128-column chunks through a 2-stage
-// ring: the activation chunk is read from global memory with 16 threads per row (512 contiguous bytes), converted
-// fp32 -> fp16 in registers and written as the 128-byte-swizzled K-major A operand; the weight chunk arrives as ONE bulk
-// copy per 64-column panel of the pre-swizzled image (cp.async.bulk, completes a transaction barrier).  One thread
-// issues tcgen05.mma; tcgen05.commit frees the stage.  Epilogue: TMEM -> registers (row per lane), bias/ReLU/residual,
-// 16-byte vector stores; the eight warps split the columns in two halves.
+// One CTA (256 threads) per 128-row x <=128-column output tile.  K is streamed in 64-column chunks (one SW128 panel)
+// through a 2-stage ring: the activation chunk is read from global memory with 8 threads per row (256 contiguous
+// bytes), converted fp32 -> fp16 in registers and written as the 128-byte-swizzled K-major A operand; the weight chunk
+// arrives as ONE bulk copy of the pre-swizzled image panel (cp.async.bulk, completes a transaction barrier).  One
+// thread issues tcgen05.mma; tcgen05.commit frees the stage.  Epilogue: TMEM -> registers (row per lane),
+// bias/ReLU/residual, 16-byte vector stores; the eight warps split the columns in two halves.
+// A CTA is a chain of latencies (global load -> convert -> barrier -> MMA -> commit), so the kernel is sized for
+// CO-RESIDENCY, not for a big tile: 66 KB of shared memory and 128 TMEM columns per CTA let three CTAs (of this or of
+// another step's launch) share an SM and hide each other's stalls — with several forwards in flight the GPU is
+// throughput-bound on the sum of all kernels' SM-time (scripts/gpu_stress.py).
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -16,8 +20,9 @@ namespace vnb {
 using namespace umma;
 
 constexpr int LT_THREADS = 256;
-constexpr int LT_A_STAGE = 128 * 256;  // 128 rows x 128 k x 2 B
-constexpr int LT_B_STAGE = 128 * 256;  // up to 128 n-rows x 128 k x 2 B
+constexpr int LT_KC = 64;              // K chunk = one 64-column SW128 panel
+constexpr int LT_A_STAGE = 128 * 128;  // 128 rows x 64 k x 2 B
+constexpr int LT_B_STAGE = 128 * 128;  // up to 128 n-rows x 64 k x 2 B
 constexpr int LT_SMEM = 2 * (LT_A_STAGE + LT_B_STAGE) + 512 /*bias*/ + 128 /*barriers*/ + 1024 /*align slack*/;
 
 __device__ __forceinline__ uint32_t lt_pack_h2(float a, float b) {
@@ -25,7 +30,7 @@ __device__ __forceinline__ uint32_t lt_pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(int rows, int cin, int cout, int k_pad, int n_pad,
+__global__ void __launch_bounds__(LT_THREADS, 3) linear_tc_kernel(int rows, int cin, int cout, int k_pad, int n_pad,
                                                                   const float* __restrict__ in,
                                                                   const char* __restrict__ w_img,
                                                                   const float* __restrict__ bias,
@@ -47,7 +52,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(int rows, int 
   const int row0 = blockIdx.x * 128;
   const int nt0 = blockIdx.y * 128;      // first image row (= output column) of this n-tile
   const int nt = min(128, n_pad - nt0);  // multiple of 16
-  const int nchunks = (k_pad + 127) / 128;
+  const int nchunks = (k_pad + LT_KC - 1) / LT_KC;
 
   if (tid == 0) {
     mbar_init(&full_b[0], 1); mbar_init(&full_b[1], 1);
@@ -63,28 +68,25 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(int rows, int 
   const uint32_t tmem_d = *tmem_ptr;
   const uint32_t idesc = make_idesc_f16_f32(128, (uint32_t)nt);
 
-  const int c16 = tid & 15;   // 16-byte (8 x fp16) chunk of the 128-wide K chunk
-  const int rsub = tid >> 4;  // rows rsub, rsub+16, ...
+  const int c8 = tid & 7;     // 16-byte (8 x fp16) chunk of the 64-wide K chunk
+  const int rsub = tid >> 3;  // rows rsub, rsub+32, rsub+64, rsub+96
   const bool vec_in = (cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
 
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1;
-    const int kc0 = c * 128;
-    const int kc = min(128, k_pad - kc0);  // multiple of 16
-    const int npan = (kc + 63) / 64;
+    const int kc0 = c * LT_KC;
+    const int kc = min(LT_KC, k_pad - kc0);  // multiple of 16
     if (c >= 2) mbar_wait(&empty[s], (uint32_t)(((c >> 1) - 1) & 1));  // stage free again
     if (tid == 0) {
-      mbar_arrive_expect_tx(&full_b[s], (uint32_t)(npan * nt * 128));
-      for (int p = 0; p < npan; ++p)
-        bulk_g2s(sB[s] + (size_t)p * nt * 128, w_img + (size_t)((kc0 >> 6) + p) * n_pad * 128 + (size_t)nt0 * 128,
-                 (uint32_t)(nt * 128), &full_b[s]);
+      mbar_arrive_expect_tx(&full_b[s], (uint32_t)(nt * 128));
+      bulk_g2s(sB[s], w_img + (size_t)(kc0 >> 6) * n_pad * 128 + (size_t)nt0 * 128, (uint32_t)(nt * 128), &full_b[s]);
     }
-    if (c16 * 8 < kc) {
-      const int kb = kc0 + c16 * 8;
-      float v[8][8];
+    if (c8 * 8 < kc) {
+      const int kb = kc0 + c8 * 8;
+      float v[4][8];
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {  // all loads first (8 independent 32-byte reads per thread)
-        const int gr = row0 + rsub + 16 * p;
+      for (int p = 0; p < 4; ++p) {  // all loads first (4 independent 32-byte reads per thread)
+        const int gr = row0 + rsub + 32 * p;
         const float* src = in + (size_t)gr * cin + kb;
         if (gr < rows && vec_in && kb + 8 <= cin) {
           const float4 a = __ldg(reinterpret_cast<const float4*>(src));
@@ -96,13 +98,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(int rows, int 
           for (int i = 0; i < 8; ++i) v[p][i] = (gr < rows && kb + i < cin) ? __ldg(src + i) : 0.f;
         }
       }
-      const uint32_t kk = (uint32_t)c16 * 8;
-      uint8_t* dst = sA[s] + (kk >> 6) * (128 * 128);
+      const uint32_t kk = (uint32_t)c8 * 8;
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
+      for (int p = 0; p < 4; ++p) {
         const uint4 pk = make_uint4(lt_pack_h2(v[p][0], v[p][1]), lt_pack_h2(v[p][2], v[p][3]),
                                     lt_pack_h2(v[p][4], v[p][5]), lt_pack_h2(v[p][6], v[p][7]));
-        *reinterpret_cast<uint4*>(dst + sw128_offset((uint32_t)(rsub + 16 * p), kk)) = pk;
+        *reinterpret_cast<uint4*>(sA[s] + sw128_offset((uint32_t)(rsub + 32 * p), kk)) = pk;
       }
     }
     fence_proxy_async_smem();
@@ -111,11 +112,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(int rows, int 
       mbar_wait(&full_b[s], (uint32_t)((c >> 1) & 1));
       tc_fence_after_sync();
       const uint32_t a0 = smem_u32(sA[s]), b0 = smem_u32(sB[s]);
-      for (int ks = 0; ks < kc / 16; ++ks) {
-        const uint32_t pan = (uint32_t)ks >> 2, kin = (uint32_t)ks & 3;
-        mma_f16_ss(tmem_d, make_desc_sw128(a0 + pan * (128 * 128) + kin * 32),
-                   make_desc_sw128(b0 + pan * (uint32_t)(nt * 128) + kin * 32), idesc, (c > 0 || ks > 0) ? 1u : 0u);
-      }
+      for (int ks = 0; ks < kc / 16; ++ks)
+        mma_f16_ss(tmem_d, make_desc_sw128(a0 + (uint32_t)ks * 32), make_desc_sw128(b0 + (uint32_t)ks * 32), idesc,
+                   (c > 0 || ks > 0) ? 1u : 0u);
       mma_commit(&empty[s]);
       if (c == nchunks - 1) mma_commit(done);
     }

@@ -102,7 +102,42 @@ __device__ float intersection2d(const float* b1, const float* b2) {
 }
 
 // :178-192
+// Exact early exits (same boolean as the full evaluation for every input, 0 <= thr <= 1 as validated at :287-300):
+//  * h <= 0 (or NaN): inter3d = 0 * inter2d is 0 or NaN, so iou is +-0 or NaN and `iou > thr` is false;
+//  * the BEV bounding rectangles of the two top faces are separated along x or z by more than `eps`: then the clip has
+//    no vertex (np == 0, area 0, iou 0 or NaN -> false) —
+//      - seg_intersect accepts a point only if it lies inside BOTH segments' coordinate ranges (exact double
+//        comparisons, :92-95), impossible for disjoint ranges;
+//      - point_in_polygon (:53-67) is false when pz is outside the polygon's z-range (no edge straddles), and for pz
+//        inside it the straddling edges come in an even number and the float abscissa
+//        (xj-xi)*(pz-zi)/(zj-zi)+xi lies within ~6e-7 * max|coordinate| of [min x, max x] (four roundings), so a query
+//        more than eps = 1e-4 * max|coordinate| outside that range sees every comparison `px < abscissa` come out
+//        the same and the parity stays even.
+//    NaN coordinates fail every comparison below and take the full path.
+__device__ __forceinline__ bool iou_trivially_false(const float* bi, const float* bj) {
+  const float h = NMS_MIN(bi[1], bj[1]) - NMS_MAX(bi[13], bj[13]);
+  if (!(h > 0.f)) return true;
+  float lo1x = bi[0], hi1x = bi[0], lo1z = bi[2], hi1z = bi[2], lo2x = bj[0], hi2x = bj[0], lo2z = bj[2], hi2z = bj[2];
+#pragma unroll
+  for (int i = 1; i < 4; ++i) {
+    lo1x = fminf(lo1x, bi[i * 3]); hi1x = fmaxf(hi1x, bi[i * 3]);
+    lo1z = fminf(lo1z, bi[i * 3 + 2]); hi1z = fmaxf(hi1z, bi[i * 3 + 2]);
+    lo2x = fminf(lo2x, bj[i * 3]); hi2x = fmaxf(hi2x, bj[i * 3]);
+    lo2z = fminf(lo2z, bj[i * 3 + 2]); hi2z = fmaxf(hi2z, bj[i * 3 + 2]);
+  }
+  const float mag = fmaxf(fmaxf(fmaxf(fabsf(lo1x), fabsf(hi1x)), fmaxf(fabsf(lo1z), fabsf(hi1z))),
+                          fmaxf(fmaxf(fabsf(lo2x), fabsf(hi2x)), fmaxf(fabsf(lo2z), fabsf(hi2z))));
+  const float eps = 1e-4f * mag;
+  bool nan = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    nan = nan || bi[i * 3] != bi[i * 3] || bi[i * 3 + 2] != bi[i * 3 + 2] || bj[i * 3] != bj[i * 3] || bj[i * 3 + 2] != bj[i * 3 + 2];
+  if (nan || !(mag < 1e30f)) return false;
+  return hi1x + eps < lo2x || hi2x + eps < lo1x || hi1z + eps < lo2z || hi2z + eps < lo1z;
+}
+
 __device__ bool iou_greater(const float* bi, const float* bj, float thr) {
+  if (iou_trivially_false(bi, bj)) return false;
   float inter2d = intersection2d(bi, bj);
   float h = NMS_MIN(bi[1], bj[1]) - NMS_MAX(bi[13], bj[13]);
   float inter3d = NMS_MAX(h, 0.f) * inter2d;

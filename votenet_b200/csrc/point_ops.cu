@@ -63,20 +63,28 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) query_ball_kernel(int n, int m,
   const float qx = q[0], qy = q[1], qz = q[2];
   int cnt = 0;
   int first = -1;
-  for (int k0 = 0; k0 < n; k0 += 32) {
-    int k = k0 + lane;
-    bool hit = false;
-    if (k < n) {
-      float dx = qx - p[k * 3 + 0], dy = qy - p[k * 3 + 1], dz = qz - p[k * 3 + 2];
-      hit = d2_ref_gpu(dx, dy, dz) <= d2_max;
+  // 128 points per step: four independent loads / distance tests / ballots in flight, then the four masks are consumed
+  // in index order (so compaction order and the early exit are those of the one-point-at-a-time scan)
+  for (int k0 = 0; k0 < n && cnt < nsample; k0 += 128) {
+    unsigned mask[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + 32 * u + lane;
+      bool hit = false;
+      if (k < n) {
+        const float dx = qx - p[k * 3 + 0], dy = qy - p[k * 3 + 1], dz = qz - p[k * 3 + 2];
+        hit = d2_ref_gpu(dx, dy, dz) <= d2_max;
+      }
+      mask[u] = __ballot_sync(0xffffffffu, hit);
     }
-    unsigned mask = __ballot_sync(0xffffffffu, hit);
-    if (mask) {
-      if (first < 0) first = k0 + __ffs(mask) - 1;
-      int pos = cnt + __popc(mask & ((1u << lane) - 1u));
-      if (hit && pos < nsample) row[pos] = k;
-      cnt += __popc(mask);
-      if (cnt >= nsample) break;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (mask[u] && cnt < nsample) {
+        if (first < 0) first = k0 + 32 * u + __ffs(mask[u]) - 1;
+        const int pos = cnt + __popc(mask[u] & ((1u << lane) - 1u));
+        if (((mask[u] >> lane) & 1u) && pos < nsample) row[pos] = k0 + 32 * u + lane;
+        cnt += __popc(mask[u]);
+      }
     }
   }
   if (cnt > nsample) cnt = nsample;

@@ -15,7 +15,7 @@ import torch
 from ._lib import check, dptr, lib
 from .config import NC, PROPOSAL_CHANNELS, VoteNetConfig
 from .synth import CLASS_MEAN_SIZE
-from .utils import HOIST_MIN_C, PRECISION_TENSOR, Layer, WeightStore
+from .utils import (HOIST_MIN_C, PRECISION_TENSOR, Layer, WeightStore, fp_module_fused, vote_layers_fused)
 
 
 def _sp(stream):
@@ -93,6 +93,13 @@ class Engine:
         for nme in names:
             l = st.layer(nme)
             if self.precision == PRECISION_TENSOR:
+                l.img
+        # fp modules (+ the voting stack behind the last one) as ONE kernel each when the widths are the fused kernel's
+        self.fuse_fp = (self.precision == PRECISION_TENSOR and tuple(cfg.fp_mlp) == (256, 256)
+                        and all(sa.mlp[-1] == 256 for sa in cfg.sa[1:]) and tuple(cfg.vote_units) == (256, 256, 259))
+        if self.fuse_fp:
+            self.vote_fused, self.vote_x0 = vote_layers_fused(st, [f"voting{i}" for i in range(3)])
+            for l in self.vote_fused:
                 l.img
         torch.cuda.synchronize(self.device)
 
@@ -229,25 +236,35 @@ class Engine:
             src_xyz, src_feat, c = l.xyz, l.feat, cfg.sa[li].mlp[-1]
         main.wait_event(e_nn)
         pts2 = s.lv[3].feat
-        for fi, (f, skip, scope) in enumerate(zip(s.fp, (s.lv[2].feat, s.lv[1].feat), ("fp1", "fp2"))):
-            check(lib.vnb_fp_interpolate_concat(B, f.n, f.m, f.c1, f.c2, dptr(f.dist), dptr(f.idx), dptr(skip), dptr(pts2),
-                                                dptr(f.cat), _sp(main)))
-            x = f.cat
-            for i in range(len(cfg.fp_mlp)):
-                self._linear(B * f.n, x, self.store.layer(f"{scope}/conv_{i}"), True, f.h[i], None, main)
-                x = f.h[i]
-            pts2 = x
-        mark("fp", main)
         ns = s.lv[1].m
         cf = cfg.seed_feat_dim
-        check(lib.vnb_concat2(B * ns, 3, cf, dptr(seeds_xyz), dptr(pts2), dptr(s.seeds), _sp(main)))
-        x = s.seeds
-        nv = len(cfg.vote_units)
-        for i in range(nv):
-            self._linear(B * ns, x, self.store.layer(f"voting{i}"), i < nv - 1, s.vh[i], None, main,
-                         residual=s.seeds if i == nv - 1 else None)
-            x = s.vh[i]
-        check(lib.vnb_split2(B * ns, 3, cf, dptr(x), dptr(s.votes_xyz), dptr(s.votes_feat), _sp(main)))
+        if self.fuse_fp:
+            # fp1: interpolate + concat + 2 layers in one kernel; fp2 + the voting stack in one kernel (csrc/fp_chain.cu)
+            f1, f2 = s.fp
+            fp_module_fused(f1.dist, f1.idx, s.lv[2].feat, pts2, [self.store.layer(f"fp1/conv_{i}") for i in range(2)],
+                            f1.h[-1], stream=main)
+            mark("fp", main)
+            fp_module_fused(f2.dist, f2.idx, s.lv[1].feat, f1.h[-1].view(B, f1.n, -1),
+                            [self.store.layer(f"fp2/conv_{i}") for i in range(2)], f2.h[-1],
+                            vote=(self.vote_fused, self.vote_x0, seeds_xyz, s.votes_xyz, s.votes_feat), stream=main)
+        else:
+            for fi, (f, skip, scope) in enumerate(zip(s.fp, (s.lv[2].feat, s.lv[1].feat), ("fp1", "fp2"))):
+                check(lib.vnb_fp_interpolate_concat(B, f.n, f.m, f.c1, f.c2, dptr(f.dist), dptr(f.idx), dptr(skip), dptr(pts2),
+                                                    dptr(f.cat), _sp(main)))
+                x = f.cat
+                for i in range(len(cfg.fp_mlp)):
+                    self._linear(B * f.n, x, self.store.layer(f"{scope}/conv_{i}"), True, f.h[i], None, main)
+                    x = f.h[i]
+                pts2 = x
+            mark("fp", main)
+            check(lib.vnb_concat2(B * ns, 3, cf, dptr(seeds_xyz), dptr(pts2), dptr(s.seeds), _sp(main)))
+            x = s.seeds
+            nv = len(cfg.vote_units)
+            for i in range(nv):
+                self._linear(B * ns, x, self.store.layer(f"voting{i}"), i < nv - 1, s.vh[i], None, main,
+                             residual=s.seeds if i == nv - 1 else None)
+                x = s.vh[i]
+            check(lib.vnb_split2(B * ns, 3, cf, dptr(x), dptr(s.votes_xyz), dptr(s.votes_feat), _sp(main)))
         mark("vote", main)
         main.wait_event(e_pf)
         check(lib.vnb_gather_point(B, ns, p.npoint, dptr(s.votes_xyz), dptr(s.p_fps), dptr(s.p_xyz), _sp(main)))

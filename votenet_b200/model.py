@@ -10,7 +10,9 @@ from . import tf_nms3d
 from ._lib import check, dptr, lib, stream_ptr
 from .config import NC, PROPOSAL_CHANNELS, VoteNetConfig
 from .synth import CLASS_MEAN_SIZE
-from .utils import (PRECISION_TENSOR, WeightStore, linear, pointnet_fp_module, pointnet_sa_module)
+from . import tf_interpolate, utils
+from .utils import (PRECISION_TENSOR, WeightStore, fp_fusable, fp_module_fused, linear, pointnet_fp_module,
+                    pointnet_sa_module, vote_layers_fused)
 
 
 def decode_boxes(proposals_xyz, proposals_output, class_mean_size):
@@ -48,22 +50,31 @@ class VoteNetB200:
             l_xyz.append(nx); l_pts.append(npts)
             out[f"sa{li + 1}_xyz"], out[f"sa{li + 1}_points"], out[f"sa{li + 1}_idx"] = nx, npts, idx
         l3_points = pointnet_fp_module(l_xyz[3], l_xyz[4], l_pts[3], l_pts[4], list(cfg.fp_mlp), "fp1", weights=W)   # :48
-        seeds_points = pointnet_fp_module(l_xyz[2], l_xyz[3], l_pts[2], l3_points, list(cfg.fp_mlp), "fp2", weights=W)  # :49
-        out["fp1_points"], out["fp2_points"] = l3_points, seeds_points
         seeds_xyz = l_xyz[2]                                                                  # :50
         b, ns, _ = seeds_xyz.shape
-        cf = seeds_points.shape[2]
-        seeds = torch.empty((b * ns, 3 + cf), dtype=torch.float32, device=xyz.device)
-        check(lib.vnb_concat2(b * ns, 3, cf, dptr(seeds_xyz), dptr(seeds_points), dptr(seeds), stream_ptr()))  # :53
-        h = seeds
-        nv = len(cfg.vote_units)
-        for i in range(nv):                                                                   # :55-56, residual :60
-            h = linear(h, W.layer(f"voting{i}"), act=i < nv - 1, precision=prec, residual=seeds if i == nv - 1 else None)
-        votes = h.reshape(b, ns, 3 + cf)
-        out["votes"] = votes
+        cf = cfg.seed_feat_dim
         votes_xyz = torch.empty((b, ns, 3), dtype=torch.float32, device=xyz.device)
         votes_points = torch.empty((b, ns, cf), dtype=torch.float32, device=xyz.device)
-        check(lib.vnb_split2(b * ns, 3, cf, dptr(h), dptr(votes_xyz), dptr(votes_points), stream_ptr()))      # :61,:85
+        if (utils.FUSE_FP and fp_fusable(l_pts[2], l3_points, cfg.fp_mlp, prec) and tuple(cfg.vote_units) == (256, 256, 259)):
+            # fp2 (:49) and the voting module (:53-61) in ONE kernel (csrc/fp_chain.cu)
+            dist, idx3 = tf_interpolate.three_nn(l_xyz[2], l_xyz[3])
+            seeds_points = torch.empty((b, ns, cf), dtype=torch.float32, device=xyz.device)
+            vl, x0 = vote_layers_fused(W, [f"voting{i}" for i in range(3)])
+            fp_module_fused(dist, idx3, l_pts[2].contiguous(), l3_points.contiguous(),
+                            [W.layer(f"fp2/conv_{i}") for i in range(2)], seeds_points,
+                            vote=(vl, x0, seeds_xyz.contiguous(), votes_xyz, votes_points))
+            out["votes"] = torch.cat([votes_xyz, votes_points], 2)
+        else:
+            seeds_points = pointnet_fp_module(l_xyz[2], l_xyz[3], l_pts[2], l3_points, list(cfg.fp_mlp), "fp2", weights=W)  # :49
+            seeds = torch.empty((b * ns, 3 + cf), dtype=torch.float32, device=xyz.device)
+            check(lib.vnb_concat2(b * ns, 3, cf, dptr(seeds_xyz), dptr(seeds_points), dptr(seeds), stream_ptr()))  # :53
+            h = seeds
+            nv = len(cfg.vote_units)
+            for i in range(nv):                                                               # :55-56, residual :60
+                h = linear(h, W.layer(f"voting{i}"), act=i < nv - 1, precision=prec, residual=seeds if i == nv - 1 else None)
+            out["votes"] = h.reshape(b, ns, 3 + cf)
+            check(lib.vnb_split2(b * ns, 3, cf, dptr(h), dptr(votes_xyz), dptr(votes_points), stream_ptr()))  # :61,:85
+        out["fp1_points"], out["fp2_points"] = l3_points, seeds_points
         p = cfg.proposal
         prop_xyz, prop_out, pidx = pointnet_sa_module(votes_xyz, votes_points, p.npoint, p.radius, p.nsample,
                                                       list(p.mlp), list(p.mlp2), False, "proposal",

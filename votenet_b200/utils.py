@@ -14,6 +14,7 @@ from .weights import fold_bn
 
 PRECISION_FP32 = 0     # fp32 SIMT kernels
 PRECISION_TENSOR = 1   # fp16 operands on tcgen05 tensor cores, fp32 accumulate
+FUSE_FP = True         # pointnet_fp_module: one fused kernel when the shapes allow it (tests flip this to cross-check)
 HOIST_MIN_C = 14       # feature widths above 13 use the hoisted layer-1 formulation (see csrc/mlp_tc.cu)
 
 
@@ -136,6 +137,56 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
     return new_xyz, new_points, idx
 
 
+def _ptr_array(tensors):
+    import ctypes as C
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _int_array(vals):
+    import ctypes as C
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def vote_layers_fused(weights, names):
+    """Weight set of the voting FC stack (model.py:53-57) in the form the fused kernel wants: first layer split into its
+    xyz rows (fp32, rank-3 update) and feature rows (tensor-core image); last layer with its output columns permuted
+    [features | xyz] so that the kernel writes votes_feat / votes_xyz directly."""
+    l0, l1, l2 = (weights.layer(nm) for nm in names)
+    dev = l0.W.device
+    f0 = weights.derived(names[0] + ":feat", lambda: Layer(l0.W[3:].contiguous(), l0.b, dev))
+    x0 = weights.derived(names[0] + ":xyz", lambda: Layer(l0.W[:3].contiguous(), torch.zeros_like(l0.b), dev))
+    p2 = weights.derived(names[2] + ":perm", lambda: Layer(torch.cat([l2.W[:, 3:], l2.W[:, :3]], 1).contiguous(),
+                                                           torch.cat([l2.b[3:], l2.b[:3]]).contiguous(), dev))
+    return [f0, l1, p2], x0
+
+
+def fp_module_fused(dist, idx, points1, points2, fp_layers, fp_out, vote=None, stream=None):
+    """vnb_fp_module_fused: three_interpolate + concat + the fp 1x1-conv stack (+ the voting FC stack) in one kernel.
+    vote = (layers, xyz_layer, seeds_xyz, votes_xyz, votes_feat) or None."""
+    b, n, _ = idx.shape
+    m, c2 = points2.shape[1], points2.shape[2]
+    c1 = points1.shape[2]
+    sp = stream_ptr(stream)
+    if vote is None:
+        check(lib.vnb_fp_module_fused(b, n, m, c1, c2, dptr(dist), dptr(idx), dptr(points1), dptr(points2), len(fp_layers),
+                                      _ptr_array([l.img for l in fp_layers]), _ptr_array([l.b for l in fp_layers]),
+                                      _int_array([l.cout for l in fp_layers]), dptr(fp_out), 0, None, None, None, None,
+                                      None, None, None, sp))
+    else:
+        vl, x0, seeds_xyz, votes_xyz, votes_feat = vote
+        check(lib.vnb_fp_module_fused(b, n, m, c1, c2, dptr(dist), dptr(idx), dptr(points1), dptr(points2), len(fp_layers),
+                                      _ptr_array([l.img for l in fp_layers]), _ptr_array([l.b for l in fp_layers]),
+                                      _int_array([l.cout for l in fp_layers]), dptr(fp_out), len(vl),
+                                      _ptr_array([l.img for l in vl]), _ptr_array([l.b for l in vl]),
+                                      _int_array([vl[0].cout, vl[1].cout, vl[2].cout]), dptr(x0.W), dptr(seeds_xyz),
+                                      dptr(votes_xyz), dptr(votes_feat), sp))
+
+
+def fp_fusable(points1, points2, mlp, precision):
+    return (precision == PRECISION_TENSOR and points1 is not None and points1.shape[-1] == 256 and points2.shape[-1] == 256
+            and tuple(mlp) == (256, 256))
+
+
 def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, scope, bn=True, *, weights):
     """PointNet Feature Propagation module — signature of /root/reference/utils.py:266 plus the `weights` store."""
     if not bn:
@@ -146,6 +197,11 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, scope, bn=True, *, wei
     c2 = points2.shape[2]
     c1 = points1.shape[2] if points1 is not None else 0
     dist, idx = tf_interpolate.three_nn(xyz1, xyz2)                                            # utils.py:278
+    if fp_fusable(points1, points2, mlp, prec) and FUSE_FP:                                    # :279-292 in one kernel
+        out = torch.empty((b, n, mlp[-1]), dtype=torch.float32, device=xyz1.device)
+        fp_module_fused(dist, idx, points1.contiguous(), points2.contiguous(),
+                        [weights.layer(f"{scope}/conv_{i}") for i in range(len(mlp))], out)
+        return out
     cat = torch.empty((b * n, c2 + c1), dtype=torch.float32, device=xyz1.device)
     check(lib.vnb_fp_interpolate_concat(b, n, m, c1, c2, dptr(dist), dptr(idx), dptr(points1, torch.float32, "points1"),
                                         dptr(points2, torch.float32, "points2"), dptr(cat), stream_ptr()))  # :279-286
