@@ -136,8 +136,7 @@ __device__ __forceinline__ bool iou_trivially_false(const float* bi, const float
   return hi1x + eps < lo2x || hi2x + eps < lo1x || hi1z + eps < lo2z || hi2z + eps < lo1z;
 }
 
-__device__ bool iou_greater(const float* bi, const float* bj, float thr) {
-  if (iou_trivially_false(bi, bj)) return false;
+__device__ bool iou_greater_full(const float* bi, const float* bj, float thr) {
   float inter2d = intersection2d(bi, bj);
   float h = NMS_MIN(bi[1], bj[1]) - NMS_MAX(bi[13], bj[13]);
   float inter3d = NMS_MAX(h, 0.f) * inter2d;
@@ -174,20 +173,53 @@ __global__ void nms_rank_kernel(int k, const float* __restrict__ scores, const f
 }
 
 // K2: mask[b][p][w] bit (q & 31), q = 32 w + lane < p  <=>  candidate p is suppressed by earlier candidate q.
-__global__ void __launch_bounds__(256) nms_mask_kernel(int k, int W, float thr, const float* __restrict__ bbox,
-                                                        const int* __restrict__ order, const int* __restrict__ ncand,
-                                                        uint32_t* __restrict__ mask) {
-  const int b = blockIdx.y, p = blockIdx.x;
+// The polygon clip is a long divergent chain, but almost every pair is rejected by the cheap exact test above, so the
+// work is split: K2a runs the cheap test for every pair (one warp per candidate p, lanes over q) and compacts the
+// survivors into one global list (warp ballot -> shared list per CTA -> one global reservation per CTA); K2b runs the
+// clip on the dense list, one thread per surviving pair, and sets mask bits with atomicOr (bits are positional, so
+// the list order is irrelevant).
+constexpr int K2A_WARPS = 8;
+__global__ void __launch_bounds__(K2A_WARPS * 32) nms_pairs_kernel(int k, const float* __restrict__ bbox,
+                                                                    const int* __restrict__ order,
+                                                                    const int* __restrict__ ncand,
+                                                                    uint2* __restrict__ pairs, unsigned* __restrict__ npairs) {
+  __shared__ uint32_t s_list[K2A_WARPS * 1024];  // k <= 1024: at most k survivors per candidate
+  __shared__ unsigned s_n, s_base;
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = blockIdx.x * K2A_WARPS + warp;
   const int nc = ncand[b];
-  if (p >= nc) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const float* bi = bbox + ((size_t)b * k + order[(size_t)b * k + p]) * 24;
-  for (int w = warp; w < W; w += nw) {
-    const int q = w * 32 + lane;
-    bool sup = false;
-    if (q < p) sup = iou_greater(bi, bbox + ((size_t)b * k + order[(size_t)b * k + q]) * 24, thr);
-    unsigned m = __ballot_sync(0xffffffffu, sup);
-    if (lane == 0) mask[((size_t)b * k + p) * W + w] = m;
+  if (blockIdx.x * K2A_WARPS >= nc) return;  // whole CTA
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  if (p < nc) {
+    const float* bi = bbox + ((size_t)b * k + order[(size_t)b * k + p]) * 24;
+    for (int q0 = 0; q0 < p; q0 += 32) {
+      const int q = q0 + lane;
+      const bool sv = q < p && !iou_trivially_false(bi, bbox + ((size_t)b * k + order[(size_t)b * k + q]) * 24);
+      const unsigned m = __ballot_sync(0xffffffffu, sv);
+      unsigned base = 0;
+      if (lane == 0 && m) base = atomicAdd(&s_n, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (sv) s_list[base + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)p << 16) | (uint32_t)q;
+    }
+  }
+  __syncthreads();
+  const unsigned n = s_n;
+  if (threadIdx.x == 0 && n) s_base = atomicAdd(npairs, n);
+  __syncthreads();
+  for (unsigned t = threadIdx.x; t < n; t += blockDim.x) pairs[s_base + t] = make_uint2((unsigned)b, s_list[t]);
+}
+
+__global__ void __launch_bounds__(128) nms_clip_kernel(int k, int W, float thr, const float* __restrict__ bbox,
+                                                        const int* __restrict__ order, const uint2* __restrict__ pairs,
+                                                        const unsigned* __restrict__ npairs, uint32_t* __restrict__ mask) {
+  const unsigned n = *npairs;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const uint2 pr = pairs[t];
+    const int b = (int)pr.x, p = (int)(pr.y >> 16), q = (int)(pr.y & 0xffffu);
+    const float* bi = bbox + ((size_t)b * k + order[(size_t)b * k + p]) * 24;   // argument order (candidate, selected), :250
+    const float* bj = bbox + ((size_t)b * k + order[(size_t)b * k + q]) * 24;
+    if (iou_greater_full(bi, bj, thr)) atomicOr(&mask[((size_t)b * k + p) * W + (q >> 5)], 1u << (q & 31));
   }
 }
 
@@ -225,7 +257,7 @@ __global__ void __launch_bounds__(256) rank_emit_kernel(int world, int per_rank,
                                                           size_t sc_stride, const char* __restrict__ kp_base,
                                                           size_t kp_stride, int* __restrict__ out_idx,
                                                           int* __restrict__ out_count) {
-  extern __shared__ char s_dyn[];
+  extern __shared__ __align__(16) char s_dyn[];
   const int total = world * per_rank;
   float* s_sc = reinterpret_cast<float*>(s_dyn);
   int* s_id = reinterpret_cast<int*>(s_sc + total);
@@ -262,11 +294,26 @@ __global__ void __launch_bounds__(256) rank_emit_kernel(int world, int per_rank,
     __syncthreads();
   }
   const int nk = s_base;
-  for (int i = (int)blockIdx.x * 256 + tid; i < nk; i += (int)gridDim.x * 256) {
+  // rank of entry i = number of entries that precede it; entries are dealt to the CTAs round-robin so every CTA of the
+  // grid has work; the scan reads four entries per shared-memory load (pad entries never precede anything)
+  const bool vec = (total & 3) == 0;
+  const int nk4 = vec ? ((nk + 3) & ~3) : nk;
+  if (tid < nk4 - nk) { s_sc[nk + tid] = -INFINITY; s_id[nk + tid] = 0x7fffffff; }
+  __syncthreads();
+  for (int i = (int)blockIdx.x + (int)gridDim.x * tid; i < nk; i += (int)gridDim.x * 256) {
     const float se = s_sc[i];
     const int e = s_id[i];
     int rank = 0;
-    for (int j = 0; j < nk; ++j) rank += (s_sc[j] > se || (s_sc[j] == se && s_id[j] < e)) ? 1 : 0;
+    if (vec) {
+      for (int j = 0; j < nk4; j += 4) {
+        const float4 sj = *reinterpret_cast<const float4*>(s_sc + j);
+        const int4 ij = *reinterpret_cast<const int4*>(s_id + j);
+        rank += ((sj.x > se) | ((sj.x == se) & (ij.x < e))) + ((sj.y > se) | ((sj.y == se) & (ij.y < e))) +
+                ((sj.z > se) | ((sj.z == se) & (ij.z < e))) + ((sj.w > se) | ((sj.w == se) & (ij.w < e)));
+      }
+    } else {
+      for (int j = 0; j < nk; ++j) rank += (s_sc[j] > se) | ((s_sc[j] == se) & (s_id[j] < e));
+    }
     out_idx[rank * 2 + 0] = e / k;
     out_idx[rank * 2 + 1] = e % k;
   }
@@ -281,7 +328,7 @@ static int launch_rank_emit(int world, int per_rank, int k, const char* sc, size
     cudaError_t e = cudaFuncSetAttribute(rank_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_err(VNB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  int grid = (world * per_rank + 255) / 256;
+  int grid = (world * per_rank + 63) / 64;
   if (grid > 32) grid = 32;
   rank_emit_kernel<<<grid, 256, smem, st>>>(world, per_rank, k, sc, scs, kp, kps, out_idx, out_count);
   return check_launch("nms3d order");
@@ -296,7 +343,8 @@ using namespace vnb;
 extern "C" size_t vnb_nms3d_workspace_bytes(int b, int k) {
   if (b <= 0 || k <= 0) return 256;
   size_t W = (size_t)(k + 31) / 32;
-  return align256((size_t)b * k * 4) + align256((size_t)b * 4) + align256((size_t)b * k * W * 4);
+  return align256((size_t)b * k * 4) + align256((size_t)b * 4) + align256((size_t)b * k * W * 4) + 256 /* pair counter */ +
+         align256((size_t)b * k * (size_t)(k > 1 ? k - 1 : 1) / 2 * 8 + 8) /* surviving (candidate, earlier) pairs */;
 }
 
 extern "C" int vnb_nms3d(int b, int k, const float* bbox, const float* scores, const float* objectiveness,
@@ -317,8 +365,13 @@ extern "C" int vnb_nms3d(int b, int k, const float* bbox, const float* scores, c
   uint32_t* mask = reinterpret_cast<uint32_t*>(ws + align256((size_t)b * k * 4) + align256((size_t)b * 4));
   nms_rank_kernel<<<b, 256, (size_t)k * 8, st>>>(k, scores, objectiveness, order, ncand, keep, out_count);
   if (int rc = check_launch("nms3d rank")) return rc;
-  nms_mask_kernel<<<dim3(k, b), 256, 0, st>>>(k, W, iou_threshold, bbox, order, ncand, mask);
-  if (int rc = check_launch("nms3d mask")) return rc;
+  unsigned* npairs = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(mask) + align256((size_t)b * k * W * 4));
+  uint2* pairs = reinterpret_cast<uint2*>(reinterpret_cast<char*>(npairs) + 256);
+  VNB_CUDA(cudaMemsetAsync(mask, 0, align256((size_t)b * k * W * 4) + 256, st));  // mask words + pair counter
+  nms_pairs_kernel<<<dim3((k + K2A_WARPS - 1) / K2A_WARPS, b), K2A_WARPS * 32, 0, st>>>(k, bbox, order, ncand, pairs, npairs);
+  if (int rc = check_launch("nms3d pairs")) return rc;
+  nms_clip_kernel<<<296, 128, 0, st>>>(k, W, iou_threshold, bbox, order, pairs, npairs, mask);
+  if (int rc = check_launch("nms3d clip")) return rc;
   size_t smem = (size_t)k * W * 4;
   if (smem > 48 * 1024)
     VNB_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
