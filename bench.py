@@ -223,10 +223,11 @@ def kernel_table(eng, cfg, peaks, flush):
     for li, l in enumerate(s.lv):
         sa = cfg.sa[li]
         if li == 0:
-            ms = t(lambda: check(lib.vnb_farthest_point_sample(B, l.n, l.m, dptr(src), dptr(l.fps), sp())))
+            ms = t(lambda: check(lib.vnb_farthest_point_sample_ties(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_tie), sp())))
             hbm("fps_sa1", ms, B * (l.m - 1) * l.n * 16, onchip)
         else:  # FPS of an FPS-ordered set: parallel proof of the identity prefix (sequential kernel only on failure)
-            ms = t(lambda: check(lib.vnb_farthest_point_sample_nested(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws), sp())))
+            ms = t(lambda: check(lib.vnb_farthest_point_sample_nested_hint(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws),
+                                                                           dptr(s.fps_tie), sp())))
             hbm(f"fps_sa{li + 1}_nested", ms, B * (l.m - 1) * l.n * 16, onchip)
         ms = t(lambda: check(lib.vnb_query_ball_point_ws(B, l.n, l.m, float(sa.radius), 64, dptr(src), dptr(l.xyz), dptr(l.idx),
                                                          dptr(l.cnt), dptr(l.bq_ws), sp())))
@@ -280,7 +281,8 @@ def kernel_table(eng, cfg, peaks, flush):
     p = cfg.proposal
 
     def prop_fn():
-        check(lib.vnb_farthest_point_sample_nested(B, ns, p.npoint, dptr(s.lv[1].xyz), dptr(s.p_fps), dptr(s.fps_ws), sp()))
+        check(lib.vnb_farthest_point_sample_nested_hint(B, ns, p.npoint, dptr(s.lv[1].xyz), dptr(s.p_fps), dptr(s.fps_ws),
+                                                        dptr(s.fps_tie), sp()))
         check(lib.vnb_gather_point(B, ns, p.npoint, dptr(s.votes_xyz), dptr(s.p_fps), dptr(s.p_xyz), sp()))
         check(lib.vnb_query_ball_point(B, ns, p.npoint, float(p.radius), 64, dptr(s.votes_xyz), dptr(s.p_xyz), dptr(s.p_idx),
                                        dptr(s.p_cnt), sp()))

@@ -63,6 +63,20 @@ int vnb_farthest_point_sample(int b, int n, int m, const float* xyz, int* out_id
 size_t vnb_fps_nested_workspace_bytes(int b, int m);
 int vnb_farthest_point_sample_nested(int b, int n, int m, const float* xyz, int* out_idx, void* workspace, void* stream);
 
+/* FPS with provenance tracking.  vnb_farthest_point_sample_ties is vnb_farthest_point_sample that also reports, per
+ * cloud, the first round whose arg-max was NOT unique (two points shared the maximal running distance exactly and the
+ * reference's tie rule decided); 0x7fffffff if every round had a unique winner, 0 when the kernel in use cannot tell.
+ * vnb_farthest_point_sample_nested_hint is vnb_farthest_point_sample_nested for an input that is the GATHER, in order,
+ * of the first n picks of such a parent call (new_xyz of the previous level, utils.py:42-45): if the parent's first
+ * tie round is >= m, every round j < m had a unique arg-max p_j over the parent's superset, p_j is in the subset, the
+ * running distances are the same floats, hence the subset's FPS picks position j — the identity prefix holds with no
+ * check at all.  Clouds whose hint is smaller fall back to the parallel proof, then to the sequential sampler.  The
+ * caller vouches for the provenance (wrong provenance = wrong indices); results are otherwise bit-identical. */
+int vnb_farthest_point_sample_ties(int b, int n, int m, const float* xyz, int* out_idx, int* first_tie_round,
+                                   void* stream);
+int vnb_farthest_point_sample_nested_hint(int b, int n, int m, const float* xyz, int* out_idx, void* workspace,
+                                          const int* parent_first_tie_round, void* stream);
+
 /* gatherpointLauncher(b,n,m,inp,idx,out)                        tf_sampling_g.cu:206-208
  * inp (b,n,3), idx (b,m) -> out (b,m,3). */
 int vnb_gather_point(int b, int n, int m, const float* inp, const int* idx, float* out, void* stream);

@@ -112,3 +112,95 @@ def test_pruned_nested_fallback_flags(cuda, variant):
     got = farthest_point_sample_nested(500, T(mix, cuda)).cpu().numpy()
     assert np.array_equal(got, O.farthest_point_sample(500, mix))
     assert np.array_equal(got[0], np.arange(500))
+
+
+# ------------------------------------------------------------------------------------------------ tie tracking / provenance hint
+def _fps_first_tie_numpy(x, m):
+    """Float32-exact emulation of the reference's FPS (tf_sampling_g.cu:105-170, distances contracted as nvcc does:
+    fmaf(dz,dz,fmaf(dx,dx,dy*dy))) that also reports the first round whose arg-max was shared by two points."""
+    f32, f64 = np.float32, np.float64
+    n = x.shape[0]
+    k = np.arange(n)
+    temp = np.full(n, 1e38, f32)
+    picks = [0]
+    first_tie = 0x7FFFFFFF
+    last = 0
+    for r in range(1, m):
+        d = (x - x[last]).astype(f32)
+        dx, dy, dz = d[:, 0], d[:, 1], d[:, 2]
+        t = (dx.astype(f64) * dx.astype(f64) + (dy * dy).astype(f32).astype(f64)).astype(f32)
+        d2 = (dz.astype(f64) * dz.astype(f64) + t.astype(f64)).astype(f32)
+        temp = np.minimum(temp, d2)
+        mx = temp.max()
+        cand = np.flatnonzero(temp == mx)
+        if cand.size > 1 and first_tie == 0x7FFFFFFF:
+            first_tie = r
+        # reference tie rule: smallest (k mod 512), then smallest k  (SURVEY.md A.1)
+        last = int(cand[np.lexsort((cand, cand % 512))[0]])
+        picks.append(last)
+    return np.asarray(picks, np.int32), first_tie
+
+
+@pytest.mark.parametrize("kind", ["sun", "uniform", "dup_of_pick", "dup_same_cell", "lattice", "mirror"])
+def test_fps_tie_round_is_exact(cuda, kind):
+    """vnb_farthest_point_sample_ties reports exactly the first round with a non-unique arg-max (what makes the
+    provenance shortcut of vnb_farthest_point_sample_nested_hint sound), on inputs with and without engineered ties."""
+    from votenet_b200 import synth
+    from votenet_b200.tf_sampling import farthest_point_sample_ties
+
+    rng = np.random.default_rng(42)
+    n, m = 20000, 300
+    if kind == "sun":
+        x = synth.synthetic_cloud(3, n)
+    else:
+        x = rng.random((n, 3), dtype=np.float32) * np.asarray([6, 2, 6], np.float32)
+    if kind == "dup_of_pick":       # an exact copy of the point picked in round 7, far away in index
+        p, _ = _fps_first_tie_numpy(x, 8)
+        x[15000] = x[p[7]]
+    elif kind == "dup_same_cell":   # copies of the round-5 pick right next to it in index order
+        p, _ = _fps_first_tie_numpy(x, 6)
+        j = int(p[5])
+        x[(j + 1) % n] = x[j]
+        x[(j + 2) % n] = x[j]
+    elif kind == "lattice":
+        x = (rng.integers(0, 12, (n, 3)) / 4).astype(np.float32)
+    elif kind == "mirror":          # every point has a mirror image across x = 0 and the start point lies on the plane
+        half = x[: n // 2].copy()
+        half[0, 0] = 0.0
+        x = np.concatenate([half, half * np.asarray([-1, 1, 1], np.float32)], 0)
+    want_idx, want_tie = _fps_first_tie_numpy(x, m)
+    assert np.array_equal(want_idx, O.farthest_point_sample(m, x[None])[0])  # the emulation is the oracle's sequence
+    got_idx, got_tie = farthest_point_sample_ties(m, T(x[None], cuda))
+    assert np.array_equal(got_idx.cpu().numpy()[0], want_idx)
+    assert int(got_tie.item()) == want_tie, (kind, int(got_tie.item()), want_tie)
+    if kind in ("sun", "uniform"):
+        assert want_tie == 0x7FFFFFFF
+
+
+@pytest.mark.parametrize("kind", ["sun", "lattice", "dup"])
+def test_fps_nested_hint_matches_oracle(cuda, kind):
+    """Nested levels through the provenance hint: identical to the oracle whether the parent was tie-free (no proof
+    runs) or not (parallel proof / sequential fallback)."""
+    from votenet_b200 import synth
+    from votenet_b200.tf_sampling import farthest_point_sample_nested_hint, farthest_point_sample_ties, gather_point
+
+    rng = np.random.default_rng(7)
+    b, n = 3, 20000
+    x = np.stack([synth.synthetic_cloud(10 + i, n) for i in range(b)], 0)
+    if kind == "lattice":
+        x[1] = (rng.integers(0, 12, (n, 3)) / 4).astype(np.float32)
+    elif kind == "dup":
+        p = O.farthest_point_sample(40, x[2:3])[0]
+        x[2, 12345] = x[2, p[33]]
+    tx = T(x, cuda)
+    f1, ties = farthest_point_sample_ties(2048, tx)
+    assert np.array_equal(f1.cpu().numpy(), O.farthest_point_sample(2048, x))
+    src, src_np = gather_point(tx, f1), O.gather_point(x, f1.cpu().numpy())
+    for m in (1024, 512, 256):
+        got = farthest_point_sample_nested_hint(m, src, ties).cpu().numpy()
+        assert np.array_equal(got, O.farthest_point_sample(m, src_np)), (kind, m, ties.tolist())
+        src, src_np = src[:, :m].contiguous(), src_np[:, :m]   # == gather of the identity prefix when it holds
+        if not np.array_equal(got, np.tile(np.arange(m, dtype=np.int32), (b, 1))):
+            break  # a level that is not the identity prefix ends the provenance chain
+    if kind == "sun":
+        assert (ties.cpu().numpy() == 0x7FFFFFFF).all()

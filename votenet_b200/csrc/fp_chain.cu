@@ -41,7 +41,9 @@ constexpr int OFF_X = 0;                // 4 panels
 constexpr int OFF_Y = 4 * PANEL;        // 4 panels; panels 0, 1 double as the layer-0 A ring (Y is first written by layer 1)
 constexpr int OFF_W = 8 * PANEL;
 constexpr int OFF_BAR = OFF_W + NSTAGE * PANEL;
-constexpr int SMEM = OFF_BAR + 32 * 8 + 16 + 1024;
+constexpr int BIAS_LD = 272;            // floats per layer
+constexpr int OFF_BIAS = OFF_BAR + 512; // float [MAX_LAYERS][BIAS_LD] biases | float [3][CW] xyz rows of the first vote layer
+constexpr int SMEM = OFF_BIAS + (MAX_LAYERS * BIAS_LD + 3 * CW) * 4 + 1024;
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 constexpr int TM_COLS = 512;
 
@@ -55,7 +57,7 @@ struct Params {
   const char* w_img[MAX_LAYERS];         // packed fp16 images; layer 2's image holds rows 3.. of its weight (K = 256);
                                          // layer 4's image has its output columns permuted [3..258, 0..2]
   const float* bias[MAX_LAYERS];         // layer 4's bias permuted like its columns
-  int k_pad[MAX_LAYERS], n_pad[MAX_LAYERS];
+  int k_pad[MAX_LAYERS], n_pad[MAX_LAYERS], n_out[MAX_LAYERS];
   const float* seeds_xyz;                // (rows, 3)                       (vote only)
   const float* w_vote_xyz;               // (3, 256) rows 0..2 of layer 2's weight, fp32   (vote only)
   float* fp_out;                         // (rows, 256) output of the fp module (= seed features), fp32
@@ -87,6 +89,8 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
   uint64_t* acc_full = bars + 2 * NSTAGE + 4;  // commit: all MMAs of the current layer completed (one phase per layer)
   uint64_t* act_full = bars + 2 * NSTAGE + 5;  // 256 arrivals: the epilogue has written the next layer's A operand
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 8);
+  float* sBias = reinterpret_cast<float*>(smem + OFF_BIAS);
+  float* sWxyz = sBias + MAX_LAYERS * BIAS_LD;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = (int)blockIdx.x * 128;
@@ -99,6 +103,11 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
     mbar_init(act_full, WORKERS);
     fence_barrier_init();
   }
+  // biases (and the rank-3 xyz weights) are read by every epilogue thread for every column: stage them once
+  for (int l = 0; l < L; ++l)
+    for (int i = tid; i < P.n_out[l]; i += THREADS) sBias[l * BIAS_LD + i] = __ldg(P.bias[l] + i);
+  if (L > 2)
+    for (int i = tid; i < 3 * CW; i += THREADS) sWxyz[i] = __ldg(P.w_vote_xyz + i);
   if (warp == 0) tmem_alloc(tmem_ptr, TM_COLS);
   tc_fence_before_sync();
   __syncthreads();  // barriers initialised before anyone touches them
@@ -191,32 +200,28 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
         uint4 pk[4];
         if (c < 4) {  // interpolated columns 64c + 8 c8 .. + 8   (tf_interpolate.cpp:107-127)
           const int col = 64 * c + 8 * c8;
+          float4 v[4][3][2];  // all 24 independent 16-byte loads of the chunk in flight before the first use
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {  // two rows at a time: 12 independent 16-byte loads in flight
-            float4 v[2][3][2];
+          for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int pp = 0; pp < 2; ++pp)
-#pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                const float4* src = reinterpret_cast<const float4*>(p2base[2 * h + pp] + (size_t)gi[2 * h + pp][i] * CW + col);
-                v[pp][i][0] = __ldg(src);
-                v[pp][i][1] = __ldg(src + 1);
-              }
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-              const int p = 2 * h + pp;
-              float o[8];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float4 a = v[pp][0][e], b = v[pp][1][e], d = v[pp][2][e];
-                o[4 * e + 0] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, gw[p][0]), __fmul_rn(b.x, gw[p][1])), __fmul_rn(d.x, gw[p][2]));
-                o[4 * e + 1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, gw[p][0]), __fmul_rn(b.y, gw[p][1])), __fmul_rn(d.y, gw[p][2]));
-                o[4 * e + 2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, gw[p][0]), __fmul_rn(b.z, gw[p][1])), __fmul_rn(d.z, gw[p][2]));
-                o[4 * e + 3] = __fadd_rn(__fadd_rn(__fmul_rn(a.w, gw[p][0]), __fmul_rn(b.w, gw[p][1])), __fmul_rn(d.w, gw[p][2]));
-              }
-              pk[p] = ok[p] ? make_uint4(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]))
-                            : make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < 3; ++i) {
+              const float4* src = reinterpret_cast<const float4*>(p2base[p] + (size_t)gi[p][i] * CW + col);
+              v[p][i][0] = __ldg(src);
+              v[p][i][1] = __ldg(src + 1);
             }
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float4 a = v[p][0][e], b = v[p][1][e], d = v[p][2][e];
+              o[4 * e + 0] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, gw[p][0]), __fmul_rn(b.x, gw[p][1])), __fmul_rn(d.x, gw[p][2]));
+              o[4 * e + 1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, gw[p][0]), __fmul_rn(b.y, gw[p][1])), __fmul_rn(d.y, gw[p][2]));
+              o[4 * e + 2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, gw[p][0]), __fmul_rn(b.z, gw[p][1])), __fmul_rn(d.z, gw[p][2]));
+              o[4 * e + 3] = __fadd_rn(__fadd_rn(__fmul_rn(a.w, gw[p][0]), __fmul_rn(b.w, gw[p][1])), __fmul_rn(d.w, gw[p][2]));
+            }
+            pk[p] = ok[p] ? make_uint4(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]))
+                          : make_uint4(0, 0, 0, 0);
           }
         } else {  // skip features, columns 64 (c-4) + 8 c8 .. + 8 of points1
           const int col = 64 * (c - 4) + 8 * c8;
@@ -263,22 +268,38 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
       const bool relu = !vote_out;                  // every layer but the last vote layer is conv/FC + BN + ReLU
       const bool xyz_term = l == 2;                 // first vote layer: + seeds_xyz . W[0:3]
       uint8_t* dst = (l & 1) ? sY : sX;             // next layer's A operand
-      const float* bias = P.bias[l];
-#pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {  // 4 x 32 columns of this thread's half
+      const float* bias = sBias + l * BIAS_LD;
+      uint32_t v[2][32];
+      tmem_ld_x32(tacc + (uint32_t)(hf * 128), v[0]);
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {  // 4 x 32 columns of this thread's half; the next TMEM load is in flight during the math
         const int col0 = hf * 128 + cb * 32;
-        uint32_t v[32];
-        tmem_ld_x32(tacc + (uint32_t)col0, v);
+        float4 rsd[8];
+        if (vote_out && live) {  // residual = the fp output this very thread stored in layer 1's epilogue; all loads first
+          const float4* rs = reinterpret_cast<const float4*>(P.fp_out + (size_t)grow * CW + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rsd[i] = rs[i];
+        }
         tmem_ld_wait();
+        if (cb + 1 < 4) tmem_ld_x32(tacc + (uint32_t)(col0 + 32), v[(cb + 1) & 1]);
         float x[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + __ldg(bias + col0 + i);
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + i);
+          x[i] = __uint_as_float(v[cb & 1][i]) + b4.x; x[i + 1] = __uint_as_float(v[cb & 1][i + 1]) + b4.y;
+          x[i + 2] = __uint_as_float(v[cb & 1][i + 2]) + b4.z; x[i + 3] = __uint_as_float(v[cb & 1][i + 3]) + b4.w;
+        }
         if (xyz_term) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            x[i] = __fmaf_rn(sz, __ldg(P.w_vote_xyz + 2 * CW + col0 + i),
-                             __fmaf_rn(sy, __ldg(P.w_vote_xyz + CW + col0 + i),
-                                       __fmaf_rn(sx, __ldg(P.w_vote_xyz + col0 + i), x[i])));
+          for (int i = 0; i < 32; i += 4) {
+            const float4 wx = *reinterpret_cast<const float4*>(sWxyz + col0 + i);
+            const float4 wy = *reinterpret_cast<const float4*>(sWxyz + CW + col0 + i);
+            const float4 wz = *reinterpret_cast<const float4*>(sWxyz + 2 * CW + col0 + i);
+            x[i] = __fmaf_rn(sz, wz.x, __fmaf_rn(sy, wy.x, __fmaf_rn(sx, wx.x, x[i])));
+            x[i + 1] = __fmaf_rn(sz, wz.y, __fmaf_rn(sy, wy.y, __fmaf_rn(sx, wx.y, x[i + 1])));
+            x[i + 2] = __fmaf_rn(sz, wz.z, __fmaf_rn(sy, wy.z, __fmaf_rn(sx, wx.z, x[i + 2])));
+            x[i + 3] = __fmaf_rn(sz, wz.w, __fmaf_rn(sy, wy.w, __fmaf_rn(sx, wx.w, x[i + 3])));
+          }
         }
         if (relu) {
 #pragma unroll
@@ -286,13 +307,10 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
         }
         if (vote_out) {
           if (live) {
-            const float4* rs = reinterpret_cast<const float4*>(P.fp_out + (size_t)grow * CW + col0);
             float4* o = reinterpret_cast<float4*>(P.votes_feat + (size_t)grow * CW + col0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 r4 = rs[i];  // written by this very thread in layer 1's epilogue
-              o[i] = make_float4(x[4 * i] + r4.x, x[4 * i + 1] + r4.y, x[4 * i + 2] + r4.z, x[4 * i + 3] + r4.w);
-            }
+            for (int i = 0; i < 8; ++i)
+              o[i] = make_float4(x[4 * i] + rsd[i].x, x[4 * i + 1] + rsd[i].y, x[4 * i + 2] + rsd[i].z, x[4 * i + 3] + rsd[i].w);
           }
         } else {
           if (fp_store && live) {
@@ -312,13 +330,13 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
         }
       }
       if (vote_out && hf == 1) {  // xyz offsets: permuted columns 256..258
-        uint32_t v[16];
-        tmem_ld_x16(tacc + 256u, v);
+        uint32_t v16[16];
+        tmem_ld_x16(tacc + 256u, v16);
         tmem_ld_wait();
         if (live) {
-          P.votes_xyz[(size_t)grow * 3 + 0] = sx + (__uint_as_float(v[0]) + __ldg(bias + 256));
-          P.votes_xyz[(size_t)grow * 3 + 1] = sy + (__uint_as_float(v[1]) + __ldg(bias + 257));
-          P.votes_xyz[(size_t)grow * 3 + 2] = sz + (__uint_as_float(v[2]) + __ldg(bias + 258));
+          P.votes_xyz[(size_t)grow * 3 + 0] = sx + (__uint_as_float(v16[0]) + bias[256]);
+          P.votes_xyz[(size_t)grow * 3 + 1] = sy + (__uint_as_float(v16[1]) + bias[257]);
+          P.votes_xyz[(size_t)grow * 3 + 2] = sz + (__uint_as_float(v16[2]) + bias[258]);
         }
       }
       if (!last) {
@@ -365,13 +383,14 @@ extern "C" int vnb_fp_module_fused(int b, int n, int m, int c1, int c2, const fl
   p.rows_total = b * n; p.n = n; p.m = m;
   p.dist = dist; p.idx = idx; p.points1 = points1; p.points2 = points2;
   p.n_layers = 2 + n_vote_layers;
-  p.w_img[0] = static_cast<const char*>(fp_w_img[0]); p.bias[0] = fp_bias[0]; p.k_pad[0] = c1 + c2; p.n_pad[0] = fpc::CW;
-  p.w_img[1] = static_cast<const char*>(fp_w_img[1]); p.bias[1] = fp_bias[1]; p.k_pad[1] = fpc::CW; p.n_pad[1] = fpc::CW;
+  p.w_img[0] = static_cast<const char*>(fp_w_img[0]); p.bias[0] = fp_bias[0]; p.k_pad[0] = c1 + c2; p.n_pad[0] = fpc::CW; p.n_out[0] = fpc::CW;
+  p.w_img[1] = static_cast<const char*>(fp_w_img[1]); p.bias[1] = fp_bias[1]; p.k_pad[1] = fpc::CW; p.n_pad[1] = fpc::CW; p.n_out[1] = fpc::CW;
   for (int i = 0; i < n_vote_layers; ++i) {
     p.w_img[2 + i] = static_cast<const char*>(vote_w_img[i]);
     p.bias[2 + i] = vote_bias[i];
     p.k_pad[2 + i] = fpc::CW;
     p.n_pad[2 + i] = i == 2 ? round_up(fpc::CW + 3, 16) : fpc::CW;
+    p.n_out[2 + i] = vote_cout[i];
   }
   p.seeds_xyz = seeds_xyz; p.w_vote_xyz = vote_w0_xyz_f32;
   p.fp_out = fp_out; p.votes_xyz = votes_xyz; p.votes_feat = votes_feat;

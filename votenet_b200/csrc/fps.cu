@@ -44,7 +44,7 @@ int g_fps_variant = 1;    // 0: register/cluster kernel only; 1: bucket-pruned s
                           // 2: bucket-pruned kernel for every n <= 20480
 
 int fps_pruned_capacity();
-int launch_fps_pruned(int b, int n, int m, const float* xyz, int* out, const int* flags, cudaStream_t st);
+int launch_fps_pruned(int b, int n, int m, const float* xyz, int* out, const int* flags, int* tie_out, cudaStream_t st);
 
 // T threads per CTA, P points per thread, CL CTAs per cluster (launch attribute, CL*T % 512 == 0); W = T/32 warps.
 // MODE 0: cluster barrier per round; MODE 1: tagged slots, receivers poll their own shared memory.
@@ -211,9 +211,11 @@ __global__ void __launch_bounds__(T) fps_cluster_kernel(int n, int m, int CL, co
 constexpr int VP = 32;  // points per CTA (one per lane)
 constexpr int VS = 8;   // segments of the pick range (one per warp)
 __global__ void __launch_bounds__(128) fps_prefix_r_kernel(int n, int m, const float* __restrict__ xyz,
-                                                           float* __restrict__ R /* (b,m) */) {
+                                                           float* __restrict__ R /* (b,m) */,
+                                                           const int* __restrict__ hint) {
   extern __shared__ float sv[];  // xyz of picks 0 .. jend-1
   const int cloud = blockIdx.y;
+  if (hint != nullptr && hint[cloud] >= m) return;  // proven by provenance (see vnb_farthest_point_sample_nested_hint)
   const float* pc = xyz + (size_t)cloud * n * 3;
   const int j0 = blockIdx.x * 128, jend = min(m, j0 + 128);
   for (int t = threadIdx.x; t < jend * 3; t += 128) sv[t] = pc[t];
@@ -228,10 +230,12 @@ __global__ void __launch_bounds__(128) fps_prefix_r_kernel(int n, int m, const f
 
 __global__ void __launch_bounds__(VP * VS) fps_prefix_verify_kernel(int n, int m, const float* __restrict__ xyz,
                                                                      const float* __restrict__ R,
-                                                                     int* __restrict__ fail /* per cloud, pre-zeroed */) {
+                                                                     int* __restrict__ fail /* per cloud, pre-zeroed */,
+                                                                     const int* __restrict__ hint) {
   extern __shared__ float4 sq[];  // [m-1]: {xyz of pick i, R[i+1]} -> one broadcast LDS.128 per round
   __shared__ float s_min[VS][VP];
   const int cloud = blockIdx.y;
+  if (hint != nullptr && hint[cloud] >= m) return;
   const float* pc = xyz + (size_t)cloud * n * 3;
   for (int i = threadIdx.x; i + 1 < m; i += VP * VS)
     sq[i] = make_float4(pc[(size_t)i * 3], pc[(size_t)i * 3 + 1], pc[(size_t)i * 3 + 2], R[(size_t)cloud * m + i + 1]);
@@ -347,9 +351,12 @@ static int fps_dispatch_t(int b, int n, int m, int CL, const float* xyz, int* ou
 // Geometry: T threads per CTA (g_fps_threads: 256 / 512 / 1024) x CL CTAs per cluster (g_fps_cl or automatic).  Few big
 // CTAs minimise the SM footprint of one call (better throughput when several calls overlap); many small CTAs minimise
 // the latency of one call.  CL*T must be a multiple of 512 (per-thread tie rule, see the header comment).
-static int fps_dispatch(int b, int n, int m, const float* xyz, int* out, const int* flags, cudaStream_t st) {
+static int fps_dispatch(int b, int n, int m, const float* xyz, int* out, const int* flags, cudaStream_t st,
+                        int* tie_out = nullptr) {
   if (n <= fps_pruned_capacity() && ((g_fps_variant == 1 && n > 2048) || g_fps_variant == 2))
-    return launch_fps_pruned(b, n, m, xyz, out, flags, st);
+    return launch_fps_pruned(b, n, m, xyz, out, flags, tie_out, st);
+  // the register / cluster kernels do not track ties: report "round 0" (no round is known to be tie-free)
+  if (tie_out != nullptr) VNB_CUDA(cudaMemsetAsync(tie_out, 0, sizeof(int) * (size_t)b, st));
   int T = g_fps_threads;
   int CL = g_fps_cl;
   if (n <= 2048 && CL <= 1) {  // small clouds: one CTA of 512 threads
@@ -417,11 +424,8 @@ extern "C" size_t vnb_fps_nested_workspace_bytes(int b, int m) {
   return (size_t)(b > 0 ? b : 1) * (2 * sizeof(int) + (size_t)(m > 0 ? m : 1) * sizeof(float)) + 256;
 }
 
-extern "C" int vnb_farthest_point_sample_nested(int b, int n, int m, const float* xyz, int* out_idx, void* workspace,
-                                                void* stream) {
-  if (int rc = fps_check_args(b, n, m)) return rc;
-  if (b == 0) return VNB_OK;
-  cudaStream_t st = as_stream(stream);
+static int fps_nested_impl(int b, int n, int m, const float* xyz, int* out_idx, void* workspace, const int* hint,
+                           cudaStream_t st) {
   const size_t smem = (size_t)m * sizeof(float4);
   if (m > n || smem > 200 * 1024)  // the identity prefix needs m <= n; huge m does not fit the proof kernel
     return fps_dispatch(b, n, m, xyz, out_idx, nullptr, st);
@@ -429,14 +433,38 @@ extern "C" int vnb_farthest_point_sample_nested(int b, int n, int m, const float
   int* done = fail + b;
   float* R = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)b * 2 * sizeof(int) + 255) / 256) * 256);
   VNB_CUDA(cudaMemsetAsync(fail, 0, sizeof(int) * (size_t)b, st));
-  VNB_CUDA(cudaFuncSetAttribute(fps_prefix_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)m * 12)));
-  fps_prefix_r_kernel<<<dim3((m + 127) / 128, b), 128, (size_t)m * 12, st>>>(n, m, xyz, R);
+  if ((size_t)m * 12 > 48 * 1024)
+    VNB_CUDA(cudaFuncSetAttribute(fps_prefix_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)m * 12)));
+  fps_prefix_r_kernel<<<dim3((m + 127) / 128, b), 128, (size_t)m * 12, st>>>(n, m, xyz, R, hint);
   if (int rc = check_launch("fps prefix R")) return rc;
-  VNB_CUDA(cudaFuncSetAttribute(fps_prefix_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fps_prefix_verify_kernel<<<dim3((n + VP - 1) / VP, b), VP * VS, smem, st>>>(n, m, xyz, R, fail);
+  if (smem > 48 * 1024)
+    VNB_CUDA(cudaFuncSetAttribute(fps_prefix_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fps_prefix_verify_kernel<<<dim3((n + VP - 1) / VP, b), VP * VS, smem, st>>>(n, m, xyz, R, fail, hint);
   if (int rc = check_launch("fps prefix proof")) return rc;
   fps_identity_kernel<<<(b * m + 255) / 256, 256, 0, st>>>(b, m, fail, out_idx, done);
   if (int rc = check_launch("fps identity")) return rc;
   // sequential kernel for the clouds whose proof failed (clusters of proven clouds exit at once)
   return fps_dispatch(b, n, m, xyz, out_idx, done, st);
+}
+
+extern "C" int vnb_farthest_point_sample_nested(int b, int n, int m, const float* xyz, int* out_idx, void* workspace,
+                                                void* stream) {
+  if (int rc = fps_check_args(b, n, m)) return rc;
+  if (b == 0) return VNB_OK;
+  return fps_nested_impl(b, n, m, xyz, out_idx, workspace, nullptr, as_stream(stream));
+}
+
+extern "C" int vnb_farthest_point_sample_ties(int b, int n, int m, const float* xyz, int* out_idx, int* first_tie_round,
+                                              void* stream) {
+  if (int rc = fps_check_args(b, n, m)) return rc;
+  VNB_REQUIRE(first_tie_round != nullptr, "farthest_point_sample_ties: first_tie_round buffer missing");
+  if (b == 0) return VNB_OK;
+  return fps_dispatch(b, n, m, xyz, out_idx, nullptr, as_stream(stream), first_tie_round);
+}
+
+extern "C" int vnb_farthest_point_sample_nested_hint(int b, int n, int m, const float* xyz, int* out_idx, void* workspace,
+                                                     const int* parent_first_tie_round, void* stream) {
+  if (int rc = fps_check_args(b, n, m)) return rc;
+  if (b == 0) return VNB_OK;
+  return fps_nested_impl(b, n, m, xyz, out_idx, workspace, parent_first_tie_round, as_stream(stream));
 }

@@ -64,9 +64,10 @@ __device__ __forceinline__ uint32_t spread4(uint32_t v) {  // abcd -> a00b00c00d
 
 // Warp arg-max of (hi as signed int, then tie key).  `tie()` is evaluated only when several lanes share the maximum.
 template <class TieFn>
-__device__ __forceinline__ int warp_argmax(int hi, int& whi, TieFn tie) {
+__device__ __forceinline__ int warp_argmax(int hi, int& whi, bool& shared_max, TieFn tie) {
   whi = redux_max_s32(hi);
   unsigned mk = __ballot_sync(0xffffffffu, hi == whi);
+  shared_max = (mk & (mk - 1u)) != 0u;
   if (mk & (mk - 1u)) {
     const uint32_t t = (hi == whi) ? tie() : 0u;
     const uint32_t wt = redux_max(t);
@@ -75,10 +76,10 @@ __device__ __forceinline__ int warp_argmax(int hi, int& whi, TieFn tie) {
   return __ffs(mk) - 1;
 }
 
-template <bool PROF>
+template <bool PROF, bool TIES>
 __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const float* __restrict__ xyz,
                                                            int* __restrict__ out, const int* __restrict__ flags,
-                                                           long long* __restrict__ prof) {
+                                                           long long* __restrict__ prof, int* __restrict__ tie_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   float2* sxy = reinterpret_cast<float2*>(smem + OFF_XY);
   uint16_t* stie = reinterpret_cast<uint16_t*>(smem + OFF_TIE);
@@ -215,10 +216,12 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
 
   // ---------------------------------------------------------------- rounds
   int chi = __float_as_int(-1.f);          // lane s (< PS): champion of sub-bucket s: temp bits,
-  uint32_t cslot = 0;                      //   its slot i*PT + tid in sxy / stie,
+  uint32_t cslot = 0;                      //   its slot i*PT + tid in sxy / stie (bit 31: another point of the sub-bucket
+                                           //   has exactly the same temp, i.e. the champion won on the tie key),
   float cx = 0.f, cy = 0.f, cz = 0.f;      //   its coordinates
   float lx = pc[0], ly = pc[1], lz = pc[2];  // last pick: index 0 (tf_sampling_g.cu:114-116)
   if (tid == 0) oc[0] = 0;
+  int first_tie = 0x7fffffff;  // first round whose arg-max was not unique (decided by the tie rule)
 
   long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt0 = 0;
 #define PF_TICK(i)                 \
@@ -247,6 +250,7 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
         float xs[PQ], ys[PQ];
         float best = -2.f;
         int bq = 0;
+        bool dup = false;  // a second point of this lane shares the lane's maximum
 #pragma unroll
         for (int q = 0; q < PQ; ++q) {
           const int i = s * PQ + q;
@@ -256,17 +260,25 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
           td[i] = fminf(d, td[i]);
           if (td[i] > best) { best = td[i]; bq = q; }  // first strict maximum in descending tie-key order
         }
+        if (TIES) {  // off the arg-max dependency chain: how many of the lane's points sit at the lane's maximum?
+          int same = 0;
+#pragma unroll
+          for (int q = 0; q < PQ; ++q) same += td[s * PQ + q] == best ? 1 : 0;
+          dup = same > 1;
+        }
         float bx = xs[0], by = ys[0], bz = z[s * PQ];
 #pragma unroll
         for (int q = 1; q < PQ; ++q)
           if (bq == q) { bx = xs[q]; by = ys[q]; bz = z[s * PQ + q]; }
         const uint32_t slot = (uint32_t)((s * PQ + bq) * PT + tid);
         int whi;
-        const int src = warp_argmax(__float_as_int(best), whi, [&] { return (uint32_t)stie[slot]; });
+        bool shared_max;
+        const int src = warp_argmax(__float_as_int(best), whi, shared_max, [&] { return (uint32_t)stie[slot]; });
+        const bool ctie = TIES && (shared_max || __ballot_sync(0xffffffffu, dup && __float_as_int(best) == whi) != 0u);
         const float wx = __shfl_sync(0xffffffffu, bx, src), wy = __shfl_sync(0xffffffffu, by, src),
                     wz = __shfl_sync(0xffffffffu, bz, src);
         const uint32_t wslot = __shfl_sync(0xffffffffu, slot, src);
-        if (lane == s) { chi = whi; cslot = wslot; cx = wx; cy = wy; cz = wz; }
+        if (lane == s) { chi = whi; cslot = wslot | (ctie ? 0x80000000u : 0u); cx = wx; cy = wy; cz = wz; }
       }
     }
     PF_TICK(1)
@@ -285,13 +297,14 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
     unsigned mk = __ballot_sync(0xffffffffu, cnt > 0);
     const unsigned multi = __ballot_sync(0xffffffffu, cnt > 1);
     int bj = h.x == whi ? 0 : (h.y == whi ? 1 : (h.z == whi ? 2 : 3));
+    const bool tie_sub = ((mk & (mk - 1u)) | multi) != 0u;  // several sub-bucket champions share the maximal temp
     if ((mk & (mk - 1u)) | multi) {  // several champions share the maximal temp exactly: highest tie key wins
       uint32_t bt = 0u;
       const int hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (hv[j] == whi) {
-          const uint32_t t = stie[s_rec[par * PNB + lane * 4 + j].x];
+          const uint32_t t = stie[s_rec[par * PNB + lane * 4 + j].x & 0x7fffffffu];
           if (t > bt) { bt = t; bj = j; }
         }
       const uint32_t wt = redux_max(bt);
@@ -301,10 +314,12 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
     const int e = src * 4 + __shfl_sync(0xffffffffu, bj, src);
     const uint4 rec = s_rec[par * PNB + e];
     lx = __uint_as_float(rec.y); ly = __uint_as_float(rec.z); lz = __uint_as_float(rec.w);
-    if (warp == (r & (PW - 1)) && lane == 0) oc[r] = tie_key_to_index((uint32_t)stie[rec.x]);
+    if (TIES && (tie_sub || (rec.x >> 31)) && whi >= 0 && first_tie == 0x7fffffff) first_tie = r;
+    if (warp == (r & (PW - 1)) && lane == 0) oc[r] = tie_key_to_index((uint32_t)stie[rec.x & 0x7fffffffu]);
     PF_TICK(3)
   }
 #undef PF_TICK
+  if (TIES && tie_out != nullptr && tid == 0) tie_out[cloud] = first_tie;
   if (PROF && prof != nullptr && lane == 0 && cloud == 0) {
     pacc[7] = clock64() - t_begin;
     for (int i = 0; i < 8; ++i) prof[warp * 8 + i] = pacc[i];
@@ -315,14 +330,19 @@ extern long long* g_fps_prof;
 
 int fps_pruned_capacity() { return PCAP; }
 
-int launch_fps_pruned(int b, int n, int m, const float* xyz, int* out, const int* flags, cudaStream_t st) {
+int launch_fps_pruned(int b, int n, int m, const float* xyz, int* out, const int* flags, int* tie_out, cudaStream_t st) {
   if (g_fps_prof != nullptr && flags == nullptr) {
-    VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
-    fps_pruned_kernel<true><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, g_fps_prof);
+    VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
+    fps_pruned_kernel<true, true><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, g_fps_prof, tie_out);
     return check_launch("farthest_point_sample (pruned, profiled)");
   }
-  VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
-  fps_pruned_kernel<false><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, nullptr);
+  if (tie_out != nullptr) {
+    VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
+    fps_pruned_kernel<false, true><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, nullptr, tie_out);
+    return check_launch("farthest_point_sample (pruned, tie tracking)");
+  }
+  VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
+  fps_pruned_kernel<false, false><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, nullptr, nullptr);
   return check_launch("farthest_point_sample (pruned)");
 }
 

@@ -153,6 +153,7 @@ class Engine:
         s.nms_ws = torch.empty((lib.vnb_nms3d_workspace_bytes(B, p.npoint),), dtype=torch.uint8, device=dev)
         mmax = max(max(sa.npoint for sa in cfg.sa), cfg.proposal.npoint)
         s.sa_ws = torch.empty((lib.vnb_sa_workspace_bytes(B, mmax, 64),), dtype=torch.uint8, device=dev)
+        s.fps_tie = torch.zeros((B,), dtype=i32, device=dev)   # first non-unique round of the sa1 FPS, per cloud
         s.fps_ws = torch.empty((lib.vnb_fps_nested_workspace_bytes(B, max(sa.npoint for sa in cfg.sa)),), dtype=torch.uint8, device=dev)
         s.done = torch.cuda.Event()
         s.samp = torch.cuda.Stream(device=dev)   # sampling chain (FPS + gathers)
@@ -200,17 +201,18 @@ class Engine:
         for li, l in enumerate(s.lv):
             if li == 0:   # the only real search (raw cloud); deeper levels sample an FPS-ordered set
                 if not (self.debug_skip_fps1 and s.used):
-                    check(lib.vnb_farthest_point_sample(B, l.n, l.m, dptr(src), dptr(l.fps), _sp(samp)))
-            else:
-                check(lib.vnb_farthest_point_sample_nested(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws), _sp(samp)))
+                    check(lib.vnb_farthest_point_sample_ties(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_tie), _sp(samp)))
+            else:  # src = the first l.n picks of sa1's FPS, in order: tie-free parent rounds need no proof
+                check(lib.vnb_farthest_point_sample_nested_hint(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws),
+                                                                dptr(s.fps_tie), _sp(samp)))
             check(lib.vnb_gather_point(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(l.xyz), _sp(samp)))
             e = ev(); e.record(samp); e_lv.append(e)
             mark(f"fps{li + 1}", samp)
             src = l.xyz
         seeds_xyz = s.lv[1].xyz
         p = cfg.proposal
-        check(lib.vnb_farthest_point_sample_nested(B, s.lv[1].m, p.npoint, dptr(seeds_xyz), dptr(s.p_fps), dptr(s.fps_ws),
-                                                   _sp(samp)))
+        check(lib.vnb_farthest_point_sample_nested_hint(B, s.lv[1].m, p.npoint, dptr(seeds_xyz), dptr(s.p_fps), dptr(s.fps_ws),
+                                                        dptr(s.fps_tie), _sp(samp)))
         e_pf = ev(); e_pf.record(samp)
         mark("fps_prop", samp)
         # ---- neighbour searches (xyz + centroids only)

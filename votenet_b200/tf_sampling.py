@@ -32,6 +32,30 @@ def farthest_point_sample_nested(npoint, inp):
     return out
 
 
+def farthest_point_sample_ties(npoint, inp):
+    """farthest_point_sample that also returns, per cloud, the first round whose arg-max was not unique (int32 (B,);
+    0x7fffffff = every round had a unique winner).  Feeds farthest_point_sample_nested(..., parent_first_tie=...)."""
+    inp = _xyz3(inp, "FarthestPointSample")
+    b, n, _ = inp.shape
+    out = torch.empty((b, int(npoint)), dtype=torch.int32, device=inp.device)
+    ties = torch.empty((b,), dtype=torch.int32, device=inp.device)
+    check(lib.vnb_farthest_point_sample_ties(b, n, int(npoint), dptr(inp, torch.float32, "inp"), dptr(out), dptr(ties),
+                                             stream_ptr()))
+    return out, ties
+
+
+def farthest_point_sample_nested_hint(npoint, inp, parent_first_tie):
+    """farthest_point_sample_nested for an `inp` that is gather_point(parent_xyz, parent_fps_idx[:, :N]) of a
+    farthest_point_sample_ties call: clouds whose parent was tie-free for `npoint` rounds need no proof at all."""
+    inp = _xyz3(inp, "FarthestPointSample")
+    b, n, _ = inp.shape
+    out = torch.empty((b, int(npoint)), dtype=torch.int32, device=inp.device)
+    ws = torch.empty((lib.vnb_fps_nested_workspace_bytes(b, int(npoint)),), dtype=torch.uint8, device=inp.device)
+    check(lib.vnb_farthest_point_sample_nested_hint(b, n, int(npoint), dptr(inp, torch.float32, "inp"), dptr(out), dptr(ws),
+                                                    dptr(parent_first_tie, torch.int32, "parent_first_tie"), stream_ptr()))
+    return out
+
+
 def gather_point(inp, idx):
     """inp (B,N,3) f32, idx (B,M) i32 -> (B,M,3) f32.   Reference: tf_sampling.py:29-37 (GatherPoint, tf_sampling.cpp:126-148)."""
     inp = _xyz3(inp, "GatherPoint")
