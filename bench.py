@@ -310,13 +310,13 @@ def kernel_table(eng, cfg, peaks, flush):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=int, default=1)
-    ap.add_argument("--inflight", type=int, default=8, help="steps in flight (independent workspaces + streams)")
+    ap.add_argument("--inflight", type=int, default=12, help="steps in flight (independent workspaces + streams)")
     ap.add_argument("--fps-cluster", type=int, default=4,
                     help="CTAs per FPS cluster (4 = 32 SMs per batch: best throughput with steps overlapped; 8 = lowest latency)")
     ap.add_argument("--fps-variant", type=int, default=None, help="0: register/cluster FPS kernel, 1: bucket-pruned (default)")
