@@ -21,7 +21,8 @@
 //     real arithmetic), the last vote layer is issued with its 259 output columns permuted [features | xyz] so that the
 //     epilogue adds the residual and writes votes_feat / votes_xyz directly (no concat, no split).
 // Warps 0-7: loaders, then epilogues (TMEM lane quadrant = warp & 3, column half = warp >> 2); warp 8: weight ring;
-// warp 9: MMA issue.
+// warp 9: MMA issue.  The two single-role warps POLL their mbarriers (a parked try_wait wakes ~300 cycles after the
+// arrive, umma.cuh, and every one of the ~50 weight sub-chunks of a tile would pay that on the critical path).
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
         for (int c = 0; c < nch; ++c)
           for (int j = 0; j < npc; ++j, ++g) {
             const int s = g % NSTAGE;
-            if (g >= NSTAGE) mbar_wait(&w_empty[s], (uint32_t)((g / NSTAGE - 1) & 1));
+            if (g >= NSTAGE) mbar_wait_spin(&w_empty[s], (uint32_t)((g / NSTAGE - 1) & 1));
             const int rws = min(128, npad - 128 * j);
             mbar_arrive_expect_tx(&w_full[s], (uint32_t)(rws * 128));
             bulk_g2s(sW + s * PANEL, P.w_img[l] + ((size_t)c * npad + 128 * j) * 128, (uint32_t)(rws * 128), &w_full[s]);
@@ -140,14 +141,14 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
       // layer l >= 1 reads the resident buffer the epilogue of layer l-1 wrote: X after even layers, Y after odd ones
       const uint32_t abase = smem_u32((l & 1) ? sX : sY);
       if (l >= 1) {
-        mbar_wait(act_full, (uint32_t)((l - 1) & 1));
+        mbar_wait_spin(act_full, (uint32_t)((l - 1) & 1));
         tc_fence_after_sync();
       }
       for (int c = 0; c < nch; ++c) {
         const int kc = min(64, P.k_pad[l] - 64 * c);
         uint32_t a0;
         if (l == 0) {
-          mbar_wait(&a_full[c & 1], (uint32_t)((c >> 1) & 1));
+          mbar_wait_spin(&a_full[c & 1], (uint32_t)((c >> 1) & 1));
           tc_fence_after_sync();
           a0 = smem_u32(sY) + (uint32_t)(c & 1) * PANEL;
         } else {
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
         }
         for (int j = 0; j < npc; ++j, ++g) {
           const int s = g % NSTAGE;
-          mbar_wait(&w_full[s], (uint32_t)((g / NSTAGE) & 1));
+          mbar_wait_spin(&w_full[s], (uint32_t)((g / NSTAGE) & 1));
           tc_fence_after_sync();
           const int rws = min(128, npad - 128 * j);
           const uint32_t idesc = make_idesc_f16_f32(128, (uint32_t)rws);
