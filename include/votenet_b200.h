@@ -66,6 +66,8 @@ int vnb_farthest_point_sample_nested(int b, int n, int m, const float* xyz, int*
 /* FPS with provenance tracking.  vnb_farthest_point_sample_ties is vnb_farthest_point_sample that also reports, per
  * cloud, the first round whose arg-max was NOT unique (two points shared the maximal running distance exactly and the
  * reference's tie rule decided); 0x7fffffff if every round had a unique winner, 0 when the kernel in use cannot tell.
+ * Only rounds < track_rounds are reported (<= 0: all m rounds) — a nested level of m' picks needs m' of them.  The
+ * tracking costs ~8 % of a round (making it conditional on the round index cost more than it saved: measured).
  * vnb_farthest_point_sample_nested_hint is vnb_farthest_point_sample_nested for an input that is the GATHER, in order,
  * of the first n picks of such a parent call (new_xyz of the previous level, utils.py:42-45): if the parent's first
  * tie round is >= m, every round j < m had a unique arg-max p_j over the parent's superset, p_j is in the subset, the
@@ -73,7 +75,7 @@ int vnb_farthest_point_sample_nested(int b, int n, int m, const float* xyz, int*
  * check at all.  Clouds whose hint is smaller fall back to the parallel proof, then to the sequential sampler.  The
  * caller vouches for the provenance (wrong provenance = wrong indices); results are otherwise bit-identical. */
 int vnb_farthest_point_sample_ties(int b, int n, int m, const float* xyz, int* out_idx, int* first_tie_round,
-                                   void* stream);
+                                   int track_rounds, void* stream);
 int vnb_farthest_point_sample_nested_hint(int b, int n, int m, const float* xyz, int* out_idx, void* workspace,
                                           const int* parent_first_tie_round, void* stream);
 

@@ -175,6 +175,11 @@ def test_fps_tie_round_is_exact(cuda, kind):
     assert int(got_tie.item()) == want_tie, (kind, int(got_tie.item()), want_tie)
     if kind in ("sun", "uniform"):
         assert want_tie == 0x7FFFFFFF
+    if kind == "dup_of_pick":  # only rounds < track_rounds are examined
+        assert want_tie == 7
+        for tr, expect in ((7, 0x7FFFFFFF), (8, 7)):
+            _, t2 = farthest_point_sample_ties(m, T(x[None], cuda), track_rounds=tr)
+            assert int(t2.item()) == expect
 
 
 @pytest.mark.parametrize("kind", ["sun", "lattice", "dup"])

@@ -30,7 +30,7 @@ _SIGS = {
     "vnb_debug_trap_buffer": ([_p], _i),
     "vnb_fps_nested_workspace_bytes": ([_i, _i], _sz),
     "vnb_farthest_point_sample_nested": ([_i, _i, _i, _p, _p, _p, _p], _i),
-    "vnb_farthest_point_sample_ties": ([_i, _i, _i, _p, _p, _p, _p], _i),
+    "vnb_farthest_point_sample_ties": ([_i, _i, _i, _p, _p, _p, _i, _p], _i),
     "vnb_farthest_point_sample_nested_hint": ([_i, _i, _i, _p, _p, _p, _p, _p], _i),
     "vnb_query_ball_point_workspace_bytes": ([_i, _i], _sz),
     "vnb_query_ball_point_ws": ([_i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p], _i),

@@ -44,7 +44,8 @@ int g_fps_variant = 1;    // 0: register/cluster kernel only; 1: bucket-pruned s
                           // 2: bucket-pruned kernel for every n <= 20480
 
 int fps_pruned_capacity();
-int launch_fps_pruned(int b, int n, int m, const float* xyz, int* out, const int* flags, int* tie_out, cudaStream_t st);
+int launch_fps_pruned(int b, int n, int m, const float* xyz, int* out, const int* flags, int* tie_out, int tie_rounds,
+                      cudaStream_t st);
 
 // T threads per CTA, P points per thread, CL CTAs per cluster (launch attribute, CL*T % 512 == 0); W = T/32 warps.
 // MODE 0: cluster barrier per round; MODE 1: tagged slots, receivers poll their own shared memory.
@@ -352,9 +353,9 @@ static int fps_dispatch_t(int b, int n, int m, int CL, const float* xyz, int* ou
 // CTAs minimise the SM footprint of one call (better throughput when several calls overlap); many small CTAs minimise
 // the latency of one call.  CL*T must be a multiple of 512 (per-thread tie rule, see the header comment).
 static int fps_dispatch(int b, int n, int m, const float* xyz, int* out, const int* flags, cudaStream_t st,
-                        int* tie_out = nullptr) {
+                        int* tie_out = nullptr, int tie_rounds = 0) {
   if (n <= fps_pruned_capacity() && ((g_fps_variant == 1 && n > 2048) || g_fps_variant == 2))
-    return launch_fps_pruned(b, n, m, xyz, out, flags, tie_out, st);
+    return launch_fps_pruned(b, n, m, xyz, out, flags, tie_out, tie_rounds, st);
   // the register / cluster kernels do not track ties: report "round 0" (no round is known to be tie-free)
   if (tie_out != nullptr) VNB_CUDA(cudaMemsetAsync(tie_out, 0, sizeof(int) * (size_t)b, st));
   int T = g_fps_threads;
@@ -455,11 +456,11 @@ extern "C" int vnb_farthest_point_sample_nested(int b, int n, int m, const float
 }
 
 extern "C" int vnb_farthest_point_sample_ties(int b, int n, int m, const float* xyz, int* out_idx, int* first_tie_round,
-                                              void* stream) {
+                                              int track_rounds, void* stream) {
   if (int rc = fps_check_args(b, n, m)) return rc;
   VNB_REQUIRE(first_tie_round != nullptr, "farthest_point_sample_ties: first_tie_round buffer missing");
   if (b == 0) return VNB_OK;
-  return fps_dispatch(b, n, m, xyz, out_idx, nullptr, as_stream(stream), first_tie_round);
+  return fps_dispatch(b, n, m, xyz, out_idx, nullptr, as_stream(stream), first_tie_round, track_rounds > 0 ? track_rounds : m);
 }
 
 extern "C" int vnb_farthest_point_sample_nested_hint(int b, int n, int m, const float* xyz, int* out_idx, void* workspace,

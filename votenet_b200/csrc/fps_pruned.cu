@@ -79,7 +79,7 @@ __device__ __forceinline__ int warp_argmax(int hi, int& whi, bool& shared_max, T
 template <bool PROF, bool TIES>
 __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const float* __restrict__ xyz,
                                                            int* __restrict__ out, const int* __restrict__ flags,
-                                                           long long* __restrict__ prof, int* __restrict__ tie_out) {
+                                                           long long* __restrict__ prof, int* __restrict__ tie_out, int tie_rounds) {
   extern __shared__ __align__(16) unsigned char smem[];
   float2* sxy = reinterpret_cast<float2*>(smem + OFF_XY);
   uint16_t* stie = reinterpret_cast<uint16_t*>(smem + OFF_TIE);
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
     const int e = src * 4 + __shfl_sync(0xffffffffu, bj, src);
     const uint4 rec = s_rec[par * PNB + e];
     lx = __uint_as_float(rec.y); ly = __uint_as_float(rec.z); lz = __uint_as_float(rec.w);
-    if (TIES && (tie_sub || (rec.x >> 31)) && whi >= 0 && first_tie == 0x7fffffff) first_tie = r;
+    if (TIES && r < tie_rounds && (tie_sub || (rec.x >> 31)) && whi >= 0 && first_tie == 0x7fffffff) first_tie = r;
     if (warp == (r & (PW - 1)) && lane == 0) oc[r] = tie_key_to_index((uint32_t)stie[rec.x & 0x7fffffffu]);
     PF_TICK(3)
   }
@@ -330,19 +330,20 @@ extern long long* g_fps_prof;
 
 int fps_pruned_capacity() { return PCAP; }
 
-int launch_fps_pruned(int b, int n, int m, const float* xyz, int* out, const int* flags, int* tie_out, cudaStream_t st) {
+int launch_fps_pruned(int b, int n, int m, const float* xyz, int* out, const int* flags, int* tie_out, int tie_rounds,
+                      cudaStream_t st) {
   if (g_fps_prof != nullptr && flags == nullptr) {
     VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
-    fps_pruned_kernel<true, true><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, g_fps_prof, tie_out);
+    fps_pruned_kernel<true, true><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, g_fps_prof, tie_out, tie_rounds);
     return check_launch("farthest_point_sample (pruned, profiled)");
   }
   if (tie_out != nullptr) {
     VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
-    fps_pruned_kernel<false, true><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, nullptr, tie_out);
+    fps_pruned_kernel<false, true><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, nullptr, tie_out, tie_rounds);
     return check_launch("farthest_point_sample (pruned, tie tracking)");
   }
   VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
-  fps_pruned_kernel<false, false><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, nullptr, nullptr);
+  fps_pruned_kernel<false, false><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, nullptr, nullptr, 0);
   return check_launch("farthest_point_sample (pruned)");
 }
 

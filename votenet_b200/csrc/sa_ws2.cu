@@ -175,6 +175,13 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
       }
       fence_proxy_async_smem();
       mbar_arrive(&h1_full[s]);
+      if (pt < 128 && t + 1 < my_tiles) {
+        // relreg holds row pt of the NEXT tile by now: pull its q row (C1 halves = 2 lines) into L1, so the next
+        // iteration's gathers are L1 hits instead of L2 round trips (no registers are held across the tile for it)
+        const char* rowp = reinterpret_cast<const char*>(q + (size_t)__float_as_int(relreg.w) * C1);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rowp));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rowp + 128));
+      }
     }
   } else if (warp == 20) {
     // ================================================================ MMA2: D2[s] = H1[s] . W2^T

@@ -66,6 +66,8 @@ class Engine:
             self.slots = [self._make_slot() for _ in range(slots)]
         self._step = 0
         self.launches_per_forward = None
+        # rounds of the sa1 FPS whose arg-max uniqueness is tracked: the largest nested sample count that relies on it
+        self.tie_rounds = max([sa.npoint for sa in cfg.sa[1:]] + [cfg.proposal.npoint])
         self.debug_skip_fps1 = False  # experiment only: capture the graph without the SA1 FPS launch
         self.timeline = None   # debugging: set to [] (with use_graph=False) to collect (step, stage, event) marks
 
@@ -201,7 +203,8 @@ class Engine:
         for li, l in enumerate(s.lv):
             if li == 0:   # the only real search (raw cloud); deeper levels sample an FPS-ordered set
                 if not (self.debug_skip_fps1 and s.used):
-                    check(lib.vnb_farthest_point_sample_ties(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_tie), _sp(samp)))
+                    check(lib.vnb_farthest_point_sample_ties(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_tie),
+                                                             self.tie_rounds, _sp(samp)))
             else:  # src = the first l.n picks of sa1's FPS, in order: tie-free parent rounds need no proof
                 check(lib.vnb_farthest_point_sample_nested_hint(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws),
                                                                 dptr(s.fps_tie), _sp(samp)))

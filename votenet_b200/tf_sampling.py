@@ -32,7 +32,7 @@ def farthest_point_sample_nested(npoint, inp):
     return out
 
 
-def farthest_point_sample_ties(npoint, inp):
+def farthest_point_sample_ties(npoint, inp, track_rounds=0):
     """farthest_point_sample that also returns, per cloud, the first round whose arg-max was not unique (int32 (B,);
     0x7fffffff = every round had a unique winner).  Feeds farthest_point_sample_nested(..., parent_first_tie=...)."""
     inp = _xyz3(inp, "FarthestPointSample")
@@ -40,7 +40,7 @@ def farthest_point_sample_ties(npoint, inp):
     out = torch.empty((b, int(npoint)), dtype=torch.int32, device=inp.device)
     ties = torch.empty((b,), dtype=torch.int32, device=inp.device)
     check(lib.vnb_farthest_point_sample_ties(b, n, int(npoint), dptr(inp, torch.float32, "inp"), dptr(out), dptr(ties),
-                                             stream_ptr()))
+                                             int(track_rounds), stream_ptr()))
     return out, ties
 
 
