@@ -261,9 +261,10 @@ def test_fps_exchange_variants(cuda, mode, thr, cl):
 
 @pytest.mark.parametrize("n,m,r,ns,kind", [(20000, 2048, 0.2, 64, "room"), (20000, 300, 0.05, 16, "room"), (8192, 512, 0.4, 64, "uniform"),
                                            (5000, 100, 3.0, 64, "uniform"), (6000, 200, 0.3, 32, "outside"), (4096, 64, 1e-4, 8, "uniform"),
-                                           (7000, 256, 0.25, 64, "flat")])
+                                           (7000, 256, 0.25, 64, "flat"), (2048, 1024, 0.4, 64, "room"), (1024, 512, 0.8, 64, "room"),
+                                           (1024, 256, 0.3, 64, "uniform"), (1500, 100, 0.05, 64, "outside")])
 def test_ball_query_grid_matches_scan(cuda, n, m, r, ns, kind):
-    """The grid + bitmap kernel (n >= 4096) is bit-identical to the exhaustive scan and to the oracle, including queries
+    """The grid + bitmap kernel (n >= 1024) is bit-identical to the exhaustive scan and to the oracle, including queries
     outside the source bounding box, degenerate (planar) clouds, huge and tiny radii."""
     from votenet_b200 import synth
     from votenet_b200._lib import check, lib

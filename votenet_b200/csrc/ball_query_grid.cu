@@ -21,6 +21,7 @@
 namespace vnb {
 
 extern int g_bq_variant;
+int g_bq_grid_min_n = 1024;  // tuning: smallest source cloud that takes the grid path
 
 struct GridHdr {      // per cloud, at the start of its workspace slice
   float ox, oy, oz;   // grid origin (min corner)
@@ -222,7 +223,7 @@ extern "C" size_t vnb_query_ball_point_workspace_bytes(int b, int n) {
 
 extern "C" int vnb_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float* xyz1,
                                        const float* xyz2, int* idx, int* pts_cnt, void* workspace, void* stream) {
-  if (workspace == nullptr || g_bq_variant == 0 || n < 4096 || radius <= 1e-20f)
+  if (workspace == nullptr || g_bq_variant == 0 || n < g_bq_grid_min_n || radius <= 1e-20f)
     return vnb_query_ball_point(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, stream);
   VNB_REQUIRE(radius > 0, "QueryBallPoint expects positive radius");          // tf_grouping.cpp:71
   VNB_REQUIRE(nsample > 0, "QueryBallPoint expects positive nsample");        // tf_grouping.cpp:74

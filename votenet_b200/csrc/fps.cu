@@ -34,6 +34,7 @@
 namespace vnb {
 
 extern int g_bq_variant;
+extern int g_bq_grid_min_n;
 extern int g_sa_variant;
 extern int g_sa_sms;
 extern int g_sa_split;
@@ -388,6 +389,7 @@ extern "C" int vnb_set_tuning(const char* key, int value) {
   else if (k == "fps_threads") g_fps_threads = value;
   else if (k == "fps_variant") g_fps_variant = value;
   else if (k == "ball_query_variant") vnb::g_bq_variant = value;
+  else if (k == "bq_grid_min_n") vnb::g_bq_grid_min_n = value;
   else if (k == "sa_variant") vnb::g_sa_variant = value;
   else if (k == "sa_sms") vnb::g_sa_sms = value;
   else if (k == "sa_split") vnb::g_sa_split = value < 1 ? 1 : value;

@@ -125,7 +125,7 @@ class Engine:
             l.q = E((B * n, sa.mlp[0]), f16) if self.sa_layers[li][3] is not None else None
             l.feat = E((B, sa.npoint, sa.mlp[-1]))
             l.bq_ws = (torch.empty((lib.vnb_query_ball_point_workspace_bytes(B, n),), dtype=torch.uint8, device=dev)
-                       if n >= 4096 else None)
+                       if n >= 512 else None)   # the C side picks scan / grid by n (tuning: bq_grid_min_n)
             s.lv.append(l)
             n = sa.npoint
         c = cfg.sa[-1].mlp[-1]

@@ -19,7 +19,7 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
     # large searched sets go through the grid + index-bitmap kernel (bit-identical outputs); it needs scratch memory
     ws = None
-    if n >= 4096:
+    if n >= 1024:
         ws = torch.empty((lib.vnb_query_ball_point_workspace_bytes(b, n),), dtype=torch.uint8, device=xyz1.device)
     check(lib.vnb_query_ball_point_ws(b, n, m, float(radius), int(nsample), dptr(xyz1, torch.float32, "xyz1"),
                                       dptr(xyz2, torch.float32, "xyz2"), dptr(idx), dptr(cnt), dptr(ws), stream_ptr()))
