@@ -200,6 +200,27 @@ int vnb_fp_module_fused(int b, int n, int m, int c1, int c2, const float* dist, 
                         const float* vote_w0_xyz_f32, const float* seeds_xyz, float* votes_xyz, float* votes_feat,
                         void* stream);
 
+/* ------------------------------------------------------------------ backward ops ---- */
+
+/* scatteraddpointLauncher(b,n,m,out_g,idx,inp_g)              tf_ops/sampling/tf_sampling_g.cu:183-192,209-211
+ * (op GatherPointGrad, tf_sampling.cpp:150-178; registered as the gradient of GatherPoint, tf_sampling.py:43-47)
+ * out_g (b,m,3), idx (b,m) -> inp_g (b,n,3) = scatter-add; inp_g is zeroed first (tf_sampling.cpp:174). */
+int vnb_gather_point_grad(int b, int n, int m, const float* out_g, const int* idx, float* inp_g, void* stream);
+
+/* groupPointGradLauncher(b,n,c,m,nsample,grad_out,idx,grad_points)   tf_ops/grouping/tf_grouping_g.cu:61-78,137-141
+ * (op GroupPointGrad, tf_grouping.cpp:173-208; gradient of GroupPoint, tf_grouping.py:42-46)
+ * grad_out (b,m,nsample,c), idx (b,m,nsample) -> grad_points (b,n,c), zeroed first (tf_grouping.cpp:203). */
+int vnb_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int* idx,
+                         float* grad_points, void* stream);
+
+/* threeinterpolate_grad_cpu(b,n,c,m,grad_out,idx,weight,grad_points)  tf_ops/3d_interpolation/tf_interpolate.cpp:131-153
+ * (op ThreeInterpolateGrad, :225-262, CPU-only in the reference; gradient of ThreeInterpolate, tf_interpolate.py:29-34)
+ * grad_out (b,n,c), idx (b,n,3), weight (b,n,3) -> grad_points (b,m,c), zeroed first (:255).
+ * All three accumulate with float atomics (as the reference's GPU kernels do): equal to a sequential sum up to the
+ * rounding of a different summation order. */
+int vnb_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx, const float* weight,
+                               float* grad_points, void* stream);
+
 /* row-wise concat / split helpers: out (rows, ca+cb) = [a (rows,ca), b (rows,cb)]  and the inverse */
 int vnb_concat2(int rows, int ca, int cb, const float* a, const float* b, float* out, void* stream);
 int vnb_split2(int rows, int ca, int cb, const float* in, float* a, float* b, void* stream);

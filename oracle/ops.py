@@ -117,6 +117,38 @@ def three_interpolate(points, idx, weight):
     return out
 
 
+def gather_point_grad(n, idx, out_g):
+    """out_g (b,m,3), idx (b,m) -> inp_g (b,n,3).  Restates tf_sampling_g.cu:183-192."""
+    out_g, pg = _f(out_g)
+    idx, pidx = _i(idx)
+    b, m = idx.shape
+    inp_g = np.zeros((b, n, 3), np.float32)
+    _lib.vno_gather_point_grad(b, int(n), m, pg, pidx, inp_g.ctypes.data_as(_fp))
+    return inp_g
+
+
+def group_point_grad(n, idx, grad_out):
+    """grad_out (b,m,ns,c), idx (b,m,ns) -> grad_points (b,n,c).  Restates tf_grouping_g.cu:61-78."""
+    grad_out, pg = _f(grad_out)
+    idx, pidx = _i(idx)
+    b, m, ns = idx.shape
+    c = grad_out.shape[3]
+    gp = np.zeros((b, n, c), np.float32)
+    _lib.vno_group_point_grad(b, int(n), c, m, ns, pg, pidx, gp.ctypes.data_as(_fp))
+    return gp
+
+
+def three_interpolate_grad(m, idx, weight, grad_out):
+    """grad_out (b,n,c), idx (b,n,3), weight (b,n,3) -> grad_points (b,m,c).  Restates tf_interpolate.cpp:131-153."""
+    grad_out, pg = _f(grad_out)
+    idx, pidx = _i(idx)
+    weight, pw = _f(weight)
+    b, n, c = grad_out.shape
+    gp = np.zeros((b, m, c), np.float32)
+    _lib.vno_three_interpolate_grad(b, n, c, int(m), pg, pidx, pw, gp.ctypes.data_as(_fp))
+    return gp
+
+
 def intersection2d(box1, box2):
     _, p1 = _f(box1)
     _, p2 = _f(box2)
@@ -188,6 +220,17 @@ class _Ref:
         rc = self.lib.ref_three_interpolate(b, m, c, n, pp, pidx, pw, out.ctypes.data_as(_fp))
         assert rc == 0
         return out
+
+    def three_interpolate_grad(self, m, idx, weight, grad_out):
+        """The reference's ThreeInterpolateGradOp::Compute (tf_interpolate.cpp:225-262), unmodified."""
+        grad_out, pg = _f(grad_out)
+        idx, pidx = _i(idx)
+        weight, pw = _f(weight)
+        b, n, c = grad_out.shape
+        gp = np.zeros((b, m, c), np.float32)
+        rc = self.lib.ref_three_interpolate_grad(b, n, c, int(m), pg, pidx, pw, gp.ctypes.data_as(_fp))
+        assert rc == 0
+        return gp
 
     def intersection2d(self, box1, box2):
         a1, p1 = _f(box1)

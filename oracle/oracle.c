@@ -154,6 +154,51 @@ void vno_three_interpolate(int b, int m, int c, int n, const float* points, cons
     }
 }
 
+/* ================= backward ops =================
+ * Sequential float sums in the reference's loop order.  The reference's GPU kernels (and the product) accumulate with
+ * atomics, whose order is not fixed: parity for these three is "equal up to the rounding of a reordered sum".      */
+
+/* ---- gather_point_grad: scatteraddpointKernel, tf_sampling_g.cu:183-192 (output zeroed, tf_sampling.cpp:174) ---- */
+void vno_gather_point_grad(int b, int n, int m, const float* out_g, const int* idx, float* inp_g) {
+  memset(inp_g, 0, sizeof(float) * (size_t)b * n * 3);
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < m; ++j) {
+      int a = idx[(size_t)i * m + j];
+      for (int l = 0; l < 3; ++l) inp_g[((size_t)i * n + a) * 3 + l] += out_g[((size_t)i * m + j) * 3 + l];
+    }
+}
+
+/* ---- group_point_grad: tf_grouping_g.cu:61-78 (output zeroed, tf_grouping.cpp:203) ---- */
+void vno_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int* idx,
+                          float* grad_points) {
+  memset(grad_points, 0, sizeof(float) * (size_t)b * n * c);
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < m; ++j)
+      for (int k = 0; k < nsample; ++k) {
+        int ii = idx[((size_t)i * m + j) * nsample + k];
+        for (int l = 0; l < c; ++l)
+          grad_points[((size_t)i * n + ii) * c + l] += grad_out[(((size_t)i * m + j) * nsample + k) * c + l];
+      }
+}
+
+/* ---- three_interpolate_grad: tf_interpolate.cpp:131-153 (output zeroed, :255) ---- */
+void vno_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx, const float* weight,
+                                float* grad_points) {
+  memset(grad_points, 0, sizeof(float) * (size_t)b * m * c);
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < n; ++j) {
+      const float* w = weight + ((size_t)i * n + j) * 3;
+      const int* id = idx + ((size_t)i * n + j) * 3;
+      const float* g = grad_out + ((size_t)i * n + j) * c;
+      float* gp = grad_points + (size_t)i * m * c;
+      for (int l = 0; l < c; ++l) {
+        gp[(size_t)id[0] * c + l] += g[l] * w[0];
+        gp[(size_t)id[1] * c + l] += g[l] * w[1];
+        gp[(size_t)id[2] * c + l] += g[l] * w[2];
+      }
+    }
+}
+
 /* ================= 3-D NMS: tf_ops/3d_nms/tf_nms3d.cpp ================= */
 
 /* :43-46 */

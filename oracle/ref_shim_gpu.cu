@@ -12,6 +12,9 @@ void gatherpointLauncher(int b, int n, int m, const float* inp, const int* idx, 
 void queryBallPointLauncher(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
                             int* idx, int* pts_cnt);
 void groupPointLauncher(int b, int n, int c, int m, int nsample, const float* points, const int* idx, float* out);
+void scatteraddpointLauncher(int b, int n, int m, const float* out_g, const int* idx, float* inp_g);          // tf_sampling.cpp:150
+void groupPointGradLauncher(int b, int n, int c, int m, int nsample, const float* grad_out, const int* idx,
+                            float* grad_points);                                                                // tf_grouping.cpp:173
 
 extern "C" {
 // all pointers are device pointers; launches go to the legacy default stream like the reference's.
@@ -30,6 +33,17 @@ int ref_gpu_query_ball_point(int b, int n, int m, float radius, int nsample, con
 }
 int ref_gpu_group_point(int b, int n, int c, int m, int nsample, const float* points, const int* idx, float* out) {
   groupPointLauncher(b, n, c, m, nsample, points, idx, out);
+  return (int)cudaDeviceSynchronize();
+}
+int ref_gpu_gather_point_grad(int b, int n, int m, const float* out_g, const int* idx, float* inp_g) {
+  cudaMemset(inp_g, 0, sizeof(float) * (size_t)b * n * 3);  // tf_sampling.cpp:174
+  scatteraddpointLauncher(b, n, m, out_g, idx, inp_g);
+  return (int)cudaDeviceSynchronize();
+}
+int ref_gpu_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int* idx,
+                             float* grad_points) {
+  cudaMemset(grad_points, 0, sizeof(float) * (size_t)b * n * c);  // tf_grouping.cpp:203
+  groupPointGradLauncher(b, n, c, m, nsample, grad_out, idx, grad_points);
   return (int)cudaDeviceSynchronize();
 }
 }

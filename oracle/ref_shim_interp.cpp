@@ -34,4 +34,20 @@ int ref_three_interpolate(int b, int m, int c, int n, const float* points, const
   return 0;
 }
 
+int ref_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx, const float* weight,
+                               float* grad_points) {
+  OpKernelConstruction cc;
+  ThreeInterpolateGradOp op(&cc);
+  OpKernelContext ctx;
+  std::vector<float> points((size_t)b * m * c, 0.f);  // input 0 is only inspected for its shape (tf_interpolate.cpp:229-233)
+  ctx.inputs.push_back(Tensor(points.data(), TensorShape{b, m, c}));
+  ctx.inputs.push_back(Tensor(idx, TensorShape{b, n, 3}));
+  ctx.inputs.push_back(Tensor(weight, TensorShape{b, n, 3}));
+  ctx.inputs.push_back(Tensor(grad_out, TensorShape{b, n, c}));
+  op.Compute(&ctx);
+  if (!ctx.status.ok()) return 1;
+  memcpy(grad_points, ctx.outputs[0].raw(), sizeof(float) * (size_t)b * m * c);
+  return 0;
+}
+
 }  // extern "C"

@@ -191,3 +191,48 @@ def test_group_and_gather_are_exact_copies():
     g = ops.group_point(pts, idx)
     for b in range(2):
         assert np.array_equal(g[b], pts[b][idx[b]])
+
+
+# ------------------------------------------------------------------------------------------------ backward ops
+@pytest.mark.parametrize("seed", [0, 1])
+def test_grad_ops_oracle_vs_reference_and_numpy(seed):
+    """The C restatement of the three scatter-add gradients: three_interpolate_grad is compared with the reference's own
+    ThreeInterpolateGradOp::Compute (compiled unmodified) bit for bit; all three with a float64 numpy scatter-add, and
+    with the adjoint identity <g, op(x)> == <op_grad(g), x> of the forward ops."""
+    rng = np.random.default_rng(seed)
+    b, n, m, c, ns = 2, 300, 64, 20, 8
+    # three_interpolate_grad
+    idx = rng.integers(0, m, (b, n, 3)).astype(np.int32)
+    w = rng.random((b, n, 3), dtype=np.float32)
+    g = rng.standard_normal((b, n, c)).astype(np.float32)
+    got = ops.three_interpolate_grad(m, idx, w, g)
+    if ops.ref.available:
+        assert np.array_equal(got, ops.ref.three_interpolate_grad(m, idx, w, g))
+    want = np.zeros((b, m, c))
+    for i in range(b):
+        for k in range(3):
+            np.add.at(want[i], idx[i, :, k], g[i].astype(np.float64) * w[i, :, k:k + 1])
+    assert np.abs(got - want).max() < 1e-4
+    pts = rng.standard_normal((b, m, c)).astype(np.float32)
+    lhs = float((ops.three_interpolate(pts, idx, w).astype(np.float64) * g).sum())
+    assert abs(lhs - float((got.astype(np.float64) * pts).sum())) < 1e-3 * max(1.0, abs(lhs))
+    # group_point_grad
+    gidx = rng.integers(0, n, (b, m, ns)).astype(np.int32)
+    gg = rng.standard_normal((b, m, ns, c)).astype(np.float32)
+    got = ops.group_point_grad(n, gidx, gg)
+    want = np.zeros((b, n, c))
+    for i in range(b):
+        np.add.at(want[i], gidx[i].reshape(-1), gg[i].reshape(-1, c).astype(np.float64))
+    assert np.abs(got - want).max() < 1e-4
+    x = rng.standard_normal((b, n, c)).astype(np.float32)
+    lhs = float((ops.group_point(x, gidx).astype(np.float64) * gg).sum())
+    assert abs(lhs - float((got.astype(np.float64) * x).sum())) < 1e-3 * max(1.0, abs(lhs))
+    # gather_point_grad (duplicates in idx accumulate)
+    pidx = rng.integers(0, 50, (b, m)).astype(np.int32)
+    pg = rng.standard_normal((b, m, 3)).astype(np.float32)
+    got = ops.gather_point_grad(n, pidx, pg)
+    want = np.zeros((b, n, 3))
+    for i in range(b):
+        np.add.at(want[i], pidx[i], pg[i].astype(np.float64))
+    assert np.abs(got - want).max() < 1e-5
+    assert (got[:, 50:] == 0).all()

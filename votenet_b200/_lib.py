@@ -50,6 +50,9 @@ _SIGS = {
     "vnb_sa_workspace_bytes": ([_i, _i, _i], _sz),
     "vnb_fp_interpolate_concat": ([_i] * 5 + [_p] * 6, _i),
     "vnb_fp_module_fused": ([_i] * 5 + [_p] * 4 + [_i] + [_p] * 4 + [_i] + [_p] * 8, _i),
+    "vnb_gather_point_grad": ([_i, _i, _i, _p, _p, _p, _p], _i),
+    "vnb_group_point_grad": ([_i] * 5 + [_p] * 4, _i),
+    "vnb_three_interpolate_grad": ([_i] * 4 + [_p] * 5, _i),
     "vnb_concat2": ([_i, _i, _i, _p, _p, _p, _p], _i),
     "vnb_split2": ([_i, _i, _i, _p, _p, _p, _p], _i),
     "vnb_decode_boxes": ([_i, _i] + [_p] * 8, _i),

@@ -32,6 +32,7 @@ SOURCES = {
     "sa1_ws2.cu": [],
     "linear_tc.cu": [],
     "fp_chain.cu": [],
+    "grad_ops.cu": [],
 }
 
 

@@ -21,9 +21,31 @@ def three_nn(xyz1, xyz2):
     return dist, idx
 
 
+class _ThreeInterpolateFn(torch.autograd.Function):
+    """ThreeInterpolate with its registered gradient (@tf.RegisterGradient('ThreeInterpolate'), tf_interpolate.py:29-34:
+    gradient w.r.t. points only, None for idx and weight)."""
+
+    @staticmethod
+    def forward(ctx, points, idx, weight):
+        ctx.save_for_backward(points, idx, weight)
+        return _three_interpolate_fwd(points, idx, weight)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        points, idx, weight = ctx.saved_tensors
+        return three_interpolate_grad(points, idx, weight, grad_out.contiguous()), None, None
+
+
 def three_interpolate(points, idx, weight):
     """points (b,m,c), idx (b,n,3) i32, weight (b,n,3) -> (b,n,c).
-    Reference: tf_interpolate.py:19-28 (ThreeInterpolate, tf_interpolate.cpp:107-127,191-222)."""
+    Reference: tf_interpolate.py:19-28 (ThreeInterpolate, tf_interpolate.cpp:107-127,191-222).
+    Differentiable w.r.t. points (ThreeInterpolateGrad) when points requires grad."""
+    if torch.is_grad_enabled() and points.requires_grad:
+        return _ThreeInterpolateFn.apply(points, idx, weight)
+    return _three_interpolate_fwd(points, idx, weight)
+
+
+def _three_interpolate_fwd(points, idx, weight):
     if points.dim() != 3:
         raise ValueError("ThreeInterpolate expects (b,m,c) points shape")  # tf_interpolate.cpp:197
     b, m, c = points.shape
@@ -36,3 +58,22 @@ def three_interpolate(points, idx, weight):
     check(lib.vnb_three_interpolate(b, m, c, n, dptr(points, torch.float32, "points"), dptr(idx, torch.int32, "idx"),
                                     dptr(weight, torch.float32, "weight"), dptr(out), stream_ptr()))
     return out
+
+
+def three_interpolate_grad(points, idx, weight, grad_out):
+    """Gradient of three_interpolate w.r.t. points: (b,m,c) <- sum over the 3 neighbours of grad_out (b,n,c) * weight.
+    Reference: ThreeInterpolateGrad, tf_interpolate.py:29-34 / tf_interpolate.cpp:131-153,225-262 (one CPU thread)."""
+    if points.dim() != 3:
+        raise ValueError("ThreeInterpolateGrad expects (b,m,c) points shape")      # tf_interpolate.cpp:231
+    b, m, c = points.shape
+    if idx.dim() != 3 or idx.shape[0] != b or idx.shape[2] != 3:
+        raise ValueError("ThreeInterpolateGrad expects (b,n,3) idx shape")         # tf_interpolate.cpp:236
+    n = idx.shape[1]
+    if tuple(weight.shape) != (b, n, 3):
+        raise ValueError("ThreeInterpolateGrad expects (b,n,3) weight shape")      # tf_interpolate.cpp:240
+    if tuple(grad_out.shape) != (b, n, c):
+        raise ValueError("ThreeInterpolateGrad expects (b,n,c) grad_out shape")    # tf_interpolate.cpp:243
+    grad_points = torch.empty((b, m, c), dtype=torch.float32, device=points.device)
+    check(lib.vnb_three_interpolate_grad(b, n, c, m, dptr(grad_out, torch.float32, "grad_out"), dptr(idx, torch.int32, "idx"),
+                                         dptr(weight, torch.float32, "weight"), dptr(grad_points), stream_ptr()))
+    return grad_points

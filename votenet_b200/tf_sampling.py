@@ -56,8 +56,29 @@ def farthest_point_sample_nested_hint(npoint, inp, parent_first_tie):
     return out
 
 
+class _GatherPointFn(torch.autograd.Function):
+    """GatherPoint with its registered gradient (@tf.RegisterGradient('GatherPoint'), tf_sampling.py:43-47)."""
+
+    @staticmethod
+    def forward(ctx, inp, idx):
+        ctx.save_for_backward(inp, idx)
+        return _gather_point_fwd(inp, idx)
+
+    @staticmethod
+    def backward(ctx, out_g):
+        inp, idx = ctx.saved_tensors
+        return gather_point_grad(inp, idx, out_g.contiguous()), None
+
+
 def gather_point(inp, idx):
-    """inp (B,N,3) f32, idx (B,M) i32 -> (B,M,3) f32.   Reference: tf_sampling.py:29-37 (GatherPoint, tf_sampling.cpp:126-148)."""
+    """inp (B,N,3) f32, idx (B,M) i32 -> (B,M,3) f32.   Reference: tf_sampling.py:29-37 (GatherPoint, tf_sampling.cpp:126-148).
+    Differentiable w.r.t. inp (GatherPointGrad) when inp requires grad."""
+    if torch.is_grad_enabled() and inp.requires_grad:
+        return _GatherPointFn.apply(inp, idx)
+    return _gather_point_fwd(inp, idx)
+
+
+def _gather_point_fwd(inp, idx):
     inp = _xyz3(inp, "GatherPoint")
     if idx.dim() != 2 or idx.shape[0] != inp.shape[0]:
         raise ValueError("GatherPoint expects (batch_size,num_result) idx shape")  # tf_sampling.cpp:136
@@ -67,3 +88,19 @@ def gather_point(inp, idx):
     check(lib.vnb_gather_point(b, n, m, dptr(inp, torch.float32, "inp"), dptr(idx, torch.int32, "idx"), dptr(out),
                                stream_ptr()))
     return out
+
+
+def gather_point_grad(inp, idx, out_g):
+    """Gradient of gather_point w.r.t. inp: (B,N,3) <- scatter-add of out_g (B,M,3) at idx (B,M).
+    Reference: GatherPointGrad, tf_sampling.py:43-47 / tf_sampling.cpp:150-178 / tf_sampling_g.cu:183-192."""
+    inp = _xyz3(inp, "GatherPointGrad")
+    if idx.dim() != 2 or idx.shape[0] != inp.shape[0]:
+        raise ValueError("GatherPointGradGpuOp expects (batch_size,num_result) idx shape")        # tf_sampling.cpp:161
+    b, n, _ = inp.shape
+    m = idx.shape[1]
+    if out_g.dim() != 3 or tuple(out_g.shape) != (b, m, 3):
+        raise ValueError("GatherPointGradGpuOp expects (batch_size,num_result,3) out_g shape")    # tf_sampling.cpp:167
+    inp_g = torch.empty((b, n, 3), dtype=torch.float32, device=inp.device)
+    check(lib.vnb_gather_point_grad(b, n, m, dptr(out_g, torch.float32, "out_g"), dptr(idx, torch.int32, "idx"), dptr(inp_g),
+                                    stream_ptr()))
+    return inp_g
