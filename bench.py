@@ -472,6 +472,9 @@ def main():
         roof = {"kernel": dom["kernel"], "bound": "hbm" if dom["unit"] == "GB/s" else "tensor", "achieved": dom["achieved"],
                 "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic,
                 "peak_source": peaks["src"], "ms_per_launch": dom["ms"],
+                # share of one forward's SERIALISED kernel time (what the ncu launch list in profiles/ shows); forwards
+                # overlap in the timed loop, so ms_per_launch is larger than ms_per_step
+                "share_of_serialised_forward": dom["ms"] / sum(r["ms"] for r in ktab),
                 "note": dom.get("note", "")}
         cpu = None if args.no_cpu_baseline else cpu_baseline(cfg, w)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
