@@ -171,6 +171,47 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
     // ================================================================ PRODUCER: one grouped row per thread
     const int pt = tid - 768;
     const float4* rp = rel + (size_t)first_tile * 128 + pt;
+    if (c <= 4) {
+      // Narrow features (VoteNet: c = 1 height or c = 3 xyz).  The producer's work per tile is ~150 cycles, but every
+      // value it needs is two DEPENDENT global loads away (table row -> feature row): with a one-tile look-ahead the
+      // whole pipeline ran at one memory latency (~900 cycles) per tile (vnb_debug_sa_trace).  Here table rows are
+      // requested FOUR tiles ahead and feature rows TWO tiles ahead (address from the row requested two tiles
+      // earlier), so each load has two tile periods to land; 28 registers of look-ahead state.
+      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, r3 = r0;   // table rows of tiles t .. t+3
+      float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4];  // features of tiles t, t+1 (, t+2)
+      if (my_tiles > 0) r0 = __ldg(rp);
+      if (my_tiles > 1) r1 = __ldg(rp + 128);
+      if (my_tiles > 2) r2 = __ldg(rp + 256);
+      if (my_tiles > 3) r3 = __ldg(rp + 384);
+      auto load_feat = [&](const float4& r, float (&f)[4]) {
+        const float* fp = feat + (size_t)__float_as_int(r.w) * c;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] = i < c ? __ldg(fp + i) : 0.f;
+      };
+      if (my_tiles > 0) load_feat(r0, f0);
+      if (my_tiles > 1) load_feat(r1, f1);
+      for (int t = 0; t < my_tiles; ++t) {
+        const int s = t & 1;
+        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t + 4 < my_tiles) r4 = __ldg(rp + (size_t)(t + 4) * 128);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f2[i] = 0.f;
+        if (t + 2 < my_tiles) load_feat(r2, f2);
+        if (t >= 2) mbar_wait(&m1_done[s], par_of(t - 2));  // M1(t-2) finished reading A0[s]
+        if (warp == 24) { S1_STAMP(0, t, 0) }
+        uint8_t* a0 = sA0 + s * A0_BYTES;
+        *reinterpret_cast<uint4*>(a0 + sw128_offset((uint32_t)pt, 0)) =
+            make_uint4(pack2(r0.x, r0.y), pack2(r0.z, f0[0]), pack2(f0[1], f0[2]), pack2(f0[3], 0.f));
+        *reinterpret_cast<uint4*>(a0 + sw128_offset((uint32_t)pt, 8)) =
+            make_uint4(0u, 0u, 0u, pack2(1.f, 1.f));  // k = 14, 15: the constant 1 that multiplies b1 (hi, lo)
+        fence_proxy_async_smem();
+        mbar_arrive(&a0_full[s]);
+        if (warp == 24) { S1_STAMP(0, t, 1) }
+        r0 = r1; r1 = r2; r2 = r3; r3 = r4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { f0[i] = f1[i]; f1[i] = f2[i]; }
+      }
+    } else {
     float4 r_cur = make_float4(0.f, 0.f, 0.f, 0.f), r_nxt = r_cur;   // table rows of tiles t, t+1
     if (my_tiles > 0) r_cur = __ldg(rp);
     if (my_tiles > 1) r_nxt = __ldg(rp + 128);
@@ -208,6 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
       r_cur = r_nxt; r_nxt = r_nn;
 #pragma unroll
       for (int i = 0; i < 11; ++i) f_cur[i] = f_nxt[i];
+    }
     }
   } else if (warp == 28) {
     // ================================================================ MMA1: D1[s] = A0[s] . W1^T  (single K = 16 step)
