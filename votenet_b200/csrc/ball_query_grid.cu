@@ -235,7 +235,8 @@ extern "C" int vnb_query_ball_point_ws(int b, int n, int m, float radius, int ns
   if (int rc = check_launch("query_ball_point grid build")) return rc;
   const size_t smem = (size_t)GQ_WARPS * ((n + 31) / 32) * 4;
   VNB_REQUIRE(smem <= 200 * 1024, "query_ball_point: n too large for the bitmap path");
-  VNB_CUDA(cudaFuncSetAttribute(grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024)  // (never lower the limit below the default: a profiler that patches the kernel needs the headroom)
+    VNB_CUDA(cudaFuncSetAttribute(grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((m + GQ_WARPS - 1) / GQ_WARPS, b);
   grid_query_kernel<<<grid, GQ_WARPS * 32, smem, st>>>(n, m, ball_d2_max(radius), nsample, xyz2,
                                                        static_cast<const char*>(workspace), slice, idx, pts_cnt);

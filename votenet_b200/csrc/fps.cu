@@ -288,8 +288,9 @@ static int launch_fps(int b, int n, int m, int CL, const float* xyz, int* out, c
   cfg.gridDim = dim3((unsigned)(b * CL));
   cfg.blockDim = dim3(T);
   cfg.dynamicSmemBytes = SP ? (size_t)T * P * sizeof(float4) : 0;
-  VNB_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<T, P, MODE, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)cfg.dynamicSmemBytes));
+  if (cfg.dynamicSmemBytes > 48 * 1024)
+    VNB_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<T, P, MODE, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)cfg.dynamicSmemBytes));
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;

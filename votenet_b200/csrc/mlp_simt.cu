@@ -121,7 +121,8 @@ int sa_simt(int b, int n, int c, int m, const float* xyz, const float* feat, con
   if (c2 > cmax) cmax = c2;
   size_t smem = (size_t)2 * 64 * cmax * sizeof(float);
   if (smem > 220 * 1024) return set_err(VNB_ERR_INVALID, "sa_group_mlp_max(fp32): channel width %d too large", cmax);
-  VNB_CUDA(cudaFuncSetAttribute(sa_simt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024)
+    VNB_CUDA(cudaFuncSetAttribute(sa_simt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sa_simt_kernel<64><<<dim3(m, b), 256, smem, st>>>(n, c, m, xyz, feat, new_xyz, idx, c1, c2, c3, w1, b1, w2, b2, w3,
                                                     b3, out, cmax);
   return check_launch("sa_group_mlp_max (fp32 simt)");
