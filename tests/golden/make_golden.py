@@ -65,6 +65,11 @@ def main():
         inter = np.array([ops.ref.intersection2d(boxes[0, i], boxes[0, j]) for i in range(16) for j in range(16)], np.float32)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), seed=seed, b=b, k=k, degenerate=deg, thr=thr, selected=sel,
                             inter2d_16x16=inter)
+    # ThreeInterpolateGrad from the reference's own op: same config-1 neighbours, seeded grad_out
+    g = np.random.default_rng(2).standard_normal((1, 1024, 256)).astype(np.float32)
+    gp = ops.ref.three_interpolate_grad(256, idx, w, g)
+    np.savez_compressed(os.path.join(HERE, "ref_interpolate_grad_config1.npz"), grad_rows=gp[:, ::16],
+                        grad_sum=np.float64(gp.astype(np.float64).sum()))
     x = fps_inputs()
     f = ops.farthest_point_sample(64, x)
     nx = ops.gather_point(x, f)

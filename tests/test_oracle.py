@@ -193,6 +193,18 @@ def test_group_and_gather_are_exact_copies():
         assert np.array_equal(g[b], pts[b][idx[b]])
 
 
+def test_golden_interpolate_grad_config1():
+    """three_interpolate_grad of the oracle == the fixture produced by the reference's own ThreeInterpolateGradOp."""
+    xyz1, xyz2, _ = make_golden.interp_inputs()
+    dist, idx = ops.three_nn(xyz1, xyz2)
+    w = make_golden.fp_weights(dist)
+    g = np.random.default_rng(2).standard_normal((1, 1024, 256)).astype(np.float32)
+    gp = ops.three_interpolate_grad(256, idx, w, g)
+    fx = golden("ref_interpolate_grad_config1")
+    assert np.array_equal(gp[:, ::16], fx["grad_rows"])
+    assert abs(float(gp.astype(np.float64).sum()) - float(fx["grad_sum"])) < 1e-9
+
+
 # ------------------------------------------------------------------------------------------------ backward ops (SURVEY §8(f) rank 1)
 @pytest.mark.parametrize("seed", [0, 1])
 def test_grad_ops_oracle_vs_reference_and_numpy(seed):
