@@ -343,7 +343,7 @@ def main():
     from votenet_b200 import synth
     from votenet_b200._lib import lib
     from votenet_b200.config import VoteNetConfig
-    from votenet_b200.dist import all_gather_records, merge_gathered, shard_range
+    from votenet_b200.dist import DetectionGather, shard_range
     from votenet_b200.engine import Engine
     from votenet_b200.weights import make_synthetic_weights
 
@@ -389,6 +389,7 @@ def main():
     d2h = eng.record_nbytes
 
     NS = args.inflight
+    gather = DetectionGather(world, B, cfg.proposal.npoint, dev, slots=NS) if world > 1 else None
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     ctl = torch.cuda.current_stream(dev)
 
@@ -397,16 +398,14 @@ def main():
         rec = eng.infer_device(ring_xyz[i % RING], ring_feat[i % RING], stream=st)
         if world > 1:
             with torch.cuda.stream(st):
-                g = all_gather_records(rec.buf, world)
-                merge_gathered(g, B, cfg.proposal.npoint)
+                gather(rec.buf, slot=(eng._step - 1) % NS)
 
     def step_host(i):
         st = streams[eng._step % NS]
         eng.infer_host(host_xyz[i % HR], host_feat[i % HR], host_out[i % HR], stream=st)
         if world > 1:
             with torch.cuda.stream(st):
-                g = all_gather_records(eng.slots[(eng._step - 1) % len(eng.slots)].rec.buf, world)
-                merge_gathered(g, B, cfg.proposal.npoint)
+                gather(eng.slots[(eng._step - 1) % NS].rec.buf, slot=(eng._step - 1) % NS)
 
     def timed(step_fn, K, W):
         for i in range(W):

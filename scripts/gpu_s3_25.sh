@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+nvidia-smi -L | wc -l; nproc
+N=4
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --no-cpu-baseline > gpurun_out/bench_${N}gpu_s3.json 2> gpurun_out/bench_${N}gpu_s3.err
+echo "${N}gpu exit=$?"; grep -v "Warning\|^$\|\*\*\*\|OMP_NUM" gpurun_out/bench_${N}gpu_s3.err | tail -n 5
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_4gpu_s3.json').read().strip().splitlines()[-1])
+print('4 GPUs: value', round(d['value'],1), 'ms/step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), d['config']['parallelism'], 'enq', d['host_enqueue_ms_per_step'])
+PY

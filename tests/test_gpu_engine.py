@@ -68,6 +68,12 @@ def test_host_api_and_merge(cuda):
     n = int(cnt.item())
     assert np.array_equal(idx[:n].cpu().numpy(), merge_gathered_host(g, B, cfg.proposal.npoint))
     assert torch.equal(idx[:n], dev.nms_idx[:n]) and n == int(dev.nms_count.item())
+    # the pre-allocated gather + merge used by bench.py's loop gives the same list
+    from votenet_b200.dist import DetectionGather
+    dg = DetectionGather(1, B, cfg.proposal.npoint, cuda, slots=2)
+    i1, c1 = dg(dev.buf, slot=1)
+    torch.cuda.synchronize()
+    assert int(c1.item()) == n and torch.equal(i1[:n], idx[:n])
     # two fake ranks: the merged list interleaves both ranks by score with global batch ids
     g2 = torch.stack([dev.buf, dev.buf.clone()], 0)
     idx2, cnt2 = merge_gathered(g2, B, cfg.proposal.npoint)

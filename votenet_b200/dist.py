@@ -44,6 +44,37 @@ def merge_gathered(gathered, b, k):
     return idx, cnt
 
 
+class DetectionGather:
+    """Pre-allocated all-gather + merge for a stream of forwards (bench.py's hot loop): one gather buffer and one merged
+    index list per in-flight slot, record offsets resolved once — per step this is ONE collective and ONE kernel launch,
+    with no allocation, fill or Python-side view construction on the host path."""
+
+    def __init__(self, world, b, k, device, slots=1, group=None):
+        from ._lib import lib
+
+        self.world, self.b, self.k, self.group = world, b, k, group
+        lay = DetectionRecord(b, k, device="cpu")
+        self.nbytes = lay.nbytes
+        self.off_scores, self.off_keep = lay.offsets["scores"][0], lay.offsets["keep"][0]
+        self.gathered = [torch.empty((world, self.nbytes), dtype=torch.uint8, device=device) for _ in range(slots)]
+        self.idx = [torch.empty((world * b * k, 2), dtype=torch.int32, device=device) for _ in range(slots)]
+        self.cnt = [torch.zeros((1,), dtype=torch.int32, device=device) for _ in range(slots)]
+        self._merge = lib.vnb_merge_detections
+
+    def __call__(self, rec_buf, slot=0):
+        """rec_buf (nbytes,) uint8 of this rank -> (idx, count) of the whole batch; asynchronous on the current stream."""
+        from ._lib import check, dptr, stream_ptr
+
+        g = self.gathered[slot]
+        if self.world == 1:
+            g[0].copy_(rec_buf, non_blocking=True)
+        else:
+            dist.all_gather_into_tensor(g.view(-1), rec_buf, group=self.group)
+        check(self._merge(self.world, self.b, self.k, dptr(g), self.nbytes, self.off_scores, self.off_keep,
+                          dptr(self.idx[slot]), dptr(self.cnt[slot]), stream_ptr()))
+        return self.idx[slot], self.cnt[slot]
+
+
 def merge_gathered_host(gathered, b, k):
     """Host (numpy) statement of the same merge — used by the gloo tests and as the checker of the device merge."""
     g = gathered.cpu()
