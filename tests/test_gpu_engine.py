@@ -79,3 +79,26 @@ def test_host_api_and_merge(cuda):
     idx2, cnt2 = merge_gathered(g2, B, cfg.proposal.npoint)
     assert int(cnt2.item()) == 2 * n
     assert np.array_equal(idx2[: 2 * n].cpu().numpy(), merge_gathered_host(g2, B, cfg.proposal.npoint))
+
+
+def test_engine_reference_shapes_batch1(cuda):
+    """The reference's own shapes (config.py:1 POINT_NUM = 20480, xyz re-used as the 3 input features model.py:35-36,
+    evaluation batch 1, evaluator.py:222): the graph engine reproduces the readable forward bit for bit."""
+    from votenet_b200 import synth
+    from votenet_b200.config import VoteNetConfig
+    from votenet_b200.engine import Engine
+    from votenet_b200.model import VoteNetB200
+    from votenet_b200.weights import make_synthetic_weights
+
+    cfg = VoteNetConfig(num_points=20480, feature_dim=3)
+    w = make_synthetic_weights(cfg, 1)
+    net = VoteNetB200(cfg, w, device=cuda)
+    eng = Engine(cfg, w, 1, device=cuda, slots=2)
+    for it in range(3):
+        xyz = torch.as_tensor(synth.synthetic_batch(500 + it, 1, cfg.num_points), device=cuda)
+        ref = net.forward(xyz, xyz)
+        rec = eng.infer_device(xyz, xyz.clone())
+        torch.cuda.synchronize()
+        assert torch.equal(rec.bboxes, ref["dec_bboxes"]) and torch.equal(rec.keep, ref["nms_keep"])
+        n = int(ref["nms_count"].item())
+        assert int(rec.nms_count.item()) == n and torch.equal(rec.nms_idx[:n], ref["nms_idx"][:n])

@@ -5,7 +5,10 @@ Same graph as `model.VoteNetB200.forward` (reference: /root/reference/model.py:3
   * the forward is scheduled on three streams — the FPS chain depends on xyz only, ball queries
     and three_nn depend on xyz + centroids only, so both run beside the feature (MLP) chain and are joined by events;
   * the whole multi-stream forward is captured into one CUDA graph per slot;
-  * two slots (independent workspaces) let step i+1's sampling chain overlap step i's feature chain;
+  * `slots` independent workspaces (bench.py: 12) keep several forwards in flight: the sa1 FPS of a forward occupies
+    8 SMs for 1.5 ms, the other 140 SMs run the feature chains of earlier forwards (DESIGN.md §5);
+  * the nested sampling levels use the provenance hint of the sa1 FPS (no proof kernels when it was tie-free), the FP
+    modules and the voting module run as one fused tensor-core kernel per FP level;
   * detections are written straight into one contiguous record (the all-gather wire layout).
 """
 import ctypes as C
