@@ -232,7 +232,7 @@ def kernel_table(eng, cfg, peaks, flush):
         ms = t(lambda: check(lib.vnb_query_ball_point_ws(B, l.n, l.m, float(sa.radius), 64, dptr(src), dptr(l.xyz), dptr(l.idx),
                                                          dptr(l.cnt), dptr(l.bq_ws), sp())))
         hbm(f"ball_query_sa{li + 1}", ms, B * (l.n * 12 + l.m * 12 + l.m * 256 + l.m * 4), "latency-bound (compulsory bytes only)")
-        ms = t(lambda: eng._sa(li, src, feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, st, s.sa_ws))
+        ms = t(lambda: eng._sa(li, src, feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, st, s.sa_ws, l.cnt))
         tensor(f"sa{li + 1}_group_mlp_max", ms, mlp_flops(B * l.m * 64, 3 + c, sa.mlp))
         src, feat, c = l.xyz, l.feat, sa.mlp[-1]
     # feature propagation: three_nn + (interpolate/concat + 2 x (1x1 conv + BN + ReLU)); voting module
@@ -286,7 +286,7 @@ def kernel_table(eng, cfg, peaks, flush):
         check(lib.vnb_gather_point(B, ns, p.npoint, dptr(s.votes_xyz), dptr(s.p_fps), dptr(s.p_xyz), sp()))
         check(lib.vnb_query_ball_point(B, ns, p.npoint, float(p.radius), 64, dptr(s.votes_xyz), dptr(s.p_xyz), dptr(s.p_idx),
                                        dptr(s.p_cnt), sp()))
-        eng._sa(len(cfg.sa), s.votes_xyz, s.votes_feat, ns, cf, s.p_xyz, s.p_idx, p.npoint, s.p_q, s.p_feat, st, s.sa_ws)
+        eng._sa(len(cfg.sa), s.votes_xyz, s.votes_feat, ns, cf, s.p_xyz, s.p_idx, p.npoint, s.p_q, s.p_feat, st, s.sa_ws, s.p_cnt)
         x = s.p_feat
         for i in range(len(p.mlp2)):
             eng._linear(B * p.npoint, x, eng.store.layer(f"proposal/conv_post_{i}"), i < len(p.mlp2) - 1, s.p_h[i], None, st)

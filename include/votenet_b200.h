@@ -175,6 +175,17 @@ int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, const float* x
 /* workspace (optional, may be NULL): vnb_sa_workspace_bytes(b,m,nsample) bytes; the pipelined tensor-core kernel of the
  * hoisted variant needs it (grouped relative coordinates); without it the single-role kernel runs. */
 size_t vnb_sa_workspace_bytes(int b, int m, int nsample);
+/* Same, with the ball query's pts_cnt (b,m) i32 (NULL = unknown): query_ball_point pads a row of cnt < nsample hits with
+ * copies of its first hit (tf_grouping_g.cu:26-29), so only cnt rows of a group are distinct and the padded rows cannot
+ * change the max-pool.  The tensor-core kernels then run each centroid in a slot of 16, 32 or 64 rows (the smallest that
+ * holds its distinct rows) and pack 8 / 4 / 2 centroids into a 128-row MMA tile (csrc/sa_pack.cu) — bit-identical
+ * outputs, 26-56 % of the tiles on SUN-RGB-D-shaped clouds.  pts_cnt must be the count returned for `idx`. */
+int vnb_sa_group_mlp_max_counted(int b, int n, int c, int m, int nsample, const float* xyz, const float* feat,
+                                 const float* new_xyz, const int* idx, const int* pts_cnt, int c1, int c2, int c3,
+                                 const float* w1_f32, const float* b1, const float* w2_f32, const float* b2,
+                                 const float* w3_f32, const float* b3, const void* w1_img, const void* w2_img,
+                                 const void* w3_img, const void* q_f16, float* out, int precision, void* workspace,
+                                 void* stream);
 
 /* pointnet_fp_module front half: inverse-distance weights + three_interpolate + concat     utils.py:279-286
  * dist (b,n,3), idx (b,n,3) from vnb_three_nn; points2 (b,m,c2) known features; points1 (b,n,c1) skip features

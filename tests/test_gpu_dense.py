@@ -232,3 +232,50 @@ def test_sa_kernel_variants_agree(cuda):
         assert rel_err(outs[2].cpu().numpy(), outs[0].cpu().numpy()) < 2e-4
         for o in outs:
             assert rel_err(o.cpu().numpy(), ref.numpy()) < TOL_TC
+
+
+@pytest.mark.parametrize("b,n,m,c,mlp", [(8, 2048, 1024, 128, (128, 128, 256)), (3, 1024, 254, 256, (128, 128, 128)),
+                                         (4, 6000, 2048, 1, (64, 64, 128)), (1, 3000, 130, 3, (64, 64, 128)),
+                                         (2, 600, 6, 128, (128, 128, 256))])
+def test_sa_tile_packing_is_bit_identical(cuda, b, n, m, c, mlp):
+    """vnb_sa_group_mlp_max_counted: with the ball query's pts_cnt the fused kernels run centroids in 16 / 32 / 64-row
+    slots (csrc/sa_pack.cu) and skip the padded duplicate rows — outputs must equal the unpacked run bit for bit, for
+    every mix of slot classes (engineered counts: 0, 1, 16, 17, 32, 33, 64; ragged last tiles of every class) and also
+    match the oracle."""
+    from votenet_b200.utils import WeightStore, sa_group_mlp_max
+
+    rng = np.random.default_rng(b * 7 + m)
+    xyz = rng.random((b, n, 3), dtype=np.float32)
+    feat = rng.standard_normal((b, n, c)).astype(np.float32)
+    new_xyz = O.gather_point(xyz, O.farthest_point_sample(m, xyz))
+    # engineered groups with the reference's padding rule: cnt distinct neighbours, then the first one repeated
+    cnt = rng.choice(np.asarray([1, 5, 16, 17, 30, 32, 33, 50, 64], np.int32), size=(b, m))
+    cnt[0, :3] = (16, 32, 64)
+    full, full_cnt = O.query_ball_point(0.45, 64, xyz, new_xyz)   # big ball: (almost) every group has 64 real hits
+    cnt = np.minimum(cnt, full_cnt).astype(np.int32)
+    idx = full.copy()
+    for i in range(b):
+        for j in range(m):
+            idx[i, j, int(cnt[i, j]):] = full[i, j, 0]              # keep the first cnt hits, pad with the first one
+    g = torch.Generator().manual_seed(3)
+    w = {}
+    cin = 3 + c
+    for i, co in enumerate(mlp):
+        w[f"s/conv{i}/W"] = torch.randn(cin, co, generator=g) * (2.0 / cin) ** 0.5
+        w[f"s/conv{i}/b"] = torch.randn(co, generator=g) * 0.05
+        cin = co
+    store = WeightStore(w, device=cuda, precision=1)
+    layers = [store.layer(f"s/conv{i}") for i in range(3)]
+    args = (T(xyz, cuda), T(feat, cuda), T(new_xyz, cuda), T(idx, cuda), layers, 1, store, "s")
+    plain = sa_group_mlp_max(*args)
+    packed = sa_group_mlp_max(*args, pts_cnt=T(cnt, cuda))
+    cnt0 = cnt.copy(); cnt0[:, ::5] = 0            # "empty ball" entries keep the full 64-row slot
+    packed0 = sa_group_mlp_max(*args, pts_cnt=T(cnt0, cuda))
+    torch.cuda.synchronize()
+    assert torch.equal(plain, packed)
+    assert torch.equal(plain, packed0)
+    grouped = np.concatenate([O.group_point(xyz, idx) - new_xyz[:, :, None, :], O.group_point(feat, idx)], -1)
+    h = torch.as_tensor(grouped)
+    for i in range(3):
+        h = D.dense_layer(h, w, f"s/conv{i}")
+    assert rel_err(packed.cpu().numpy(), h.max(dim=2).values.numpy()) < TOL_TC

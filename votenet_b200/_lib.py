@@ -47,6 +47,7 @@ _SIGS = {
     "vnb_pack_weight_f16": ([_i, _i, _p, _p, _p], _i),
     "vnb_linear": ([_i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _i, _p], _i),
     "vnb_sa_group_mlp_max": ([_i] * 5 + [_p] * 4 + [_i] * 3 + [_p] * 11 + [_i, _p, _p], _i),
+    "vnb_sa_group_mlp_max_counted": ([_i] * 5 + [_p] * 5 + [_i] * 3 + [_p] * 11 + [_i, _p, _p], _i),
     "vnb_sa_workspace_bytes": ([_i, _i, _i], _sz),
     "vnb_fp_interpolate_concat": ([_i] * 5 + [_p] * 6, _i),
     "vnb_fp_module_fused": ([_i] * 5 + [_p] * 4 + [_i] + [_p] * 4 + [_i] + [_p] * 8, _i),

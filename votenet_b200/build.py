@@ -28,6 +28,7 @@ SOURCES = {
     "mlp_tc.cu": [],
     "sa_ws.cu": [],
     "sa_ws2.cu": [],
+    "sa_pack.cu": [],
     "sa1_ws.cu": [],
     "sa1_ws2.cu": [],
     "linear_tc.cu": [],

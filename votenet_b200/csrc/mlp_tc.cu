@@ -33,10 +33,12 @@ int sa_ws_dispatch(int b, int n, int m, const float* xyz, const float* new_xyz, 
 int sa1_ws_dispatch(int b, int n, int c, int m, const float* xyz, const float* feat, const float* new_xyz, const int* idx,
                     int c1, int c2, int c3, const float* b1, const float* b2, const float* b3, const void* w1_img,
                     const void* w2_img, const void* w3_img, float* out, void* workspace, cudaStream_t st);
-int sa_ws2_dispatch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, int c1, int c2, int c3,
+int sa_ws2_dispatch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, const int* pts_cnt, int c1,
+                    int c2, int c3,
                     const float* w1x, const float* b2, const float* b3, const void* w2_img, const void* w3_img,
                     const void* q, float* out, void* workspace, cudaStream_t st);  // sa_ws2.cu
 int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* feat, const float* new_xyz, const int* idx,
+                     const int* pts_cnt,
                      int c1, int c2, int c3, const float* b1, const float* b2, const float* b3, const void* w1_img,
                      const void* w2_img, const void* w3_img, float* out, void* workspace, cudaStream_t st);  // sa1_ws2.cu
 int linear_tc(int rows, int cin, int cout, const float* in, const void* w_img, const float* bias, const float* res,
@@ -344,9 +346,14 @@ static int launch_sa_tc(int b, int n, int c, int m, const float* xyz, const floa
 
 using namespace vnb;
 
+namespace vnb {
+size_t sa_rel_bytes(long long rows);              // sa_pack.cu
+size_t sa_tile_table_bytes(int total_centroids);  // sa_pack.cu
+}  // namespace vnb
+
 extern "C" size_t vnb_sa_workspace_bytes(int b, int m, int nsample) {
   if (b <= 0 || m <= 0 || nsample <= 0) return 256;
-  return (size_t)b * m * nsample * 16;
+  return sa_rel_bytes((long long)b * m * nsample) + sa_tile_table_bytes(b * m);  // rel table | tile header | tile table
 }
 
 extern "C" size_t vnb_weight_image_bytes(int cin, int cout) {
@@ -382,11 +389,28 @@ extern "C" int vnb_linear(int rows, int cin, int cout, const float* in, const fl
   return linear_tc(rows, cin, cout, in, w_img, bias, residual, act, out_f32, out_f16, st);
 }
 
+extern "C" int vnb_sa_group_mlp_max_counted(int b, int n, int c, int m, int nsample, const float* xyz, const float* feat,
+                                            const float* new_xyz, const int* idx, const int* pts_cnt, int c1, int c2, int c3,
+                                            const float* w1_f32, const float* b1, const float* w2_f32, const float* b2,
+                                            const float* w3_f32, const float* b3, const void* w1_img, const void* w2_img,
+                                            const void* w3_img, const void* q_f16, float* out, int precision,
+                                            void* workspace, void* stream);
+
 extern "C" int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, const float* xyz, const float* feat,
                                     const float* new_xyz, const int* idx, int c1, int c2, int c3, const float* w1_f32,
                                     const float* b1, const float* w2_f32, const float* b2, const float* w3_f32,
                                     const float* b3, const void* w1_img, const void* w2_img, const void* w3_img,
                                     const void* q_f16, float* out, int precision, void* workspace, void* stream) {
+  return vnb_sa_group_mlp_max_counted(b, n, c, m, nsample, xyz, feat, new_xyz, idx, nullptr, c1, c2, c3, w1_f32, b1, w2_f32,
+                                      b2, w3_f32, b3, w1_img, w2_img, w3_img, q_f16, out, precision, workspace, stream);
+}
+
+extern "C" int vnb_sa_group_mlp_max_counted(int b, int n, int c, int m, int nsample, const float* xyz, const float* feat,
+                                            const float* new_xyz, const int* idx, const int* pts_cnt, int c1, int c2, int c3,
+                                            const float* w1_f32, const float* b1, const float* w2_f32, const float* b2,
+                                            const float* w3_f32, const float* b3, const void* w1_img, const void* w2_img,
+                                            const void* w3_img, const void* q_f16, float* out, int precision,
+                                            void* workspace, void* stream) {
   VNB_REQUIRE(nsample == 64, "sa_group_mlp_max: nsample must be 64 (got %d)", nsample);
   VNB_REQUIRE(b >= 0 && n > 0 && c >= 0 && m >= 0 && c1 > 0 && c2 > 0 && c3 > 0, "sa_group_mlp_max: bad shape");
   if (b == 0 || m == 0) return VNB_OK;
@@ -402,7 +426,7 @@ extern "C" int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, con
   if (!hoist) {
     VNB_REQUIRE(w1_img != nullptr, "sa_group_mlp_max(tensor cores): w1_img missing");
     if (g_sa_variant >= 2) {  // second-generation pipeline (sa1_ws2.cu)
-      int rc = sa1_ws2_dispatch(b, n, c, m, xyz, feat, new_xyz, idx, c1, c2, c3, b1, b2, b3, w1_img, w2_img, w3_img, out,
+      int rc = sa1_ws2_dispatch(b, n, c, m, xyz, feat, new_xyz, idx, pts_cnt, c1, c2, c3, b1, b2, b3, w1_img, w2_img, w3_img, out,
                                 workspace, st);
       if (rc >= 0) return rc;
     }
@@ -418,7 +442,7 @@ extern "C" int vnb_sa_group_mlp_max(int b, int n, int c, int m, int nsample, con
     VNB_REQUIRE(q_f16 != nullptr && w1_f32 != nullptr,
                 "sa_group_mlp_max(tensor cores): hoisted layer 1 needs q_f16 and w1_f32 (rows 0..2)");
     if (g_sa_variant >= 2) {  // second-generation pipeline (sa_ws2.cu)
-      int rc = sa_ws2_dispatch(b, n, m, xyz, new_xyz, idx, c1, c2, c3, w1_f32, b2, b3, w2_img, w3_img, q_f16, out, workspace, st);
+      int rc = sa_ws2_dispatch(b, n, m, xyz, new_xyz, idx, pts_cnt, c1, c2, c3, w1_f32, b2, b3, w2_img, w3_img, q_f16, out, workspace, st);
       if (rc >= 0) return rc;
     }
     if (g_sa_variant >= 1) {  // warp-specialised, pipelined kernel (sa_ws.cu)

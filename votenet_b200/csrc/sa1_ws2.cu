@@ -69,7 +69,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_centroids, int tiles_per_cta,
+__global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* __restrict__ hdr,
+                                                             const int* __restrict__ tile_cid,
                                                              const float4* __restrict__ rel,
                                                              const float* __restrict__ feat,
                                                              const float* __restrict__ b1, const float* __restrict__ b2,
@@ -109,6 +110,14 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 36);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // tile table written by sa_pack_tiles_kernel (sa_pack.cu): tiles of 2 x 64-row, then 4 x 32-row, then 8 x 16-row slots
+  const int ntiles = __ldg(hdr), t64 = __ldg(hdr + 1), t32 = __ldg(hdr + 2);
+  const int tiles_per_cta = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int first_tile = (int)blockIdx.x * tiles_per_cta;
+  const int my_tiles = max(0, min(tiles_per_cta, ntiles - first_tile));
+  auto shift_of = [&](int tile) { return tile < t64 ? 6 : (tile < t64 + t32 ? 5 : 4); };  // log2(rows per slot)
+  if (my_tiles == 0) return;  // whole CTA, before any barrier / TMEM / bulk copy exists
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
@@ -160,9 +169,6 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_ptr;
 
-  const int ntiles = total_centroids / 2;
-  const int first_tile = (int)blockIdx.x * tiles_per_cta;
-  const int my_tiles = max(0, min(tiles_per_cta, ntiles - first_tile));
   // use number t>>1 of a [2]-slotted barrier -> parity (t>>1)&1; use number t>>2 of an [NH]-slotted one -> (t>>2)&1
   auto par_of = [](int t) { return (uint32_t)((t >> 1) & 1); };
   auto par4 = [](int t) { return (uint32_t)((t >> 2) & 1); };
@@ -170,19 +176,24 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
   if (warp >= 24 && warp < 28) {
     // ================================================================ PRODUCER: one grouped row per thread
     const int pt = tid - 768;
-    const float4* rp = rel + (size_t)first_tile * 128 + pt;
+    // tile row pt = sample (pt mod slot) of the centroid in slot (pt / slot); empty slots read row 0 (discarded later)
+    auto cid_of = [&](int tile) { return __ldg(tile_cid + (size_t)tile * 8 + (pt >> shift_of(tile))); };
+    auto src_row = [&](int tile, int cid) {
+      return cid < 0 ? (size_t)0 : (size_t)cid * 64 + (size_t)(pt & ((1 << shift_of(tile)) - 1));
+    };
     if (c <= 4) {
       // Narrow features (VoteNet: c = 1 height or c = 3 xyz).  The producer's work per tile is ~150 cycles, but every
-      // value it needs is two DEPENDENT global loads away (table row -> feature row): with a one-tile look-ahead the
-      // whole pipeline ran at one memory latency (~900 cycles) per tile (vnb_debug_sa_trace).  Here table rows are
-      // requested FOUR tiles ahead and feature rows TWO tiles ahead (address from the row requested two tiles
-      // earlier), so each load has two tile periods to land; 28 registers of look-ahead state.
+      // value it needs is a chain of DEPENDENT global loads away (tile table -> table row -> feature row): centroid ids
+      // are requested FIVE tiles ahead, table rows FOUR and feature rows TWO, so each load has at least a tile period
+      // (usually two) to land; ~30 registers of look-ahead state.
       float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, r3 = r0;   // table rows of tiles t .. t+3
       float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4];  // features of tiles t, t+1 (, t+2)
-      if (my_tiles > 0) r0 = __ldg(rp);
-      if (my_tiles > 1) r1 = __ldg(rp + 128);
-      if (my_tiles > 2) r2 = __ldg(rp + 256);
-      if (my_tiles > 3) r3 = __ldg(rp + 384);
+      int c4 = -1;                                                              // centroid of this row in tile t+4
+      if (my_tiles > 0) r0 = __ldg(rel + src_row(first_tile, cid_of(first_tile)));
+      if (my_tiles > 1) r1 = __ldg(rel + src_row(first_tile + 1, cid_of(first_tile + 1)));
+      if (my_tiles > 2) r2 = __ldg(rel + src_row(first_tile + 2, cid_of(first_tile + 2)));
+      if (my_tiles > 3) r3 = __ldg(rel + src_row(first_tile + 3, cid_of(first_tile + 3)));
+      if (my_tiles > 4) c4 = cid_of(first_tile + 4);
       auto load_feat = [&](const float4& r, float (&f)[4]) {
         const float* fp = feat + (size_t)__float_as_int(r.w) * c;
 #pragma unroll
@@ -193,7 +204,8 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t & 1;
         float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t + 4 < my_tiles) r4 = __ldg(rp + (size_t)(t + 4) * 128);
+        if (t + 4 < my_tiles) r4 = __ldg(rel + src_row(first_tile + t + 4, c4));
+        if (t + 5 < my_tiles) c4 = cid_of(first_tile + t + 5);
 #pragma unroll
         for (int i = 0; i < 4; ++i) f2[i] = 0.f;
         if (t + 2 < my_tiles) load_feat(r2, f2);
@@ -213,8 +225,8 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
       }
     } else {
     float4 r_cur = make_float4(0.f, 0.f, 0.f, 0.f), r_nxt = r_cur;   // table rows of tiles t, t+1
-    if (my_tiles > 0) r_cur = __ldg(rp);
-    if (my_tiles > 1) r_nxt = __ldg(rp + 128);
+    if (my_tiles > 0) r_cur = __ldg(rel + src_row(first_tile, cid_of(first_tile)));
+    if (my_tiles > 1) r_nxt = __ldg(rel + src_row(first_tile + 1, cid_of(first_tile + 1)));
     float f_cur[11], f_nxt[11];
 #pragma unroll
     for (int i = 0; i < 11; ++i) f_cur[i] = f_nxt[i] = 0.f;
@@ -234,7 +246,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
         for (int i = 0; i < 11; ++i)
           if (i < c) f_nxt[i] = __ldg(f + i);
       }
-      if (t + 2 < my_tiles) r_nn = __ldg(rp + (size_t)(t + 2) * 128);
+      if (t + 2 < my_tiles) r_nn = __ldg(rel + src_row(first_tile + t + 2, cid_of(first_tile + t + 2)));
       if (t >= 2) mbar_wait(&m1_done[s], par_of(t - 2));  // M1(t-2) finished reading A0[s]
       if (warp == 24) { S1_STAMP(0, t, 0) }
       uint8_t* a0 = sA0 + s * A0_BYTES;
@@ -370,12 +382,18 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
     const float bias3 = sB3[ch];
     for (int t = s; t < my_tiles; t += 2) {
       const int tile = first_tile + t;
+      const int shift = shift_of(tile);
       mbar_wait(&m3_done[t & 3], par4(t));
       tc_fence_after_sync();
       if (q == 0) { S1_STAMP(6 + s, t, 0) }
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // four independent chains
+        // centroids whose samples sit in this half of the tile: one (64-row slots), two (32) or four (16)
+        int cid[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          cid[k] = __ldg(tile_cid + (size_t)tile * 8 + (shift == 6 ? g : (shift == 5 ? 2 * g + (k & 1) : 4 * g + k)));
+        float mb[4];  // maxima of the four 16-column blocks of this half of the tile
         // 16-column loads: ptxas hoists the next load over the current reduction, and two x32 loads do not fit the
         // 64-register budget of this 992-thread CTA (it spilled a whole load)
 #pragma unroll
@@ -387,16 +405,25 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, int total_ce
             tc_fence_before_sync();
             mbar_arrive(&d3_empty[s]);  // D3[s] has been read
           }
-#pragma unroll
-          for (int i = 0; i < 16; i += 8) {
-            m0 = fmaxf(fmaxf(m0, __uint_as_float(v[i])), __uint_as_float(v[i + 4]));
-            m1 = fmaxf(fmaxf(m1, __uint_as_float(v[i + 1])), __uint_as_float(v[i + 5]));
-            m2 = fmaxf(fmaxf(m2, __uint_as_float(v[i + 2])), __uint_as_float(v[i + 6]));
-            m3 = fmaxf(fmaxf(m3, __uint_as_float(v[i + 3])), __uint_as_float(v[i + 7]));
-          }
+          float a0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[4])), a1 = fmaxf(__uint_as_float(v[1]), __uint_as_float(v[5]));
+          float a2 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[6])), a3 = fmaxf(__uint_as_float(v[3]), __uint_as_float(v[7]));
+          a0 = fmaxf(fmaxf(a0, __uint_as_float(v[8])), __uint_as_float(v[12]));
+          a1 = fmaxf(fmaxf(a1, __uint_as_float(v[9])), __uint_as_float(v[13]));
+          a2 = fmaxf(fmaxf(a2, __uint_as_float(v[10])), __uint_as_float(v[14]));
+          a3 = fmaxf(fmaxf(a3, __uint_as_float(v[11])), __uint_as_float(v[15]));
+          mb[qq] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
         }
-        const float mval = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        out[((size_t)tile * 2 + g) * C3 + ch] = fmaxf(mval + bias3, 0.f);  // bias + ReLU commute with the max
+        // bias + ReLU commute with the max
+        if (shift == 6) {
+          if (cid[0] >= 0) out[(size_t)cid[0] * C3 + ch] = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])) + bias3, 0.f);
+        } else if (shift == 5) {
+          if (cid[0] >= 0) out[(size_t)cid[0] * C3 + ch] = fmaxf(fmaxf(mb[0], mb[1]) + bias3, 0.f);
+          if (cid[1] >= 0) out[(size_t)cid[1] * C3 + ch] = fmaxf(fmaxf(mb[2], mb[3]) + bias3, 0.f);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (cid[k] >= 0) out[(size_t)cid[k] * C3 + ch] = fmaxf(mb[k] + bias3, 0.f);
+        }
       }
       if (q == 0) { S1_STAMP(6 + s, t, 1) }
     }
@@ -413,12 +440,14 @@ extern int g_sa_variant;  // mlp_tc.cu
 long long* g_sa_trace = nullptr;  // debugging: device buffer of 12 x 64 x 2 int64 (vnb_debug_sa_trace)
 
 extern int g_sa_sms, g_sa_split;  // mlp_tc.cu
+size_t sa_rel_bytes(long long rows);                                                                  // sa_pack.cu
+int launch_sa_pack(int total_centroids, const int* pts_cnt, int* hdr, int* tile_cid, cudaStream_t st);  // sa_pack.cu
 void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx, void* rel,
                       cudaStream_t st);  // sa_ws.cu
 
 // returns -1 when no instance matches
 int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* feat, const float* new_xyz, const int* idx,
-                     int c1, int c2, int c3, const float* b1, const float* b2, const float* b3, const void* w1_img,
+                     const int* pts_cnt, int c1, int c2, int c3, const float* b1, const float* b2, const float* b3, const void* w1_img,
                      const void* w2_img, const void* w3_img, float* out, void* workspace, cudaStream_t st) {
   if (workspace == nullptr || !(c1 == 64 && c2 == 64 && c3 == 128) || c > 11) return -1;  // k = 14, 15 carry the bias
   auto kern = s1v2::sa1_ws2_kernel;
@@ -429,12 +458,14 @@ int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* 
   const long long rows = (long long)b * m * 64;
   launch_group_rel(n, m, rows, xyz, new_xyz, idx, workspace, st);
   if (int rc = check_launch("sa_group_mlp_max: grouped relative coordinates")) return rc;
-  const int ntiles = b * m / 2;
+  int* hdr = reinterpret_cast<int*>(static_cast<char*>(workspace) + sa_rel_bytes(rows));
+  int* tile_cid = hdr + 64;
+  if (int rc = launch_sa_pack(b * m, pts_cnt, hdr, tile_cid, st)) return rc;
   if (g_sa_sms > 0 && g_sa_sms < sms) sms = g_sa_sms;  // leave room for concurrently running FPS CTAs
   sms *= g_sa_split;
-  const int tpc = (ntiles + sms - 1) / sms;          // one wave: one CTA per SM, contiguous chunks
-  const int grid = (ntiles + tpc - 1) / tpc;
-  kern<<<grid, s1v2::THREADS, s1v2::SMEM, st>>>(c, b * m, tpc, static_cast<const float4*>(workspace), feat, b1, b2, b3,
+  const int cap = b * m / 2 + 3;
+  const int grid = sms < cap ? sms : cap;             // one wave: contiguous chunks of the (device-side) tile count
+  kern<<<grid, s1v2::THREADS, s1v2::SMEM, st>>>(c, hdr, tile_cid, static_cast<const float4*>(workspace), feat, b1, b2, b3,
                                                 static_cast<const char*>(w1_img), static_cast<const char*>(w2_img),
                                                 static_cast<const char*>(w3_img), out, g_sa_trace, g_sa_variant == 3 ? 1 : 0);  // MMA issuers park (default) or poll (sa_variant 3)
   return check_launch("sa_group_mlp_max (tcgen05, warp-specialised v2, narrow input)");

@@ -1,0 +1,84 @@
+// Tile packing for the fused SA kernels: skip the ball query's padding rows.
+//
+// query_ball_point pads a row of fewer than nsample hits with copies of its FIRST hit (tf_grouping_g.cu:26-29), so a
+// centroid with cnt hits contributes only cnt distinct grouped rows; the other 64 - cnt rows repeat row 0, produce the
+// same activations and cannot change the max-pool (utils.py:132).  On SUN-RGB-D-shaped clouds the mean count is 25 / 11
+// / 23 / 26 of 64 at the four levels.  The fused kernels therefore run centroids in SLOTS of 16, 32 or 64 rows — the
+// smallest that holds all of a centroid's distinct rows — and a 128-row MMA tile carries 8, 4 or 2 centroids of one
+// slot size.  This kernel classifies the centroids by pts_cnt and writes the tile table:
+//   hdr[0] = total tiles, hdr[1] = tiles of 64-row slots (first), hdr[2] = tiles of 32-row slots (next); the rest are 16s
+//   tile_cid[t*8 + g] = centroid (flat b*m index) in slot g of tile t, -1 = empty slot
+// Per-row results do not depend on which tile a row sits in, so the outputs are bit-identical to the unpacked kernels.
+// cnt == 0 (empty ball, rows never written by the reference) and pts_cnt == NULL keep the full 64-row slot.
+// One CTA: counts -> block scan -> ordered placement (deterministic table).
+#include "common.cuh"
+
+namespace vnb {
+
+constexpr int PK_T = 1024;
+
+__device__ __forceinline__ int slot_class(int c) { return (c <= 0 || c > 32) ? 0 : (c > 16 ? 1 : 2); }  // 0: 64, 1: 32, 2: 16
+
+__global__ void __launch_bounds__(PK_T) sa_pack_tiles_kernel(int total, const int* __restrict__ cnt, int* __restrict__ hdr,
+                                                             int* __restrict__ tile_cid) {
+  __shared__ int s_w[3][PK_T / 32];
+  __shared__ int s_tot[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (total + PK_T - 1) / PK_T;
+  const int i0 = tid * per, i1 = min(total, i0 + per);
+  int c[3] = {0, 0, 0};
+  for (int i = i0; i < i1; ++i) ++c[cnt ? slot_class(cnt[i]) : 0];
+  int base[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {  // block-wide exclusive scan of c[k]
+    int inc = c[k];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_w[k][warp] = inc;
+    base[k] = inc - c[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int v = s_w[k][lane];
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      s_w[k][lane] = inc - v;
+      if (lane == 31) s_tot[k] = inc;
+    }
+  }
+  __syncthreads();
+  const int n64 = s_tot[0], n32 = s_tot[1], n16 = s_tot[2];
+  const int t64 = (n64 + 1) >> 1, t32 = (n32 + 3) >> 2, t16 = (n16 + 7) >> 3;
+  if (tid == 0) { hdr[0] = t64 + t32 + t16; hdr[1] = t64; hdr[2] = t32; hdr[3] = 0; }
+  int p[3] = {base[0] + s_w[0][warp], base[1] + s_w[1][warp], base[2] + s_w[2][warp]};
+  for (int i = i0; i < i1; ++i) {
+    const int k = cnt ? slot_class(cnt[i]) : 0;
+    const int q = p[k]++;
+    int slot;
+    if (k == 0) slot = (q >> 1) * 8 + (q & 1);
+    else if (k == 1) slot = (t64 + (q >> 2)) * 8 + (q & 3);
+    else slot = (t64 + t32 + (q >> 3)) * 8 + (q & 7);
+    tile_cid[slot] = i;
+  }
+}
+
+// workspace layout of the fused SA path: [rel: rows * 16 B][hdr: 256 B][tile_cid: (total/2 + 4) * 32 B]
+size_t sa_rel_bytes(long long rows) { return ((size_t)rows * 16 + 255) / 256 * 256; }
+size_t sa_tile_table_bytes(int total_centroids) { return 256 + ((size_t)total_centroids / 2 + 4) * 32; }
+
+int launch_sa_pack(int total_centroids, const int* pts_cnt, int* hdr, int* tile_cid, cudaStream_t st) {
+  VNB_CUDA(cudaMemsetAsync(tile_cid, 0xFF, ((size_t)total_centroids / 2 + 4) * 32, st));  // every slot empty (-1)
+  sa_pack_tiles_kernel<<<1, PK_T, 0, st>>>(total_centroids, pts_cnt, hdr, tile_cid);
+  return check_launch("sa_group_mlp_max: tile packing");
+}
+
+}  // namespace vnb

@@ -71,7 +71,8 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 }
 
 template <int C1, int C2, int C3>
-__global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids, int tiles_per_cta,
+__global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restrict__ hdr,
+                                                            const int* __restrict__ tile_cid,
                                                             const float4* __restrict__ rel,
                                                             const float* __restrict__ w1x /* (3,C1) */,
                                                             const float* __restrict__ b2, const float* __restrict__ b3,
@@ -102,15 +103,25 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  // tile table written by sa_pack_tiles_kernel (sa_pack.cu): tiles of 2 x 64-row, then 4 x 32-row, then 8 x 16-row slots
+  const int ntiles = __ldg(hdr), t64 = __ldg(hdr + 1), t32 = __ldg(hdr + 2);
+  const int tiles_per_cta = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int first_tile = (int)blockIdx.x * tiles_per_cta;
+  const int my_tiles = max(0, min(tiles_per_cta, ntiles - first_tile));
+  auto shift_of = [&](int tile) { return tile < t64 ? 6 : (tile < t64 + t32 ? 5 : 4); };  // log2(rows per slot)
+  if (my_tiles == 0) return;  // whole CTA, before any barrier / TMEM / bulk copy exists
+
   if (tid == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&h1_full[s], PRODUCERS); mbar_init(&m2_done[s], 1); mbar_init(&d2_empty[s], 128); }
     for (int c = 0; c < NCH; ++c) { mbar_init(&h2c_full[c], 128); mbar_init(&m3c_done[c], 1); }
     mbar_init(d3_empty, 256);
     fence_barrier_init();
-    mbar_arrive_expect_tx(bar_w, (uint32_t)(K::W2_BYTES + K::W3_BYTES));
-    bulk_g2s(sW2, w2_img, K::W2_BYTES, bar_w);
-    bulk_g2s(sW3, w3_img, K::W3_BYTES, bar_w);
+    if (my_tiles > 0) {  // a CTA without tiles must not leave a bulk copy in flight when it exits
+      mbar_arrive_expect_tx(bar_w, (uint32_t)(K::W2_BYTES + K::W3_BYTES));
+      bulk_g2s(sW2, w2_img, K::W2_BYTES, bar_w);
+      bulk_g2s(sW3, w3_img, K::W3_BYTES, bar_w);
+    }
   }
   for (int i = tid; i < C2; i += THREADS) sB2[i] = b2[i];
   for (int i = tid; i < C3; i += THREADS) sB3[i] = b3[i];
@@ -119,10 +130,6 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_ptr;
-
-  const int ntiles = total_centroids / 2;
-  const int first_tile = (int)blockIdx.x * tiles_per_cta;
-  const int my_tiles = max(0, min(tiles_per_cta, ntiles - first_tile));
 
   if (warp >= 12 && warp < 20) {
     // ================================================================ PRODUCER (256 threads)
@@ -136,14 +143,22 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
       wy[i] = make_float2(w1x[C1 + chunk * 8 + 2 * i], w1x[C1 + chunk * 8 + 2 * i + 1]);
       wz[i] = make_float2(w1x[2 * C1 + chunk * 8 + 2 * i], w1x[2 * C1 + chunk * 8 + 2 * i + 1]);
     }
+    // tile row pt = sample (pt mod slot) of the centroid in slot (pt / slot); empty slots read row 0 (discarded later)
+    auto cid_of = [&](int tile) { return __ldg(tile_cid + (size_t)tile * 8 + (pt >> shift_of(tile))); };
+    auto src_row = [&](int tile, int cid) {
+      return cid < 0 ? (size_t)0 : (size_t)cid * 64 + (size_t)(pt & ((1 << shift_of(tile)) - 1));
+    };
     float4 relreg = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pt < 128 && my_tiles > 0) relreg = __ldg(rel + (size_t)first_tile * 128 + pt);
+    int cid_nxt = -1;  // centroid of this row in tile t+1 (requested one tile before its table row)
+    if (pt < 128 && my_tiles > 0) relreg = __ldg(rel + src_row(first_tile, cid_of(first_tile)));
+    if (pt < 128 && my_tiles > 1) cid_nxt = cid_of(first_tile + 1);
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = first_tile + t;
       const int s = t & 1;
       if (pt < 128) {
         sRel[s * 128 + pt] = relreg;                                                    // this tile
-        if (t + 1 < my_tiles) relreg = __ldg(rel + (size_t)(tile + 1) * 128 + pt);      // prefetch the next
+        if (t + 1 < my_tiles) relreg = __ldg(rel + src_row(tile + 1, cid_nxt));         // prefetch the next
+        if (t + 2 < my_tiles) cid_nxt = cid_of(tile + 2);
       }
       named_bar(1, PRODUCERS);  // sRel[s] visible; its previous readers (tile t-2) passed the barrier of tile t-1
       const float4* srel = sRel + s * 128;
@@ -281,6 +296,14 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
     for (int hh = 0; hh < C3 / 128; ++hh) bias3[hh] = sB3[hh * 128 + qd * 32 + lane];
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = first_tile + t;
+      const int shift = shift_of(tile);
+      // centroids whose samples sit in this warp's 64 columns: one (64-row slots), two (32) or four (16)
+      int cid[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int slot = shift == 6 ? g : (shift == 5 ? 2 * g + (k >> 1) : 4 * g + k);
+        cid[k] = __ldg(tile_cid + (size_t)tile * 8 + slot);
+      }
       mbar_wait(&m3c_done[NCH - 1], (uint32_t)(t & 1));  // the last chunk's commit == D3(t) complete
       tc_fence_after_sync();
 #pragma unroll
@@ -293,17 +316,31 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
           tc_fence_before_sync();
           mbar_arrive(d3_empty);  // D3 has been read: free for M3(t+1)
         }
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // four independent chains
+        float mb[4];  // maxima of the four 16-column blocks (independent chains)
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          m0 = fmaxf(fmaxf(m0, __uint_as_float(v[0][i])), __uint_as_float(v[1][i]));
-          m1 = fmaxf(fmaxf(m1, __uint_as_float(v[0][i + 1])), __uint_as_float(v[1][i + 1]));
-          m2 = fmaxf(fmaxf(m2, __uint_as_float(v[0][i + 2])), __uint_as_float(v[1][i + 2]));
-          m3 = fmaxf(fmaxf(m3, __uint_as_float(v[0][i + 3])), __uint_as_float(v[1][i + 3]));
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t* vv = &v[k >> 1][(k & 1) * 16];
+          float a0 = __uint_as_float(vv[0]), a1 = __uint_as_float(vv[1]), a2 = __uint_as_float(vv[2]), a3 = __uint_as_float(vv[3]);
+#pragma unroll
+          for (int i = 4; i < 16; i += 4) {
+            a0 = fmaxf(a0, __uint_as_float(vv[i])); a1 = fmaxf(a1, __uint_as_float(vv[i + 1]));
+            a2 = fmaxf(a2, __uint_as_float(vv[i + 2])); a3 = fmaxf(a3, __uint_as_float(vv[i + 3]));
+          }
+          mb[k] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
         }
-        const float mval = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        if (shift == 6) {
+          mb[0] = fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3]));
+        } else if (shift == 5) {
+          mb[0] = fmaxf(mb[0], mb[1]);
+          mb[2] = fmaxf(mb[2], mb[3]);
+        }
         // bias + ReLU commute with the max (both monotone)
-        out[((size_t)tile * 2 + g) * C3 + hh * 128 + qd * 32 + lane] = fmaxf(mval + bias3[hh], 0.f);
+        const int ch = hh * 128 + qd * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool emit = shift == 6 ? k == 0 : (shift == 5 ? (k & 1) == 0 : true);
+          if (emit && cid[k] >= 0) out[(size_t)cid[k] * C3 + ch] = fmaxf(mb[k] + bias3[hh], 0.f);
+        }
       }
     }
   }
@@ -315,11 +352,14 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(int total_centroids,
 }  // namespace s2v2
 
 extern int g_sa_sms, g_sa_split;  // mlp_tc.cu
+size_t sa_rel_bytes(long long rows);                                                                  // sa_pack.cu
+int launch_sa_pack(int total_centroids, const int* pts_cnt, int* hdr, int* tile_cid, cudaStream_t st);  // sa_pack.cu
 void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx, void* rel,
                       cudaStream_t st);  // sa_ws.cu
 
 template <int C1, int C2, int C3>
-static int s2v2_launch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, const float* w1x,
+static int s2v2_launch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, const int* pts_cnt,
+                       const float* w1x,
                        const float* b2, const float* b3, const void* w2_img, const void* w3_img, const void* q, float* out,
                        void* workspace, cudaStream_t st) {
   using K = s2v2::Cfg<C1, C2, C3>;
@@ -328,29 +368,32 @@ static int s2v2_launch(int b, int n, int m, const float* xyz, const float* new_x
   int dev = 0, sms = 148;
   VNB_CUDA(cudaGetDevice(&dev));
   VNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int ntiles = b * m / 2;
   const long long rows = (long long)b * m * 64;
   launch_group_rel(n, m, rows, xyz, new_xyz, idx, workspace, st);
   if (int rc = check_launch("sa_group_mlp_max: grouped relative coordinates")) return rc;
+  int* hdr = reinterpret_cast<int*>(static_cast<char*>(workspace) + sa_rel_bytes(rows));
+  int* tile_cid = hdr + 64;
+  if (int rc = launch_sa_pack(b * m, pts_cnt, hdr, tile_cid, st)) return rc;
   if (g_sa_sms > 0 && g_sa_sms < sms) sms = g_sa_sms;  // leave room for concurrently running FPS CTAs
   sms *= g_sa_split;
-  const int tpc = (ntiles + sms - 1) / sms;          // one wave: one CTA per SM, contiguous chunks
-  const int grid = (ntiles + tpc - 1) / tpc;
-  kern<<<grid, s2v2::THREADS, K::SMEM, st>>>(b * m, tpc, static_cast<const float4*>(workspace), w1x, b2, b3,
+  const int cap = b * m / 2 + 3;
+  const int grid = sms < cap ? sms : cap;             // one wave: contiguous chunks of the (device-side) tile count
+  kern<<<grid, s2v2::THREADS, K::SMEM, st>>>(hdr, tile_cid, static_cast<const float4*>(workspace), w1x, b2, b3,
                                              static_cast<const char*>(w2_img), static_cast<const char*>(w3_img),
                                              static_cast<const __half*>(q), out);
   return check_launch("sa_group_mlp_max (tcgen05, warp-specialised v2)");
 }
 
 // returns -1 when no instance matches
-int sa_ws2_dispatch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, int c1, int c2, int c3,
+int sa_ws2_dispatch(int b, int n, int m, const float* xyz, const float* new_xyz, const int* idx, const int* pts_cnt,
+                    int c1, int c2, int c3,
                     const float* w1x, const float* b2, const float* b3, const void* w2_img, const void* w3_img,
                     const void* q, float* out, void* workspace, cudaStream_t st) {
   if (workspace == nullptr) return -1;
   if (c1 == 128 && c2 == 128 && c3 == 256)
-    return s2v2_launch<128, 128, 256>(b, n, m, xyz, new_xyz, idx, w1x, b2, b3, w2_img, w3_img, q, out, workspace, st);
+    return s2v2_launch<128, 128, 256>(b, n, m, xyz, new_xyz, idx, pts_cnt, w1x, b2, b3, w2_img, w3_img, q, out, workspace, st);
   if (c1 == 128 && c2 == 128 && c3 == 128)
-    return s2v2_launch<128, 128, 128>(b, n, m, xyz, new_xyz, idx, w1x, b2, b3, w2_img, w3_img, q, out, workspace, st);
+    return s2v2_launch<128, 128, 128>(b, n, m, xyz, new_xyz, idx, pts_cnt, w1x, b2, b3, w2_img, w3_img, q, out, workspace, st);
   return -1;
 }
 

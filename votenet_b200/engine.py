@@ -173,17 +173,18 @@ class Engine:
                              dptr(layer.img) if self.precision == PRECISION_TENSOR else None, dptr(layer.b),
                              dptr(residual), 1 if act else 0, dptr(out32), dptr(out16), int(self.precision), _sp(st)))
 
-    def _sa(self, li, xyz, feat, n, c, new_xyz, idx, m, q, out, st, ws=None):
+    def _sa(self, li, xyz, feat, n, c, new_xyz, idx, m, q, out, st, ws=None, cnt=None):
         l1, l2, l3, lf, _ = self.sa_layers[li]
         B = self.B
         tc = self.precision == PRECISION_TENSOR
         if lf is not None:  # hoisted layer 1: q = feat @ W1[3:] + b1, fp16, once per source point
             self._linear(B * n, feat, lf, False, None, q, st)
-        check(lib.vnb_sa_group_mlp_max(B, n, c, m, 64, dptr(xyz), dptr(feat), dptr(new_xyz), dptr(idx), l1.cout, l2.cout,
-                                       l3.cout, dptr(l1.W), dptr(l1.b), dptr(l2.W), dptr(l2.b), dptr(l3.W), dptr(l3.b),
-                                       dptr(l1.img) if (tc and lf is None) else None, dptr(l2.img) if tc else None,
-                                       dptr(l3.img) if tc else None, dptr(q) if lf is not None else None, dptr(out),
-                                       int(self.precision), dptr(ws), _sp(st)))
+        check(lib.vnb_sa_group_mlp_max_counted(B, n, c, m, 64, dptr(xyz), dptr(feat), dptr(new_xyz), dptr(idx), dptr(cnt),
+                                               l1.cout, l2.cout, l3.cout, dptr(l1.W), dptr(l1.b), dptr(l2.W), dptr(l2.b),
+                                               dptr(l3.W), dptr(l3.b), dptr(l1.img) if (tc and lf is None) else None,
+                                               dptr(l2.img) if tc else None, dptr(l3.img) if tc else None,
+                                               dptr(q) if lf is not None else None, dptr(out), int(self.precision),
+                                               dptr(ws), _sp(st)))
 
     def _enqueue(self, s, main):
         """Enqueue one forward over slot `s`: sampling chain on s_samp, neighbour searches on s_aux, features on main."""
@@ -239,7 +240,7 @@ class Engine:
         for li, l in enumerate(s.lv):
             main.wait_event(e_bq[li])
             mark(f"sa{li + 1}_begin", main)
-            self._sa(li, src_xyz, src_feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, main, s.sa_ws)
+            self._sa(li, src_xyz, src_feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, main, s.sa_ws, l.cnt)
             mark(f"sa{li + 1}", main)
             src_xyz, src_feat, c = l.xyz, l.feat, cfg.sa[li].mlp[-1]
         main.wait_event(e_nn)
@@ -278,7 +279,8 @@ class Engine:
         check(lib.vnb_gather_point(B, ns, p.npoint, dptr(s.votes_xyz), dptr(s.p_fps), dptr(s.p_xyz), _sp(main)))
         check(lib.vnb_query_ball_point(B, ns, p.npoint, float(p.radius), 64, dptr(s.votes_xyz), dptr(s.p_xyz),
                                        dptr(s.p_idx), dptr(s.p_cnt), _sp(main)))
-        self._sa(len(cfg.sa), s.votes_xyz, s.votes_feat, ns, cf, s.p_xyz, s.p_idx, p.npoint, s.p_q, s.p_feat, main, s.sa_ws)
+        self._sa(len(cfg.sa), s.votes_xyz, s.votes_feat, ns, cf, s.p_xyz, s.p_idx, p.npoint, s.p_q, s.p_feat, main, s.sa_ws,
+                 s.p_cnt)
         x = s.p_feat
         for i in range(len(p.mlp2)):
             self._linear(B * p.npoint, x, self.store.layer(f"proposal/conv_post_{i}"), i < len(p.mlp2) - 1, s.p_h[i], None,

@@ -80,8 +80,9 @@ def linear(x, layer, act, precision, residual=None, out_f16=False):
     return out
 
 
-def sa_group_mlp_max(xyz, points, new_xyz, idx, layers, precision, store=None, scope=None):
-    """Fused grouping + 3-layer shared MLP + max-pool (utils.py:49-55,120-132)."""
+def sa_group_mlp_max(xyz, points, new_xyz, idx, layers, precision, store=None, scope=None, pts_cnt=None):
+    """Fused grouping + 3-layer shared MLP + max-pool (utils.py:49-55,120-132).  pts_cnt (the ball query's second output)
+    lets the tensor-core kernels skip the padded duplicate rows (same result, fewer tiles)."""
     b, n, _ = xyz.shape
     c = points.shape[2]
     m, ns = idx.shape[1], idx.shape[2]
@@ -99,11 +100,12 @@ def sa_group_mlp_max(xyz, points, new_xyz, idx, layers, precision, store=None, s
             q = linear(points.reshape(b * n, c), lf, act=False, precision=precision, out_f16=True)
         else:
             w1_img = l1.img
-    check(lib.vnb_sa_group_mlp_max(b, n, c, m, ns, dptr(xyz, torch.float32, "xyz"), dptr(points, torch.float32, "points"),
-                                   dptr(new_xyz, torch.float32, "new_xyz"), dptr(idx, torch.int32, "idx"), l1.cout,
-                                   l2.cout, l3.cout, dptr(l1.W), dptr(l1.b), dptr(l2.W), dptr(l2.b), dptr(l3.W),
-                                   dptr(l3.b), dptr(w1_img), dptr(w2_img), dptr(w3_img), dptr(q), dptr(out),
-                                   int(precision), dptr(ws), stream_ptr()))
+    check(lib.vnb_sa_group_mlp_max_counted(b, n, c, m, ns, dptr(xyz, torch.float32, "xyz"),
+                                           dptr(points, torch.float32, "points"), dptr(new_xyz, torch.float32, "new_xyz"),
+                                           dptr(idx, torch.int32, "idx"), dptr(pts_cnt, torch.int32, "pts_cnt"), l1.cout,
+                                           l2.cout, l3.cout, dptr(l1.W), dptr(l1.b), dptr(l2.W), dptr(l2.b), dptr(l3.W),
+                                           dptr(l3.b), dptr(w1_img), dptr(w2_img), dptr(w3_img), dptr(q), dptr(out),
+                                           int(precision), dptr(ws), stream_ptr()))
     return out
 
 
@@ -123,11 +125,11 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
     fps = tf_sampling.farthest_point_sample_nested if fps_in.shape[1] <= 4096 else tf_sampling.farthest_point_sample
     fps_idx = fps(npoint, fps_in)
     new_xyz = tf_sampling.gather_point(xyz, fps_idx)
-    idx, _ = tf_grouping.query_ball_point(radius, nsample, xyz, new_xyz)                                 # utils.py:49
+    idx, pts_cnt = tf_grouping.query_ball_point(radius, nsample, xyz, new_xyz)                           # utils.py:49
     layers = [weights.layer(f"{scope}/conv{i}") for i in range(3)]
     for l, co in zip(layers, mlp):
         assert l.cout == co, f"{scope}: weight set does not match mlp={mlp}"
-    new_points = sa_group_mlp_max(xyz, points, new_xyz, idx, layers, prec, weights, scope)               # :50-55,120-132
+    new_points = sa_group_mlp_max(xyz, points, new_xyz, idx, layers, prec, weights, scope, pts_cnt)      # :50-55,120-132
     if mlp2 is not None:                                                                                  # :149-155
         b, m, c = new_points.shape
         h = new_points.reshape(b * m, c)
