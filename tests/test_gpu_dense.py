@@ -263,6 +263,10 @@ def test_sa_tile_packing_is_bit_identical(cuda, b, n, m, c, mlp):
     for i, co in enumerate(mlp):
         w[f"s/conv{i}/W"] = torch.randn(cin, co, generator=g) * (2.0 / cin) ** 0.5
         w[f"s/conv{i}/b"] = torch.randn(co, generator=g) * 0.05
+        w[f"s/conv{i}/bn/gamma"] = torch.rand(co, generator=g) * 0.4 + 0.8   # BN keys make the oracle apply BN + ReLU
+        w[f"s/conv{i}/bn/beta"] = torch.randn(co, generator=g) * 0.05
+        w[f"s/conv{i}/bn/mean/EMA"] = torch.randn(co, generator=g) * 0.05
+        w[f"s/conv{i}/bn/variance/EMA"] = torch.rand(co, generator=g) * 0.4 + 0.8
         cin = co
     store = WeightStore(w, device=cuda, precision=1)
     layers = [store.layer(f"s/conv{i}") for i in range(3)]

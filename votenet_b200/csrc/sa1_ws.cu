@@ -255,8 +255,8 @@ __global__ void __launch_bounds__(S1_THREADS, 1) sa1_ws_kernel(int c, int total_
   if (warp == 0) tmem_dealloc(tmem, Cfg::TM_COLS);
 }
 
-void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx, void* rel,
-                      cudaStream_t st);  // sa_ws.cu
+void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx,
+                      const int* pts_cnt, void* rel, cudaStream_t st);  // sa_ws.cu
 
 // returns -1 when no instance matches
 int sa1_ws_dispatch(int b, int n, int c, int m, const float* xyz, const float* feat, const float* new_xyz, const int* idx,
@@ -270,7 +270,7 @@ int sa1_ws_dispatch(int b, int n, int c, int m, const float* xyz, const float* f
   VNB_CUDA(cudaGetDevice(&dev));
   VNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long rows = (long long)b * m * 64;
-  launch_group_rel(n, m, rows, xyz, new_xyz, idx, workspace, st);
+  launch_group_rel(n, m, rows, xyz, new_xyz, idx, nullptr, workspace, st);
   if (int rc = check_launch("sa_group_mlp_max: grouped relative coordinates")) return rc;
   const int ntiles = b * m / 2;
   int tpc = ntiles / (2 * sms);

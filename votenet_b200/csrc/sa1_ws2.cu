@@ -442,8 +442,8 @@ long long* g_sa_trace = nullptr;  // debugging: device buffer of 12 x 64 x 2 int
 extern int g_sa_sms, g_sa_split;  // mlp_tc.cu
 size_t sa_rel_bytes(long long rows);                                                                  // sa_pack.cu
 int launch_sa_pack(int total_centroids, const int* pts_cnt, int* hdr, int* tile_cid, cudaStream_t st);  // sa_pack.cu
-void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx, void* rel,
-                      cudaStream_t st);  // sa_ws.cu
+void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx,
+                      const int* pts_cnt, void* rel, cudaStream_t st);  // sa_ws.cu
 
 // returns -1 when no instance matches
 int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* feat, const float* new_xyz, const int* idx,
@@ -456,7 +456,7 @@ int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* 
   VNB_CUDA(cudaGetDevice(&dev));
   VNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long rows = (long long)b * m * 64;
-  launch_group_rel(n, m, rows, xyz, new_xyz, idx, workspace, st);
+  launch_group_rel(n, m, rows, xyz, new_xyz, idx, pts_cnt, workspace, st);
   if (int rc = check_launch("sa_group_mlp_max: grouped relative coordinates")) return rc;
   int* hdr = reinterpret_cast<int*>(static_cast<char*>(workspace) + sa_rel_bytes(rows));
   int* tile_cid = hdr + 64;

@@ -58,12 +58,18 @@ constexpr int WS_THREADS = 17 * 32;
 constexpr int WS_PRODUCERS = 256;
 
 // relative coordinates (utils.py:51) and flat source-row index of every grouped row: rel[(g*64+s)] = {xyz[idx]-c, row}
+// pts_cnt (optional): rows beyond the centroid's slot (16 / 32 / 64 rows, sa_pack.cu) are never read and are skipped.
 __global__ void group_rel_kernel(int n, int m, long long total_rows, const float* __restrict__ xyz,
                                  const float* __restrict__ new_xyz, const int* __restrict__ idx,
-                                 float4* __restrict__ rel) {
+                                 const int* __restrict__ pts_cnt, float4* __restrict__ rel) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total_rows) return;
   const int g = (int)(t >> 6);
+  if (pts_cnt != nullptr) {
+    const int c = pts_cnt[g];
+    const int slot = (c <= 0 || c > 32) ? 64 : (c > 16 ? 32 : 16);
+    if ((int)(t & 63) >= slot) return;
+  }
   const int bi = g / m;
   const int pid = idx[t];
   const float* pp = xyz + ((size_t)bi * n + pid) * 3;
@@ -280,9 +286,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sa_ws_kernel(int n, int m, int 
   if (warp == 0) tmem_dealloc(tmem, Cfg::TM_COLS);
 }
 
-void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx, void* rel,
-                      cudaStream_t st) {
-  group_rel_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(n, m, rows, xyz, new_xyz, idx, static_cast<float4*>(rel));
+void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx,
+                      const int* pts_cnt, void* rel, cudaStream_t st) {
+  group_rel_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(n, m, rows, xyz, new_xyz, idx, pts_cnt,
+                                                                   static_cast<float4*>(rel));
 }
 
 template <int C1, int C2, int C3>
@@ -298,7 +305,7 @@ static int launch_ws(int b, int n, int m, const float* xyz, const float* new_xyz
   const int ntiles = b * m / 2;
   float4* rel = static_cast<float4*>(workspace);
   const long long rows = (long long)b * m * 64;
-  group_rel_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(n, m, rows, xyz, new_xyz, idx, rel);
+  group_rel_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(n, m, rows, xyz, new_xyz, idx, nullptr, rel);
   if (int rc = check_launch("sa_group_mlp_max: grouped relative coordinates")) return rc;
   int tpc = ntiles / (2 * sms);
   tpc = tpc < 2 ? 2 : (tpc > 16 ? 16 : tpc);
