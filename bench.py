@@ -316,7 +316,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=int, default=1)
-    ap.add_argument("--inflight", type=int, default=12, help="steps in flight (independent workspaces + streams)")
+    ap.add_argument("--inflight", type=int, default=16, help="steps in flight (independent workspaces + streams)")
     ap.add_argument("--fps-cluster", type=int, default=4,
                     help="CTAs per FPS cluster (4 = 32 SMs per batch: best throughput with steps overlapped; 8 = lowest latency)")
     ap.add_argument("--fps-variant", type=int, default=None, help="0: register/cluster FPS kernel, 1: bucket-pruned (default)")

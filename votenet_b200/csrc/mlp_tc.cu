@@ -45,6 +45,7 @@ int linear_tc(int rows, int cin, int cout, const float* in, const void* w_img, c
               int act, float* out_f32, void* out_f16, cudaStream_t st);  // linear_tc.cu
 int g_sa_sms = 0;    // tuning: SMs the fused SA kernels size their grid for (0 = all)
 int g_sa_split = 1;  // tuning: CTAs (chunks of tiles) per SM
+int g_sa_min_tpc = 24;  // tuning: fewest tiles a CTA of the fused SA kernels takes (fewer CTAs when tiles are scarce)
 int g_sa_variant = 2;  // 0: single-role kernel (sa_tc_kernel), 1: warp-specialised pipeline, first generation,
                        // 2: second generation (one MMA issuer per layer, one wave) where available
 

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
                                                              const float* __restrict__ b3, const char* __restrict__ w1_img,
                                                              const char* __restrict__ w2_img,
                                                              const char* __restrict__ w3_img, float* __restrict__ out,
-                                                             long long* __restrict__ trace, int mma_spin) {
+                                                             long long* __restrict__ trace, int mma_spin, int min_tpc) {
   // debugging aid: CTA 0 stamps clock64() at the start (after its input wait) and the end of every stage of its first
   // TRACE_T tiles: trace[(role * TRACE_T + t) * 2 + {0,1}], roles P, M1, M2, M3, E1, E2, E3(g=0), E3(g=1)
   const bool tr = trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
@@ -113,7 +113,11 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
 
   // tile table written by sa_pack_tiles_kernel (sa_pack.cu): tiles of 2 x 64-row, then 4 x 32-row, then 8 x 16-row slots
   const int ntiles = __ldg(hdr), t64 = __ldg(hdr + 1), t32 = __ldg(hdr + 2);
-  const int tiles_per_cta = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  // CTAs that share the tiles: a CTA has a fixed cost (prologue, weight copy, pipeline fill and drain ~ 10 us), so with few
+  // tiles (the packed deeper levels) fewer CTAs with >= min_tpc tiles each occupy far fewer SM-microseconds — what counts
+  // when other forwards' kernels are waiting for SMs; the surplus CTAs exit at once
+  const int active = max(1, min((int)gridDim.x, (ntiles + min_tpc - 1) / min_tpc));
+  const int tiles_per_cta = (ntiles + active - 1) / active;
   const int first_tile = (int)blockIdx.x * tiles_per_cta;
   const int my_tiles = max(0, min(tiles_per_cta, ntiles - first_tile));
   auto shift_of = [&](int tile) { return tile < t64 ? 6 : (tile < t64 + t32 ? 5 : 4); };  // log2(rows per slot)
@@ -383,6 +387,9 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
     for (int t = s; t < my_tiles; t += 2) {
       const int tile = first_tile + t;
       const int shift = shift_of(tile);
+      // the tile's eight slot entries, requested BEFORE the wait for the accumulator so the (L2) latency hides behind it
+      const int4 ca = __ldg(reinterpret_cast<const int4*>(tile_cid + (size_t)tile * 8));
+      const int4 cb = __ldg(reinterpret_cast<const int4*>(tile_cid + (size_t)tile * 8) + 1);
       mbar_wait(&m3_done[t & 3], par4(t));
       tc_fence_after_sync();
       if (q == 0) { S1_STAMP(6 + s, t, 0) }
@@ -390,9 +397,13 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
       for (int g = 0; g < 2; ++g) {
         // centroids whose samples sit in this half of the tile: one (64-row slots), two (32) or four (16)
         int cid[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          cid[k] = __ldg(tile_cid + (size_t)tile * 8 + (shift == 6 ? g : (shift == 5 ? 2 * g + (k & 1) : 4 * g + k)));
+        if (shift == 6) {
+          cid[0] = g == 0 ? ca.x : ca.y; cid[1] = cid[2] = cid[3] = -1;
+        } else if (shift == 5) {
+          cid[0] = g == 0 ? ca.x : ca.z; cid[1] = g == 0 ? ca.y : ca.w; cid[2] = cid[3] = -1;
+        } else {
+          cid[0] = g == 0 ? ca.x : cb.x; cid[1] = g == 0 ? ca.y : cb.y; cid[2] = g == 0 ? ca.z : cb.z; cid[3] = g == 0 ? ca.w : cb.w;
+        }
         float mb[4];  // maxima of the four 16-column blocks of this half of the tile
         // 16-column loads: ptxas hoists the next load over the current reduction, and two x32 loads do not fit the
         // 64-register budget of this 992-thread CTA (it spilled a whole load)
@@ -439,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
 extern int g_sa_variant;  // mlp_tc.cu
 long long* g_sa_trace = nullptr;  // debugging: device buffer of 12 x 64 x 2 int64 (vnb_debug_sa_trace)
 
-extern int g_sa_sms, g_sa_split;  // mlp_tc.cu
+extern int g_sa_sms, g_sa_split, g_sa_min_tpc;  // mlp_tc.cu
 size_t sa_rel_bytes(long long rows);                                                                  // sa_pack.cu
 int launch_sa_pack(int total_centroids, const int* pts_cnt, int* hdr, int* tile_cid, cudaStream_t st);  // sa_pack.cu
 void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx,
@@ -467,7 +478,7 @@ int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* 
   const int grid = sms < cap ? sms : cap;             // one wave: contiguous chunks of the (device-side) tile count
   kern<<<grid, s1v2::THREADS, s1v2::SMEM, st>>>(c, hdr, tile_cid, static_cast<const float4*>(workspace), feat, b1, b2, b3,
                                                 static_cast<const char*>(w1_img), static_cast<const char*>(w2_img),
-                                                static_cast<const char*>(w3_img), out, g_sa_trace, g_sa_variant == 3 ? 1 : 0);  // MMA issuers park (default) or poll (sa_variant 3)
+                                                static_cast<const char*>(w3_img), out, g_sa_trace, g_sa_variant == 3 ? 1 : 0, g_sa_min_tpc);  // MMA issuers park (default) or poll (sa_variant 3)
   return check_launch("sa_group_mlp_max (tcgen05, warp-specialised v2, narrow input)");
 }
 

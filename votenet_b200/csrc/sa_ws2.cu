@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
                                                             const float* __restrict__ b2, const float* __restrict__ b3,
                                                             const char* __restrict__ w2_img,
                                                             const char* __restrict__ w3_img,
-                                                            const __half* __restrict__ q, float* __restrict__ out) {
+                                                            const __half* __restrict__ q, float* __restrict__ out,
+                                                            int min_tpc) {
   using K = Cfg<C1, C2, C3>;
   constexpr int NCH = K::NCHUNK;
   extern __shared__ uint8_t smem_raw[];
@@ -105,7 +106,11 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
 
   // tile table written by sa_pack_tiles_kernel (sa_pack.cu): tiles of 2 x 64-row, then 4 x 32-row, then 8 x 16-row slots
   const int ntiles = __ldg(hdr), t64 = __ldg(hdr + 1), t32 = __ldg(hdr + 2);
-  const int tiles_per_cta = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  // CTAs that share the tiles: a CTA has a fixed cost (prologue, weight copy, pipeline fill and drain ~ 10 us), so with few
+  // tiles (the packed deeper levels) fewer CTAs with >= min_tpc tiles each occupy far fewer SM-microseconds — what counts
+  // when other forwards' kernels are waiting for SMs; the surplus CTAs exit at once
+  const int active = max(1, min((int)gridDim.x, (ntiles + min_tpc - 1) / min_tpc));
+  const int tiles_per_cta = (ntiles + active - 1) / active;
   const int first_tile = (int)blockIdx.x * tiles_per_cta;
   const int my_tiles = max(0, min(tiles_per_cta, ntiles - first_tile));
   auto shift_of = [&](int tile) { return tile < t64 ? 6 : (tile < t64 + t32 ? 5 : 4); };  // log2(rows per slot)
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
 
 }  // namespace s2v2
 
-extern int g_sa_sms, g_sa_split;  // mlp_tc.cu
+extern int g_sa_sms, g_sa_split, g_sa_min_tpc;  // mlp_tc.cu
 size_t sa_rel_bytes(long long rows);                                                                  // sa_pack.cu
 int launch_sa_pack(int total_centroids, const int* pts_cnt, int* hdr, int* tile_cid, cudaStream_t st);  // sa_pack.cu
 void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx,
@@ -380,7 +385,7 @@ static int s2v2_launch(int b, int n, int m, const float* xyz, const float* new_x
   const int grid = sms < cap ? sms : cap;             // one wave: contiguous chunks of the (device-side) tile count
   kern<<<grid, s2v2::THREADS, K::SMEM, st>>>(hdr, tile_cid, static_cast<const float4*>(workspace), w1x, b2, b3,
                                              static_cast<const char*>(w2_img), static_cast<const char*>(w3_img),
-                                             static_cast<const __half*>(q), out);
+                                             static_cast<const __half*>(q), out, g_sa_min_tpc);
   return check_launch("sa_group_mlp_max (tcgen05, warp-specialised v2)");
 }
 
