@@ -8,7 +8,8 @@ Same graph as `model.VoteNetB200.forward` (reference: /root/reference/model.py:3
   * `slots` independent workspaces (bench.py: 12) keep several forwards in flight: the sa1 FPS of a forward occupies
     8 SMs for 1.5 ms, the other 140 SMs run the feature chains of earlier forwards (DESIGN.md §5);
   * the nested sampling levels use the provenance hint of the sa1 FPS (no proof kernels when it was tie-free), the FP
-    modules and the voting module run as one fused tensor-core kernel per FP level;
+    modules and the voting module run as one fused tensor-core kernel per FP level, the SA kernels get the ball
+    query's hit counts and skip the padded duplicate rows;
   * detections are written straight into one contiguous record (the all-gather wire layout).
 """
 import ctypes as C
