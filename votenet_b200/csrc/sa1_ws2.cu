@@ -393,6 +393,32 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
       mbar_wait(&m3_done[t & 3], par4(t));
       tc_fence_after_sync();
       if (q == 0) { S1_STAMP(6 + s, t, 0) }
+      // eight 16-column blocks; the load of block k+1 is in flight while block k is reduced (two 16-register buffers —
+      // left to itself ptxas stopped hoisting the next load once the per-slot reduction was added, and eight exposed
+      // TMEM round trips made this stage pace the whole kernel)
+      float mbv[8];
+      {
+        uint32_t v[2][16];
+        tmem_ld_x16(tacc, v[0]);
+#pragma unroll
+        for (int blk = 0; blk < 8; ++blk) {
+          tmem_ld_wait();
+          if (blk + 1 < 8) {
+            tmem_ld_x16(tacc + (blk + 1) * 16, v[(blk + 1) & 1]);
+          } else {
+            tc_fence_before_sync();
+            mbar_arrive(&d3_empty[s]);  // D3[s] has been read
+          }
+          const uint32_t* w = v[blk & 1];
+          float a0 = fmaxf(__uint_as_float(w[0]), __uint_as_float(w[4])), a1 = fmaxf(__uint_as_float(w[1]), __uint_as_float(w[5]));
+          float a2 = fmaxf(__uint_as_float(w[2]), __uint_as_float(w[6])), a3 = fmaxf(__uint_as_float(w[3]), __uint_as_float(w[7]));
+          a0 = fmaxf(fmaxf(a0, __uint_as_float(w[8])), __uint_as_float(w[12]));
+          a1 = fmaxf(fmaxf(a1, __uint_as_float(w[9])), __uint_as_float(w[13]));
+          a2 = fmaxf(fmaxf(a2, __uint_as_float(w[10])), __uint_as_float(w[14]));
+          a3 = fmaxf(fmaxf(a3, __uint_as_float(w[11])), __uint_as_float(w[15]));
+          mbv[blk] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        }
+      }
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         // centroids whose samples sit in this half of the tile: one (64-row slots), two (32) or four (16)
@@ -404,26 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
         } else {
           cid[0] = g == 0 ? ca.x : cb.x; cid[1] = g == 0 ? ca.y : cb.y; cid[2] = g == 0 ? ca.z : cb.z; cid[3] = g == 0 ? ca.w : cb.w;
         }
-        float mb[4];  // maxima of the four 16-column blocks of this half of the tile
-        // 16-column loads: ptxas hoists the next load over the current reduction, and two x32 loads do not fit the
-        // 64-register budget of this 992-thread CTA (it spilled a whole load)
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          uint32_t v[16];
-          tmem_ld_x16(tacc + g * 64 + qq * 16, v);
-          tmem_ld_wait();
-          if (g == 1 && qq == 3) {
-            tc_fence_before_sync();
-            mbar_arrive(&d3_empty[s]);  // D3[s] has been read
-          }
-          float a0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[4])), a1 = fmaxf(__uint_as_float(v[1]), __uint_as_float(v[5]));
-          float a2 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[6])), a3 = fmaxf(__uint_as_float(v[3]), __uint_as_float(v[7]));
-          a0 = fmaxf(fmaxf(a0, __uint_as_float(v[8])), __uint_as_float(v[12]));
-          a1 = fmaxf(fmaxf(a1, __uint_as_float(v[9])), __uint_as_float(v[13]));
-          a2 = fmaxf(fmaxf(a2, __uint_as_float(v[10])), __uint_as_float(v[14]));
-          a3 = fmaxf(fmaxf(a3, __uint_as_float(v[11])), __uint_as_float(v[15]));
-          mb[qq] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-        }
+        const float* mb = &mbv[4 * g];
         // bias + ReLU commute with the max
         if (shift == 6) {
           if (cid[0] >= 0) out[(size_t)cid[0] * C3 + ch] = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])) + bias3, 0.f);
