@@ -4,7 +4,7 @@
  * CPU restatement ("oracle") of the reference VoteNet op algorithms, function by function.  Every function
  * cites the reference file:line it follows (paths relative to /root/reference).  Pinned against the real
  * reference: oracle/_ref/libvotenet_ref_cpu.so (the reference's own tf_interpolate.cpp / tf_nms3d.cpp compiled
- * unmodified) in tests/test_oracle_vs_ref.py, and against the reference's own GPU kernels
+ * unmodified) in tests/test_oracle.py, and against the reference's own GPU kernels
  * (oracle/_ref/libvotenet_ref_gpu.so) on the GPU box in tests/test_gpu_ref_kernels.py.
  *
  * Build: gcc -O2 -ffp-contract=off (see oracle/Makefile); single-threaded like the reference CPU ops — callers

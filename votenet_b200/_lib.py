@@ -95,4 +95,7 @@ def dptr(t, dtype=None, name="tensor"):
         raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise ValueError(f"{name}: tensor must be contiguous")
+    if t.device.index != torch.cuda.current_device():   # the C side launches on the CURRENT device
+        raise ValueError(f"{name}: tensor lives on {t.device} but the current CUDA device is {torch.cuda.current_device()} "
+                         "(wrap the call in `with torch.cuda.device(...)`)")
     return C.c_void_p(t.data_ptr())

@@ -42,8 +42,9 @@ constexpr int PBINS = 4096;      // Morton cells (4 bits per axis)
 
 constexpr size_t OFF_XY = 0;                                   // float2 [PP][PT]
 constexpr size_t OFF_TIE = OFF_XY + (size_t)PP * PT * 8;       // uint16 [PP][PT]
-constexpr size_t OFF_HI = OFF_TIE + (size_t)PP * PT * 2;       // int    [2][PNB]
-constexpr size_t OFF_REC = OFF_HI + 2 * PNB * 4;               // uint4  [2][PNB]  {slot, x, y, z}
+constexpr size_t OFF_HI = OFF_TIE + (size_t)PP * PT * 2;       // int    [2][PNB]  champion temp bits
+constexpr size_t OFF_TK = OFF_HI + 2 * PNB * 4;                // uint32 [2][PNB]  champion tie key | shared-temp flag << 16
+constexpr size_t OFF_REC = OFF_TK + 2 * PNB * 4;               // float4 [2][PNB]  champion {x, y, z, -}
 constexpr size_t OFF_RED = OFF_REC + 2 * PNB * 16;             // float  [PW][8]   setup reductions
 constexpr size_t PRUNED_SMEM = OFF_RED + PW * 8 * 4;
 // setup-only aliases (dead before the point arrays are filled)
@@ -62,20 +63,6 @@ __device__ __forceinline__ uint32_t spread4(uint32_t v) {  // abcd -> a00b00c00d
   return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
 }
 
-// Warp arg-max of (hi as signed int, then tie key).  `tie()` is evaluated only when several lanes share the maximum.
-template <class TieFn>
-__device__ __forceinline__ int warp_argmax(int hi, int& whi, bool& shared_max, TieFn tie) {
-  whi = redux_max_s32(hi);
-  unsigned mk = __ballot_sync(0xffffffffu, hi == whi);
-  shared_max = (mk & (mk - 1u)) != 0u;
-  if (mk & (mk - 1u)) {
-    const uint32_t t = (hi == whi) ? tie() : 0u;
-    const uint32_t wt = redux_max(t);
-    mk = __ballot_sync(0xffffffffu, hi == whi && t == wt);
-  }
-  return __ffs(mk) - 1;
-}
-
 template <bool PROF, bool TIES>
 __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const float* __restrict__ xyz,
                                                            int* __restrict__ out, const int* __restrict__ flags,
@@ -84,7 +71,8 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
   float2* sxy = reinterpret_cast<float2*>(smem + OFF_XY);
   uint16_t* stie = reinterpret_cast<uint16_t*>(smem + OFF_TIE);
   int* s_hi = reinterpret_cast<int*>(smem + OFF_HI);
-  uint4* s_rec = reinterpret_cast<uint4*>(smem + OFF_REC);
+  uint32_t* s_tk = reinterpret_cast<uint32_t*>(smem + OFF_TK);
+  float4* s_rec = reinterpret_cast<float4*>(smem + OFF_REC);
   float* s_red = reinterpret_cast<float*>(smem + OFF_RED);
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem + OFF_HIST);
   uint16_t* skey = reinterpret_cast<uint16_t*>(smem + OFF_KEY);
@@ -215,13 +203,16 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
   __syncthreads();
 
   // ---------------------------------------------------------------- rounds
-  int chi = __float_as_int(-1.f);          // lane s (< PS): champion of sub-bucket s: temp bits,
-  uint32_t cslot = 0;                      //   its slot i*PT + tid in sxy / stie (bit 31: another point of the sub-bucket
-                                           //   has exactly the same temp, i.e. the champion won on the tie key),
-  float cx = 0.f, cy = 0.f, cz = 0.f;      //   its coordinates
+  // Champion table (one entry per sub-bucket, two copies indexed by round parity): temp bits, tie key (+ bit 16: the
+  // champion's temp is shared by another point of the sub-bucket), coordinates.  A rescan's winning lane writes the
+  // entry of the CURRENT parity in place; the other copy is brought up to date one round later by lane s (after the
+  // barrier that ends every read of that copy) — so warps without an active sub-bucket publish nothing at all.
+  int chi = __float_as_int(-1.f);            // lane s (< PS): champion temp bits of sub-bucket s (for the bound test)
   float lx = pc[0], ly = pc[1], lz = pc[2];  // last pick: index 0 (tf_sampling_g.cu:114-116)
   if (tid == 0) oc[0] = 0;
   int first_tie = 0x7fffffff;  // first round whose arg-max was not unique (decided by the tie rule)
+  unsigned prev_mask = 0u;     // sub-buckets of this warp rescanned in the previous round
+  const int tb = warp * PS + (lane & (PS - 1));  // table entry of "my" sub-bucket (lanes < PS)
 
   long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt0 = 0;
 #define PF_TICK(i)                 \
@@ -234,6 +225,15 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
 
   for (int r = 1; r < m; ++r) {
     const int par = r & 1;
+    int* t_hi = s_hi + par * PNB;
+    uint32_t* t_tk = s_tk + par * PNB;
+    float4* t_rec = s_rec + par * PNB;
+    // ---- entries written last round live in the other copy only: fetch them now, store after the bound test
+    const bool stale = lane < PS && ((prev_mask >> lane) & 1u);
+    int c_hi = 0;
+    uint32_t c_tk = 0u;
+    float4 c_rec = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (stale) { c_hi = s_hi[(par ^ 1) * PNB + tb]; c_tk = s_tk[(par ^ 1) * PNB + tb]; c_rec = s_rec[(par ^ 1) * PNB + tb]; }
     // ---- which sub-buckets can change?  (lanes 0..7, one sub-bucket each)
     const float gx = fmaxf(fmaxf(blx - lx, lx - bhx), 0.f);
     const float gy = fmaxf(fmaxf(bly - ly, ly - bhy), 0.f);
@@ -241,6 +241,8 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
     const float bound = d2_ref_gpu(gx, gy, gz);
     const bool act = lane < PS && (r == 1 || bound < __int_as_float(chi));
     const unsigned mask = __ballot_sync(0xffffffffu, act);
+    if (stale) { t_hi[tb] = c_hi; t_tk[tb] = c_tk; t_rec[tb] = c_rec; }
+    __syncwarp();  // the copy above precedes this round's in-place writes of the same entries
     PF_TICK(0)
     if (PROF && mask) { pacc[4] += __popc(mask); pacc[5] += 1; }
     // ---- rescan the active sub-buckets of this warp
@@ -248,74 +250,65 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
     for (int s = 0; s < PS; ++s) {
       if (mask & (1u << s)) {
         float xs[PQ], ys[PQ];
-        float best = -2.f;
-        int bq = 0;
-        bool dup = false;  // a second point of this lane shares the lane's maximum
 #pragma unroll
         for (int q = 0; q < PQ; ++q) {
           const int i = s * PQ + q;
           const float2 v = sxy[i * PT + tid];
           xs[q] = v.x; ys[q] = v.y;
-          const float d = d2_ref_gpu(v.x - lx, v.y - ly, z[i] - lz);
-          td[i] = fminf(d, td[i]);
-          if (td[i] > best) { best = td[i]; bq = q; }  // first strict maximum in descending tie-key order
+          td[i] = fminf(d2_ref_gpu(v.x - lx, v.y - ly, z[i] - lz), td[i]);
         }
-        if (TIES) {  // off the arg-max dependency chain: how many of the lane's points sit at the lane's maximum?
+        const float best = fmaxf(fmaxf(fmaxf(td[s * PQ], td[s * PQ + 1]), fmaxf(td[s * PQ + 2], td[s * PQ + 3])), td[s * PQ + 4]);
+        // first maximum in descending tie-key order = the reference's per-thread rule
+        int bq = PQ - 1;
+#pragma unroll
+        for (int q = PQ - 2; q >= 0; --q) bq = td[s * PQ + q] == best ? q : bq;
+        const uint32_t tkm = stie[(s * PQ + bq) * PT + tid];    // in flight beside the first reduction
+        const int whi = redux_max_s32(__float_as_int(best));
+        const bool mine = __float_as_int(best) == whi;
+        const uint32_t wk = redux_max(mine ? ((tkm << 5) | (uint32_t)lane) : 0u);
+        bool dup = false;
+        if (TIES) {  // another point of the sub-bucket shares the champion's temp (another lane, or inside the lane)
           int same = 0;
 #pragma unroll
           for (int q = 0; q < PQ; ++q) same += td[s * PQ + q] == best ? 1 : 0;
-          dup = same > 1;
+          const unsigned mm = __ballot_sync(0xffffffffu, mine);
+          dup = (mm & (mm - 1u)) != 0u || __ballot_sync(0xffffffffu, mine && same > 1) != 0u;
         }
-        float bx = xs[0], by = ys[0], bz = z[s * PQ];
+        if (mine && (wk & 31u) == (uint32_t)lane) {
+          float bx = xs[0], by = ys[0], bz = z[s * PQ];
 #pragma unroll
-        for (int q = 1; q < PQ; ++q)
-          if (bq == q) { bx = xs[q]; by = ys[q]; bz = z[s * PQ + q]; }
-        const uint32_t slot = (uint32_t)((s * PQ + bq) * PT + tid);
-        int whi;
-        bool shared_max;
-        const int src = warp_argmax(__float_as_int(best), whi, shared_max, [&] { return (uint32_t)stie[slot]; });
-        const bool ctie = TIES && (shared_max || __ballot_sync(0xffffffffu, dup && __float_as_int(best) == whi) != 0u);
-        const float wx = __shfl_sync(0xffffffffu, bx, src), wy = __shfl_sync(0xffffffffu, by, src),
-                    wz = __shfl_sync(0xffffffffu, bz, src);
-        const uint32_t wslot = __shfl_sync(0xffffffffu, slot, src);
-        if (lane == s) { chi = whi; cslot = wslot | (ctie ? 0x80000000u : 0u); cx = wx; cy = wy; cz = wz; }
+          for (int q = 1; q < PQ; ++q)
+            if (bq == q) { bx = xs[q]; by = ys[q]; bz = z[s * PQ + q]; }
+          t_hi[warp * PS + s] = whi;
+          t_tk[warp * PS + s] = (wk >> 5) | (dup ? 0x10000u : 0u);
+          t_rec[warp * PS + s] = make_float4(bx, by, bz, 0.f);
+        }
+        if (lane == s) chi = whi;
       }
     }
+    prev_mask = mask;
     PF_TICK(1)
-    // ---- publish the 8 sub-bucket champions of this warp (double-buffered by round parity), one barrier
-    if (lane < PS) {
-      s_hi[par * PNB + warp * PS + lane] = chi;
-      s_rec[par * PNB + warp * PS + lane] = make_uint4(cslot, __float_as_uint(cx), __float_as_uint(cy), __float_as_uint(cz));
-    }
     __syncthreads();
     PF_TICK(2)
-    // ---- every warp reduces the 128 champions (4 per lane)
-    const int4 h = reinterpret_cast<const int4*>(s_hi + par * PNB)[lane];
-    const int hb = max(max(h.x, h.y), max(h.z, h.w));
-    const int whi = redux_max_s32(hb);
-    const int cnt = (h.x == whi) + (h.y == whi) + (h.z == whi) + (h.w == whi);
-    unsigned mk = __ballot_sync(0xffffffffu, cnt > 0);
-    const unsigned multi = __ballot_sync(0xffffffffu, cnt > 1);
-    int bj = h.x == whi ? 0 : (h.y == whi ? 1 : (h.z == whi ? 2 : 3));
-    const bool tie_sub = ((mk & (mk - 1u)) | multi) != 0u;  // several sub-bucket champions share the maximal temp
-    if ((mk & (mk - 1u)) | multi) {  // several champions share the maximal temp exactly: highest tie key wins
-      uint32_t bt = 0u;
-      const int hv[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (hv[j] == whi) {
-          const uint32_t t = stie[s_rec[par * PNB + lane * 4 + j].x & 0x7fffffffu];
-          if (t > bt) { bt = t; bj = j; }
-        }
-      const uint32_t wt = redux_max(bt);
-      mk = __ballot_sync(0xffffffffu, cnt > 0 && bt == wt);
+    // ---- every warp reduces the 128 champions (4 per lane): max temp, then max tie key among the holders
+    const int4 h = reinterpret_cast<const int4*>(t_hi)[lane];
+    const uint4 t = reinterpret_cast<const uint4*>(t_tk)[lane];
+    const int whi = redux_max_s32(max(max(h.x, h.y), max(h.z, h.w)));
+    // key: tie key (bits 8..23) | entry (bits 1..7) | shared-temp flag (bit 0); tie keys are unique per point
+    const uint32_t e0 = (uint32_t)lane << 3;
+    const uint32_t k0 = h.x == whi ? (((t.x & 0xffffu) << 8) | e0 | (t.x >> 16)) : 0u;
+    const uint32_t k1 = h.y == whi ? (((t.y & 0xffffu) << 8) | (e0 + 2u) | (t.y >> 16)) : 0u;
+    const uint32_t k2 = h.z == whi ? (((t.z & 0xffffu) << 8) | (e0 + 4u) | (t.z >> 16)) : 0u;
+    const uint32_t k3 = h.w == whi ? (((t.w & 0xffffu) << 8) | (e0 + 6u) | (t.w >> 16)) : 0u;
+    const uint32_t wk = redux_max(max(max(k0, k1), max(k2, k3)));
+    const float4 rec = t_rec[(wk >> 1) & 127u];
+    lx = rec.x; ly = rec.y; lz = rec.z;
+    if (TIES && r < tie_rounds && first_tie == 0x7fffffff && whi >= 0) {
+      const int cnt = (h.x == whi) + (h.y == whi) + (h.z == whi) + (h.w == whi);
+      const unsigned holders = __ballot_sync(0xffffffffu, cnt > 0), multi = __ballot_sync(0xffffffffu, cnt > 1);
+      if ((holders & (holders - 1u)) | multi | (wk & 1u)) first_tie = r;
     }
-    const int src = __ffs(mk) - 1;
-    const int e = src * 4 + __shfl_sync(0xffffffffu, bj, src);
-    const uint4 rec = s_rec[par * PNB + e];
-    lx = __uint_as_float(rec.y); ly = __uint_as_float(rec.z); lz = __uint_as_float(rec.w);
-    if (TIES && r < tie_rounds && (tie_sub || (rec.x >> 31)) && whi >= 0 && first_tie == 0x7fffffff) first_tie = r;
-    if (warp == (r & (PW - 1)) && lane == 0) oc[r] = tie_key_to_index((uint32_t)stie[rec.x & 0x7fffffffu]);
+    if (warp == (r & (PW - 1)) && lane == 0) oc[r] = tie_key_to_index(wk >> 8);
     PF_TICK(3)
   }
 #undef PF_TICK

@@ -5,7 +5,7 @@ Same graph as `model.VoteNetB200.forward` (reference: /root/reference/model.py:3
   * the forward is scheduled on three streams — the FPS chain depends on xyz only, ball queries
     and three_nn depend on xyz + centroids only, so both run beside the feature (MLP) chain and are joined by events;
   * the whole multi-stream forward is captured into one CUDA graph per slot;
-  * `slots` independent workspaces (bench.py: 12) keep several forwards in flight: the sa1 FPS of a forward occupies
+  * `slots` independent workspaces (bench.py: 16) keep several forwards in flight: the sa1 FPS of a forward occupies
     8 SMs for 1.5 ms, the other 140 SMs run the feature chains of earlier forwards (DESIGN.md §5);
   * the nested sampling levels use the provenance hint of the sa1 FPS (no proof kernels when it was tie-free), the FP
     modules and the voting module run as one fused tensor-core kernel per FP level, the SA kernels get the ball
@@ -303,14 +303,22 @@ class Engine:
     def infer_device(self, xyz, feat, stream=None):
         """xyz (B,N,3), feat (B,N,C) CUDA f32 -> DetectionRecord (device views; valid until this slot is reused, i.e.
         until the call after next).  Asynchronous on `stream` (default: current stream)."""
-        main = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            main = stream if stream is not None else torch.cuda.current_stream(self.device)
+            s = self._next_slot(main)
+            with torch.cuda.stream(main):
+                s.xyz.copy_(xyz, non_blocking=True)
+                s.feat.copy_(feat, non_blocking=True)
+            self._run_slot(s, main)
+        return s.rec
+
+    def _next_slot(self, main):
+        """Round-robin slot; its previous forward may have run on another stream, so `main` waits for it first."""
         s = self.slots[self._step % len(self.slots)]
         self._step += 1
-        with torch.cuda.stream(main):
-            s.xyz.copy_(xyz, non_blocking=True)
-            s.feat.copy_(feat, non_blocking=True)
-        self._run_slot(s, main)
-        return s.rec
+        if s.used:
+            main.wait_event(s.done)
+        return s
 
     def _run_slot(self, s, main):
         if not self.use_graph:
@@ -340,17 +348,18 @@ class Engine:
     def infer_host(self, xyz_pinned, feat_pinned, out_pinned, stream=None):
         """End-to-end call with HOST buffers: pinned inputs are copied host->device, the forward runs, and the detection
         record is copied device->host into `out_pinned` (uint8, rec.nbytes).  Asynchronous; returns the slot's event."""
-        main = stream if stream is not None else torch.cuda.current_stream(self.device)
-        s = self.slots[self._step % len(self.slots)]
-        self._step += 1
-        with torch.cuda.stream(main):
-            s.xyz.copy_(xyz_pinned, non_blocking=True)
-            s.feat.copy_(feat_pinned, non_blocking=True)
-        self._run_slot(s, main)
-        with torch.cuda.stream(main):
-            out_pinned.copy_(s.rec.buf, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(main)
+        with torch.cuda.device(self.device):
+            main = stream if stream is not None else torch.cuda.current_stream(self.device)
+            s = self._next_slot(main)
+            with torch.cuda.stream(main):
+                s.xyz.copy_(xyz_pinned, non_blocking=True)
+                s.feat.copy_(feat_pinned, non_blocking=True)
+            self._run_slot(s, main)
+            with torch.cuda.stream(main):
+                out_pinned.copy_(s.rec.buf, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            s.done.record(main)   # the slot is busy until its record has left for the host
         return ev
 
     @property
