@@ -223,12 +223,20 @@ def kernel_table(eng, cfg, peaks, flush):
     for li, l in enumerate(s.lv):
         sa = cfg.sa[li]
         if li == 0:
-            ms = t(lambda: check(lib.vnb_farthest_point_sample_ties(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_tie), eng.tie_rounds, sp())))
+            ms = t(lambda: check(lib.vnb_farthest_point_sample(B, l.n, l.m, dptr(src), dptr(l.fps), sp())))
             hbm("fps_sa1", ms, B * (l.m - 1) * l.n * 16, onchip)
-        else:  # FPS of an FPS-ordered set: parallel proof of the identity prefix (sequential kernel only on failure)
+        elif li == 1:  # FPS of an FPS-ordered set: parallel proof of the identity prefix (sequential kernel only on failure)
+            ms = t(lambda: check(lib.vnb_farthest_point_sample_nested_proof(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws),
+                                                                            dptr(s.fps_tie), sp())))
+            rows.append(dict(kernel="fps_sa2_identity_proof", ms=ms, bound="hbm", algo_bytes=B * l.n * 12, achieved=B * l.n * 12 / ms / 1e6,
+                             peak=peaks["hbm"], unit="GB/s",
+                             note="proof kernels: the sampled set is a prefix of sa1's picks; latency-bound (compulsory bytes only)"))
+        else:  # covered by the sa2-level proof: identity prefix written by early-exit launches (no sampling work at all)
             ms = t(lambda: check(lib.vnb_farthest_point_sample_nested_hint(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws),
                                                                            dptr(s.fps_tie), sp())))
-            hbm(f"fps_sa{li + 1}_nested", ms, B * (l.m - 1) * l.n * 16, onchip)
+            rows.append(dict(kernel=f"fps_sa{li + 1}_covered_by_proof", ms=ms, bound="hbm", algo_bytes=B * l.m * 4,
+                             achieved=B * l.m * 4 / ms / 1e6, peak=peaks["hbm"], unit="GB/s",
+                             note="no sampler runs (identity prefix proven at sa2): launch latency of the early-exit kernels"))
         ms = t(lambda: check(lib.vnb_query_ball_point_ws(B, l.n, l.m, float(sa.radius), 64, dptr(src), dptr(l.xyz), dptr(l.idx),
                                                          dptr(l.cnt), dptr(l.bq_ws), sp())))
         hbm(f"ball_query_sa{li + 1}", ms, B * (l.n * 12 + l.m * 12 + l.m * 256 + l.m * 4), "latency-bound (compulsory bytes only)")
@@ -296,10 +304,10 @@ def kernel_table(eng, cfg, peaks, flush):
     r = s.rec
 
     def nms_fn():
-        check(lib.vnb_decode_boxes(B, p.npoint, dptr(s.p_xyz), dptr(s.p_h[-1]), dptr(eng.mean_size), dptr(r.bboxes),
-                                   dptr(r.scores), dptr(r.objectness), dptr(r.class_scores), sp()))
-        check(lib.vnb_nms3d(B, p.npoint, dptr(r.bboxes), dptr(r.scores), dptr(r.objectness), float(cfg.nms_iou), dptr(r.keep),
-                            dptr(r.nms_idx), dptr(r.nms_count), dptr(s.nms_ws), sp()))
+        check(lib.vnb_decode_nms3d(B, p.npoint, dptr(s.p_xyz), dptr(s.p_h[-1]), dptr(eng.mean_size), float(cfg.nms_iou),
+                                   dptr(r.bboxes), dptr(r.scores), dptr(r.objectness), dptr(r.class_scores), dptr(r.keep),
+                                   dptr(r.nms_idx), dptr(r.nms_key), dptr(r.nms_count), dptr(s.bboxes_pred),
+                                   dptr(s.class_scores_pred), dptr(s.batch_idx), dptr(s.nms_ws), sp()))
     ms = t(nms_fn)
     hbm("decode_nms3d", ms, B * (p.npoint * (79 + 3) * 4 + eng.record_nbytes // B), "latency-bound (compulsory bytes only)")
     for r_ in rows:

@@ -76,6 +76,16 @@ int vnb_farthest_point_sample_nested(int b, int n, int m, const float* xyz, int*
  * caller vouches for the provenance (wrong provenance = wrong indices); results are otherwise bit-identical. */
 int vnb_farthest_point_sample_ties(int b, int n, int m, const float* xyz, int* out_idx, int* first_tie_round,
                                    int track_rounds, void* stream);
+/* vnb_farthest_point_sample_nested that also reports what it proved: proven_rounds[cloud] = m when the identity prefix
+ * 0..m-1 was PROVEN for the cloud (every round j < m of FPS over these n points picks position j, under the reference's
+ * index-based tie rule), else 0.  That array is a valid hint (parent_first_tie_round) for
+ * vnb_farthest_point_sample_nested_hint on any PREFIX xyz[:, :n'] of the same points, n' <= n, for m' <= m picks: a
+ * competitor inside the prefix is inside the proven set too, it has the same running distance and the same index
+ * there, so position j wins the prefix's round j as well.  One proof at the first nested level (2048 -> 1024) thus
+ * covers the deeper levels and the proposal module's sampling (utils.py:42-45, model.py:89-93), which all sample
+ * prefixes of it — without tie tracking in the big sa1 sampler. */
+int vnb_farthest_point_sample_nested_proof(int b, int n, int m, const float* xyz, int* out_idx, void* workspace,
+                                           int* proven_rounds, void* stream);
 int vnb_farthest_point_sample_nested_hint(int b, int n, int m, const float* xyz, int* out_idx, void* workspace,
                                           const int* parent_first_tie_round, void* stream);
 
@@ -118,7 +128,8 @@ int vnb_three_interpolate(int b, int m, int c, int n, const float* points, const
 /* ------------------------------------------------------------------ tf_ops/3d_nms --------------------- */
 
 /* NonMaxSuppression3DOp::Compute                                 tf_nms3d.cpp:283-305 (+ :202-273)
- * bbox (b,k,8,3), scores (b,k), objectiveness (b,k,2), 0 <= iou_threshold <= 1.   k <= 1024.
+ * bbox (b,k,8,3), scores (b,k), objectiveness (b,k,2), 0 <= iou_threshold <= 1.   k <= 1024 (one CTA per cloud holds
+ * the cloud's suppression bitmask in shared memory); any b.  NaN scores rank last (the order stays total).
  * Outputs (all caller-allocated):
  *   keep      (b,k)   u8   1 where the box survives NMS (the per-cloud keep mask)
  *   out_idx   (b*k,2) i32  rows (batch, box) of the survivors in the reference's GLOBAL descending-score order
@@ -130,13 +141,33 @@ size_t vnb_nms3d_workspace_bytes(int b, int k);
 int vnb_nms3d(int b, int k, const float* bbox, const float* scores, const float* objectiveness, float iou_threshold,
               uint8_t* keep, int* out_idx, int* out_count, void* workspace, void* stream);
 
-/* Global ordering of NMS survivors across an all-gathered batch: `gathered` holds `world`
- * records of `rank_stride` bytes; in each, scores (b,k) f32 sit at byte offset off_scores and keep (b,k) u8 at
- * off_keep.  Writes rows (global_batch, box) with global_batch = rank*b + local, in descending score order (ties:
- * ascending (global_batch, box)) and their number — the reference's (Nnms,2) output for the whole sharded batch
- * (tf_nms3d.cpp:240-272). */
-int vnb_merge_detections(int world, int b, int k, const void* gathered, size_t rank_stride, size_t off_scores,
-                         size_t off_keep, int* out_idx, int* out_count, void* stream);
+/* Box decode (model.py:100-129) + NonMaxSuppression3DOp (tf_nms3d.cpp:202-305) as ONE kernel, one CTA per cloud —
+ * what the forward path calls.  Inputs as vnb_decode_boxes, outputs as vnb_decode_boxes + vnb_nms3d, plus
+ *   out_key (b*k) u32   the order-preserving score key of every row of out_idx (descending): together with out_idx
+ *                       and out_count this is a rank's sorted detection list, the input of vnb_merge_detections.
+ * and, where the pointers are not NULL, the output gathers of model.py:135-137 over this batch, rows in out_idx order:
+ *   bboxes_pred (b*k,8,3) f32 = bboxes[out_idx], class_scores_pred (b*k,10) f32, batch_idx (b*k) i32 (first out_count rows).
+ * workspace: vnb_nms3d_workspace_bytes(b,k). */
+int vnb_decode_nms3d(int b, int k, const float* proposals_xyz, const float* proposals_output,
+                     const float* class_mean_size, float iou_threshold, float* bboxes, float* scores,
+                     float* objectness, float* class_scores, uint8_t* keep, int* out_idx, uint32_t* out_key,
+                     int* out_count, float* bboxes_pred, float* class_scores_pred, int* batch_idx, void* workspace,
+                     void* stream);
+
+/* Global ordering of NMS survivors across an all-gathered batch and the output gathers of
+ * model.py:135-137.  `gathered` holds `world` (<= 64) records of `rank_stride` bytes; record r carries, at the given
+ * byte offsets, its rank's sorted detection list — rows (local_batch, box) i32 at off_idx, their score keys u32 at
+ * off_key, the row count i32 at off_count (all three as written by vnb_decode_nms3d) — and the decoded boxes
+ * (b,k,8,3) f32 at off_bboxes / class scores (b,k,10) f32 at off_class_scores.  A k-way merge by rank (own position +
+ * binary searches in the other lists) writes
+ *   out_idx (world*b*k,2) i32  rows (global_batch, box), global_batch = rank*b + local, descending score, exact ties by
+ *                              ascending (global_batch, box) — the reference's (Nnms,2) output for the whole sharded
+ *                              batch (tf_nms3d.cpp:240-272);  out_count (1) i32 = Nnms
+ * and, where the pointers are not NULL, the three gathers of model.py:135-137:
+ *   bboxes_pred (world*b*k,8,3) f32, class_scores_pred (world*b*k,10) f32, batch_idx (world*b*k) i32  (first Nnms rows). */
+int vnb_merge_detections(int world, int b, int k, const void* gathered, size_t rank_stride, size_t off_idx,
+                         size_t off_key, size_t off_count, size_t off_bboxes, size_t off_class_scores, int* out_idx,
+                         int* out_count, float* bboxes_pred, float* class_scores_pred, int* batch_idx, void* stream);
 
 /* ------------------------------------------------------------------ fused layers (boundary B) --------- */
 /* The dense arithmetic the reference delegates to TensorFlow/Tensorpack (Conv2D 1x1 + BN(EMA) + ReLU + reduce_max,

@@ -209,3 +209,43 @@ def test_fps_nested_hint_matches_oracle(cuda, kind):
             break  # a level that is not the identity prefix ends the provenance chain
     if kind == "sun":
         assert (ties.cpu().numpy() == 0x7FFFFFFF).all()
+
+
+@pytest.mark.parametrize("kind", ["sun", "lattice", "dup", "dup_late"])
+def test_fps_nested_proof_chain_matches_oracle(cuda, kind):
+    """The engine's sampling chain: plain FPS on the raw cloud, ONE parallel proof at the first nested level
+    (2048 -> 1024) whose per-cloud result is the hint of every deeper level and of the proposal module's sampling
+    (1024 -> 512, 512 -> 256, 1024 -> 256).  Identical to the oracle with and without engineered ties — including a
+    tie beyond the proven rounds and clouds whose proof fails (hint 0: proof / sequential fallback at every level)."""
+    from votenet_b200 import synth
+    from votenet_b200.tf_sampling import (farthest_point_sample, farthest_point_sample_nested_hint,
+                                          farthest_point_sample_nested_proof, gather_point)
+
+    rng = np.random.default_rng(8)
+    b, n = 3, 20000
+    x = np.stack([synth.synthetic_cloud(20 + i, n) for i in range(b)], 0)
+    if kind == "lattice":
+        x[1] = (rng.integers(0, 12, (n, 3)) / 4).astype(np.float32)
+    elif kind in ("dup", "dup_late"):
+        p = O.farthest_point_sample(1500, x[2:3])[0]
+        x[2, 12345] = x[2, p[33 if kind == "dup" else 1400]]   # an exact duplicate of an early / a late pick
+    tx = T(x, cuda)
+    f1 = farthest_point_sample(2048, tx)
+    assert np.array_equal(f1.cpu().numpy(), O.farthest_point_sample(2048, x))
+    l1, l1_np = gather_point(tx, f1), O.gather_point(x, f1.cpu().numpy())
+    f2, proven = farthest_point_sample_nested_proof(1024, l1)
+    assert np.array_equal(f2.cpu().numpy(), O.farthest_point_sample(1024, l1_np)), (kind, proven.tolist())
+    ident = np.array_equal(f2.cpu().numpy(), np.tile(np.arange(1024, dtype=np.int32), (b, 1)))
+    pv = proven.cpu().numpy()
+    assert set(pv.tolist()) <= {0, 1024}
+    if kind == "sun":
+        assert (pv == 1024).all() and ident
+    l2, l2_np = gather_point(l1, f2), O.gather_point(l1_np, f2.cpu().numpy())
+    # deeper levels + the proposal sampling take the proof's result as their hint (valid while the chain is a prefix chain)
+    for (src, src_np, m) in ((l2, l2_np, 512), (l2, l2_np, 256)):
+        got = farthest_point_sample_nested_hint(m, src, proven).cpu().numpy()
+        assert np.array_equal(got, O.farthest_point_sample(m, src_np)), (kind, m, pv.tolist())
+    f3 = farthest_point_sample_nested_hint(512, l2, proven)
+    l3, l3_np = gather_point(l2, f3), O.gather_point(l2_np, f3.cpu().numpy())
+    got = farthest_point_sample_nested_hint(256, l3, proven).cpu().numpy()
+    assert np.array_equal(got, O.farthest_point_sample(256, l3_np)), (kind, pv.tolist())

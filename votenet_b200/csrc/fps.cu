@@ -276,9 +276,11 @@ __global__ void __launch_bounds__(VP * VS) fps_prefix_verify_kernel(int n, int m
   if (live && bad) atomicOr(&fail[cloud], 1);
 }
 
-__global__ void fps_identity_kernel(int b, int m, const int* __restrict__ fail, int* __restrict__ out, int* __restrict__ done) {
+__global__ void fps_identity_kernel(int b, int m, const int* __restrict__ fail, int* __restrict__ out, int* __restrict__ done,
+                                    int* __restrict__ proven_rounds) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < b) done[t] = fail[t] ? 0 : 1;
+  if (t < b && proven_rounds != nullptr) proven_rounds[t] = fail[t] ? 0 : m;
   if (t >= b * m) return;
   if (!fail[t / m]) out[t] = t % m;
 }
@@ -384,12 +386,15 @@ static int fps_dispatch(int b, int n, int m, const float* xyz, int* out, const i
 
 using namespace vnb;
 
+namespace vnb { extern int g_fps_dispatch, g_fps_ablate; }
 extern "C" int vnb_set_tuning(const char* key, int value) {
   std::string_view k(key);
   if (k == "fps_mode") g_fps_mode = value;
   else if (k == "fps_cluster") g_fps_cl = value;
   else if (k == "fps_threads") g_fps_threads = value;
   else if (k == "fps_variant") g_fps_variant = value;
+  else if (k == "fps_dispatch") vnb::g_fps_dispatch = value;
+  else if (k == "fps_ablate") vnb::g_fps_ablate = value;
   else if (k == "ball_query_variant") vnb::g_bq_variant = value;
   else if (k == "bq_grid_min_n") vnb::g_bq_grid_min_n = value;
   else if (k == "sa_variant") vnb::g_sa_variant = value;
@@ -430,11 +435,21 @@ extern "C" size_t vnb_fps_nested_workspace_bytes(int b, int m) {
   return (size_t)(b > 0 ? b : 1) * (2 * sizeof(int) + (size_t)(m > 0 ? m : 1) * sizeof(float)) + 256;
 }
 
+__global__ void fps_fill_kernel(int b, int* __restrict__ v, int value) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < b) v[t] = value;
+}
+
 static int fps_nested_impl(int b, int n, int m, const float* xyz, int* out_idx, void* workspace, const int* hint,
-                           cudaStream_t st) {
+                           cudaStream_t st, int* proven_rounds = nullptr) {
   const size_t smem = (size_t)m * sizeof(float4);
-  if (m > n || smem > 200 * 1024)  // the identity prefix needs m <= n; huge m does not fit the proof kernel
+  if (m > n || smem > 200 * 1024) {  // the identity prefix needs m <= n; huge m does not fit the proof kernel
+    if (proven_rounds != nullptr) {
+      fps_fill_kernel<<<(b + 127) / 128, 128, 0, st>>>(b, proven_rounds, 0);
+      if (int rc = check_launch("fps proven rounds")) return rc;
+    }
     return fps_dispatch(b, n, m, xyz, out_idx, nullptr, st);
+  }
   int* fail = static_cast<int*>(workspace);
   int* done = fail + b;
   float* R = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)b * 2 * sizeof(int) + 255) / 256) * 256);
@@ -447,7 +462,7 @@ static int fps_nested_impl(int b, int n, int m, const float* xyz, int* out_idx, 
     VNB_CUDA(cudaFuncSetAttribute(fps_prefix_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fps_prefix_verify_kernel<<<dim3((n + VP - 1) / VP, b), VP * VS, smem, st>>>(n, m, xyz, R, fail, hint);
   if (int rc = check_launch("fps prefix proof")) return rc;
-  fps_identity_kernel<<<(b * m + 255) / 256, 256, 0, st>>>(b, m, fail, out_idx, done);
+  fps_identity_kernel<<<(b * m + 255) / 256, 256, 0, st>>>(b, m, fail, out_idx, done, proven_rounds);
   if (int rc = check_launch("fps identity")) return rc;
   // sequential kernel for the clouds whose proof failed (clusters of proven clouds exit at once)
   return fps_dispatch(b, n, m, xyz, out_idx, done, st);
@@ -458,6 +473,14 @@ extern "C" int vnb_farthest_point_sample_nested(int b, int n, int m, const float
   if (int rc = fps_check_args(b, n, m)) return rc;
   if (b == 0) return VNB_OK;
   return fps_nested_impl(b, n, m, xyz, out_idx, workspace, nullptr, as_stream(stream));
+}
+
+extern "C" int vnb_farthest_point_sample_nested_proof(int b, int n, int m, const float* xyz, int* out_idx, void* workspace,
+                                                      int* proven_rounds, void* stream) {
+  if (int rc = fps_check_args(b, n, m)) return rc;
+  VNB_REQUIRE(proven_rounds != nullptr, "farthest_point_sample_nested_proof: proven_rounds buffer missing");
+  if (b == 0) return VNB_OK;
+  return fps_nested_impl(b, n, m, xyz, out_idx, workspace, nullptr, as_stream(stream), proven_rounds);
 }
 
 extern "C" int vnb_farthest_point_sample_ties(int b, int n, int m, const float* xyz, int* out_idx, int* first_tie_round,

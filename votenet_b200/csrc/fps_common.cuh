@@ -47,6 +47,11 @@ __device__ __forceinline__ int tie_key_to_index(uint32_t key) {
   return (int)((t >> 6) | ((t & 63u) << 9));
 }
 
+__device__ __forceinline__ uint32_t redux_add(uint32_t v) {
+  uint32_t r;
+  asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
 __device__ __forceinline__ int redux_max_s32(int v) {
   int r;
   asm volatile("redux.sync.max.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));

@@ -42,11 +42,17 @@ constexpr int PBINS = 4096;      // Morton cells (4 bits per axis)
 
 constexpr size_t OFF_XY = 0;                                   // float2 [PP][PT]
 constexpr size_t OFF_TIE = OFF_XY + (size_t)PP * PT * 8;       // uint16 [PP][PT]
-constexpr size_t OFF_HI = OFF_TIE + (size_t)PP * PT * 2;       // int    [2][PNB]  champion temp bits
-constexpr size_t OFF_TK = OFF_HI + 2 * PNB * 4;                // uint32 [2][PNB]  champion tie key | shared-temp flag << 16
-constexpr size_t OFF_REC = OFF_TK + 2 * PNB * 4;               // float4 [2][PNB]  champion {x, y, z, -}
-constexpr size_t OFF_RED = OFF_REC + 2 * PNB * 16;             // float  [PW][8]   setup reductions
-constexpr size_t PRUNED_SMEM = OFF_RED + PW * 8 * 4;
+constexpr size_t OFF_HI = OFF_TIE + (size_t)PP * PT * 2;       // int    [2][PW]   warp champion temp bits
+constexpr size_t OFF_TK = OFF_HI + 2 * PW * 4;                 // uint32 [2][PW]   warp champion key (tie key << 8 | entry << 1 | shared)
+constexpr size_t OFF_WREC = OFF_TK + 2 * PW * 4;               // float4 [2][PW]   warp champion {x, y, z, -}
+constexpr size_t OFF_REC = OFF_WREC + 2 * PW * 16;             // float4 [PNB]     sub-bucket champion {x, y, z, -} (warp-private)
+constexpr size_t OFF_RED = OFF_REC + PNB * 16;                 // float  [PW][8]   setup reductions
+constexpr int PZS = 8;           // z of the LAST PZS points of a thread lives in shared memory, not in registers: 80
+                                 // registers of point state leave too few for the rest of the round loop, and with the
+                                 // whole L1 carved out as shared memory a compiler spill is an L2 round trip
+constexpr int PZR = PP - PZS;    // z of points 0..PZR-1: registers
+constexpr size_t OFF_Z = OFF_RED + PW * 8 * 4;                 // float  [PZS][PT]
+constexpr size_t PRUNED_SMEM = OFF_Z + (size_t)PZS * PT * 4;
 // setup-only aliases (dead before the point arrays are filled)
 constexpr size_t OFF_HIST = OFF_XY;                            // uint32 [PBINS]
 constexpr size_t OFF_KEY = OFF_XY + PBINS * 4;                 // uint16 [PCAP] cell key of point k
@@ -63,16 +69,47 @@ __device__ __forceinline__ uint32_t spread4(uint32_t v) {  // abcd -> a00b00c00d
   return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
 }
 
-template <bool PROF, bool TIES>
+// Register-specific part of a rescan of sub-bucket S: new running distances of the lane's PQ points, the lane-local
+// champion (first maximum in descending tie-key order = the reference's per-thread rule), its coordinates, and how many
+// of the lane's points share that maximum.
+template <int S, bool TIES>
+__device__ __forceinline__ void rescan_head(const float2* __restrict__ sxy, const float* __restrict__ sz, int tid,
+                                            const float (&zr)[PZR], float (&td)[PP],
+                                            float lx, float ly, float lz, float& best, int& bq, int& same, float& bx,
+                                            float& by, float& bz) {
+  float xs[PQ], ys[PQ], z[PQ];
+#pragma unroll
+  for (int q = 0; q < PQ; ++q) {
+    const int i = S * PQ + q;
+    const float2 v = sxy[i * PT + tid];
+    xs[q] = v.x; ys[q] = v.y;
+    z[q] = i < PZR ? zr[i < PZR ? i : 0] : sz[(i - PZR) * PT + tid];
+    td[i] = fminf(d2_ref_gpu(v.x - lx, v.y - ly, z[q] - lz), td[i]);
+  }
+  best = fmaxf(fmaxf(fmaxf(td[S * PQ], td[S * PQ + 1]), fmaxf(td[S * PQ + 2], td[S * PQ + 3])), td[S * PQ + 4]);
+  bq = PQ - 1;
+  bx = xs[PQ - 1]; by = ys[PQ - 1]; bz = z[PQ - 1];
+  same = 0;
+#pragma unroll
+  for (int q = PQ - 2; q >= 0; --q)
+    if (td[S * PQ + q] == best) { bq = q; bx = xs[q]; by = ys[q]; bz = z[q]; }
+  if (TIES) {
+#pragma unroll
+    for (int q = 0; q < PQ; ++q) same += td[S * PQ + q] == best ? 1 : 0;
+  }
+}
+
+template <bool PROF, bool TIES, bool ABL>
 __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const float* __restrict__ xyz,
                                                            int* __restrict__ out, const int* __restrict__ flags,
-                                                           long long* __restrict__ prof, int* __restrict__ tie_out, int tie_rounds) {
+                                                           long long* __restrict__ prof, int* __restrict__ tie_out, int tie_rounds, int abl) {
   extern __shared__ __align__(16) unsigned char smem[];
   float2* sxy = reinterpret_cast<float2*>(smem + OFF_XY);
   uint16_t* stie = reinterpret_cast<uint16_t*>(smem + OFF_TIE);
-  int* s_hi = reinterpret_cast<int*>(smem + OFF_HI);
-  uint32_t* s_tk = reinterpret_cast<uint32_t*>(smem + OFF_TK);
+  int* s_whi = reinterpret_cast<int*>(smem + OFF_HI);
+  uint32_t* s_wkey = reinterpret_cast<uint32_t*>(smem + OFF_TK);
   float4* s_rec = reinterpret_cast<float4*>(smem + OFF_REC);
+  float4* s_wrec = reinterpret_cast<float4*>(smem + OFF_WREC);
   float* s_red = reinterpret_cast<float*>(smem + OFF_RED);
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem + OFF_HIST);
   uint16_t* skey = reinterpret_cast<uint16_t*>(smem + OFF_KEY);
@@ -172,28 +209,30 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
         tk[s * PQ + b + 1] = min(u, v);
       }
   }
-  float z[PP], td[PP];
+  float zr[PZR], td[PP];
   float blx = 0.f, bly = 0.f, blz = 0.f, bhx = 0.f, bhy = 0.f, bhz = 0.f;  // lane s: bounding box of sub-bucket s
+  float* sz = reinterpret_cast<float*>(smem + OFF_Z);
 #pragma unroll
   for (int s = 0; s < PS; ++s) {
     float l0 = INFINITY, l1 = INFINITY, l2 = INFINITY, h0 = -INFINITY, h1 = -INFINITY, h2 = -INFINITY;
 #pragma unroll
     for (int q = 0; q < PQ; ++q) {
       const int i = s * PQ + q;
-      float x = 0.f, y = 0.f;
+      float x = 0.f, y = 0.f, zi = 0.f;
       if (tk[i] != 0u) {
         const int k = tie_key_to_index(tk[i]);
-        x = pc[(size_t)k * 3]; y = pc[(size_t)k * 3 + 1]; z[i] = pc[(size_t)k * 3 + 2];
+        x = pc[(size_t)k * 3]; y = pc[(size_t)k * 3 + 1]; zi = pc[(size_t)k * 3 + 2];
         td[i] = 1e38f;  // tf_sampling_g.cu:118
         l0 = fminf(l0, x); h0 = fmaxf(h0, x);
         l1 = fminf(l1, y); h1 = fmaxf(h1, y);
-        l2 = fminf(l2, z[i]); h2 = fmaxf(h2, z[i]);
+        l2 = fminf(l2, zi); h2 = fmaxf(h2, zi);
       } else {
-        z[i] = 0.f;
         td[i] = -1.f;  // padding: min(d,-1) stays -1; a negative temp never wins a signed max against a real point
       }
       sxy[i * PT + tid] = make_float2(x, y);
       stie[i * PT + tid] = (uint16_t)tk[i];
+      if (i < PZR) zr[i < PZR ? i : 0] = zi;
+      else sz[(i - PZR) * PT + tid] = zi;
     }
     l0 = funmap(redux_min_s32(fmap(l0))); h0 = funmap(redux_max_s32(fmap(h0)));
     l1 = funmap(redux_min_s32(fmap(l1))); h1 = funmap(redux_max_s32(fmap(h1)));
@@ -203,141 +242,149 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
   __syncthreads();
 
   // ---------------------------------------------------------------- rounds
-  // Champion table (one entry per sub-bucket, two copies indexed by round parity): temp bits, tie key (+ bit 16: the
-  // champion's temp is shared by another point of the sub-bucket), coordinates.  A rescan's winning lane writes the
-  // entry of the CURRENT parity in place; the other copy is brought up to date one round later by lane s (after the
-  // barrier that ends every read of that copy) — so warps without an active sub-bucket publish nothing at all.
-  int chi = __float_as_int(-1.f);            // lane s (< PS): champion temp bits of sub-bucket s (for the bound test)
+  // Two-level champion cache.  Lane s (< PS) keeps the champion of "its" sub-bucket in registers: temp bits `chi` and a
+  // key `ckey` = tie key << 8 | table entry << 1 | (another point of the sub-bucket shares that temp); its coordinates
+  // sit in t_rec[entry], a table only the owning warp touches.  A warp that rescanned something re-elects the best of
+  // its PS champions (wwhi / wwk / wrec, uniform registers); EVERY warp publishes that warp champion every round into
+  // the copy of the 16-entry table selected by the round's parity (three predicated stores from registers) — no
+  // read-modify-write of shared tables, so the only hazard is write-after-read across rounds, which the parity removes.
+  // The end-of-round reduction is over PW = 16 warp champions.  What all 16 warps execute between two barriers costs
+  // issue slots as much as latency (4 warps per scheduler run the same code at the same time), so that part is kept
+  // to ~45 instructions; the picks go to global memory as raw keys and are decoded after the loop.
+  int chi = __float_as_int(-1.f);
+  uint32_t ckey = 0u;
+  int wwhi = (int)0x80000000;
+  uint32_t wwk = 0u;
+  float4 wrec = make_float4(0.f, 0.f, 0.f, 0.f);
   float lx = pc[0], ly = pc[1], lz = pc[2];  // last pick: index 0 (tf_sampling_g.cu:114-116)
-  if (tid == 0) oc[0] = 0;
   int first_tie = 0x7fffffff;  // first round whose arg-max was not unique (decided by the tie rule)
-  unsigned prev_mask = 0u;     // sub-buckets of this warp rescanned in the previous round
-  const int tb = warp * PS + (lane & (PS - 1));  // table entry of "my" sub-bucket (lanes < PS)
+  float4* t_rec = s_rec + warp * PS;   // this warp's PS sub-bucket champions {x, y, z, -}
 
   long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt0 = 0;
-#define PF_TICK(i)                 \
-  if (PROF) {                      \
-    const long long _t = clock64(); \
-    pacc[i] += _t - pt0;           \
-    pt0 = _t;                      \
+  // phase clock: the read is ordered after `dep` has been produced (a true point on the dependency chain)
+#define PF_TICK(i, dep)                                                                  \
+  if (PROF) {                                                                            \
+    long long _t;                                                                        \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(_t) : "r"((int)(dep)) : "memory");      \
+    pacc[i] += _t - pt0;                                                                 \
+    pt0 = _t;                                                                            \
   }
-  if (PROF) { pt0 = clock64(); pacc[6] = pt0 - t_begin; }
+  const long long t_setup = PROF ? clock64() - t_begin : 0;
+  if (PROF) pt0 = clock64();
 
   for (int r = 1; r < m; ++r) {
     const int par = r & 1;
-    int* t_hi = s_hi + par * PNB;
-    uint32_t* t_tk = s_tk + par * PNB;
-    float4* t_rec = s_rec + par * PNB;
-    // ---- entries written last round live in the other copy only: fetch them now, store after the bound test
-    const bool stale = lane < PS && ((prev_mask >> lane) & 1u);
-    int c_hi = 0;
-    uint32_t c_tk = 0u;
-    float4 c_rec = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (stale) { c_hi = s_hi[(par ^ 1) * PNB + tb]; c_tk = s_tk[(par ^ 1) * PNB + tb]; c_rec = s_rec[(par ^ 1) * PNB + tb]; }
-    // ---- which sub-buckets can change?  (lanes 0..7, one sub-bucket each)
+    // ---- which sub-buckets can change?  (lanes 0..7, one sub-bucket each; the other lanes compute on zeros)
     const float gx = fmaxf(fmaxf(blx - lx, lx - bhx), 0.f);
     const float gy = fmaxf(fmaxf(bly - ly, ly - bhy), 0.f);
     const float gz = fmaxf(fmaxf(blz - lz, lz - bhz), 0.f);
     const float bound = d2_ref_gpu(gx, gy, gz);
-    const bool act = lane < PS && (r == 1 || bound < __int_as_float(chi));
+    bool act = lane < PS && (r == 1 || bound < __int_as_float(chi));
+    if (ABL) act = act && (r == 1 || !(abl & 3));
     const unsigned mask = __ballot_sync(0xffffffffu, act);
-    if (stale) { t_hi[tb] = c_hi; t_tk[tb] = c_tk; t_rec[tb] = c_rec; }
-    __syncwarp();  // the copy above precedes this round's in-place writes of the same entries
-    PF_TICK(0)
+    PF_TICK(0, mask)
     if (PROF && mask) { pacc[4] += __popc(mask); pacc[5] += 1; }
-    // ---- rescan the active sub-buckets of this warp
-#pragma unroll
-    for (int s = 0; s < PS; ++s) {
-      if (mask & (1u << s)) {
-        float xs[PQ], ys[PQ];
-#pragma unroll
-        for (int q = 0; q < PQ; ++q) {
-          const int i = s * PQ + q;
-          const float2 v = sxy[i * PT + tid];
-          xs[q] = v.x; ys[q] = v.y;
-          td[i] = fminf(d2_ref_gpu(v.x - lx, v.y - ly, z[i] - lz), td[i]);
-        }
-        const float best = fmaxf(fmaxf(fmaxf(td[s * PQ], td[s * PQ + 1]), fmaxf(td[s * PQ + 2], td[s * PQ + 3])), td[s * PQ + 4]);
-        // first maximum in descending tie-key order = the reference's per-thread rule
-        int bq = PQ - 1;
-#pragma unroll
-        for (int q = PQ - 2; q >= 0; --q) bq = td[s * PQ + q] == best ? q : bq;
+    // ---- rescan the active sub-buckets of this warp, then re-elect the warp's champion
+    if (!ABL && mask) {   // (the ablation variant has no rescan code at all: measures the loop without its bulk)
+      auto elect = [&](int s, float best, int bq, int same, float bx, float by, float bz) {
         const uint32_t tkm = stie[(s * PQ + bq) * PT + tid];    // in flight beside the first reduction
         const int whi = redux_max_s32(__float_as_int(best));
         const bool mine = __float_as_int(best) == whi;
         const uint32_t wk = redux_max(mine ? ((tkm << 5) | (uint32_t)lane) : 0u);
-        bool dup = false;
-        if (TIES) {  // another point of the sub-bucket shares the champion's temp (another lane, or inside the lane)
-          int same = 0;
-#pragma unroll
-          for (int q = 0; q < PQ; ++q) same += td[s * PQ + q] == best ? 1 : 0;
+        // tie tracking: how many points of the sub-bucket sit at the champion's temp (off the election's chain)
+        // (votes, not redux.add: REDUX.SUM is far slower than the CREDUX min/max path)
+        bool shared = false;
+        if (TIES) {
           const unsigned mm = __ballot_sync(0xffffffffu, mine);
-          dup = (mm & (mm - 1u)) != 0u || __ballot_sync(0xffffffffu, mine && same > 1) != 0u;
+          shared = (mm & (mm - 1u)) != 0u || __ballot_sync(0xffffffffu, mine && same > 1) != 0u;
         }
-        if (mine && (wk & 31u) == (uint32_t)lane) {
-          float bx = xs[0], by = ys[0], bz = z[s * PQ];
-#pragma unroll
-          for (int q = 1; q < PQ; ++q)
-            if (bq == q) { bx = xs[q]; by = ys[q]; bz = z[s * PQ + q]; }
-          t_hi[warp * PS + s] = whi;
-          t_tk[warp * PS + s] = (wk >> 5) | (dup ? 0x10000u : 0u);
-          t_rec[warp * PS + s] = make_float4(bx, by, bz, 0.f);
+        if (mine && (wk & 31u) == (uint32_t)lane) t_rec[s] = make_float4(bx, by, bz, 0.f);
+        if (lane == s) {
+          chi = whi;
+          ckey = ((wk >> 5) << 8) | (uint32_t)((warp * PS + s) << 1) | (shared ? 1u : 0u);
         }
-        if (lane == s) chi = whi;
+      };
+      float best, bx, by, bz;
+      int bq, same;
+#define VNB_RESCAN(S)                                                                        \
+      if (mask & (1u << S)) {                                                                  \
+        rescan_head<S, TIES>(sxy, sz, tid, zr, td, lx, ly, lz, best, bq, same, bx, by, bz);    \
+        elect(S, best, bq, same, bx, by, bz);                                                  \
       }
+      VNB_RESCAN(0) VNB_RESCAN(1) VNB_RESCAN(2) VNB_RESCAN(3) VNB_RESCAN(4) VNB_RESCAN(5) VNB_RESCAN(6) VNB_RESCAN(7)
+#undef VNB_RESCAN
+      wwhi = redux_max_s32(lane < PS ? chi : (int)0x80000000);
+      const bool top = lane < PS && chi == wwhi;
+      wwk = redux_max(top ? ckey : 0u);
+      if (TIES) {
+        const unsigned tm = __ballot_sync(0xffffffffu, top);
+        if (tm & (tm - 1u)) wwk |= 1u;
+      }
+      __syncwarp();   // the winners' t_rec stores above are visible to the whole warp
+      wrec = t_rec[(wwk >> 1) & (PS - 1)];
     }
-    prev_mask = mask;
-    PF_TICK(1)
+    // ---- every warp publishes its champion (registers -> this round's copy of the table)
+    if (lane == PS) { s_whi[par * PW + warp] = wwhi; s_wkey[par * PW + warp] = wwk; }
+    if (lane == PS + 1) s_wrec[par * PW + warp] = wrec;
+    PF_TICK(1, wwk)
     __syncthreads();
-    PF_TICK(2)
-    // ---- every warp reduces the 128 champions (4 per lane): max temp, then max tie key among the holders
-    const int4 h = reinterpret_cast<const int4*>(t_hi)[lane];
-    const uint4 t = reinterpret_cast<const uint4*>(t_tk)[lane];
-    const int whi = redux_max_s32(max(max(h.x, h.y), max(h.z, h.w)));
-    // key: tie key (bits 8..23) | entry (bits 1..7) | shared-temp flag (bit 0); tie keys are unique per point
-    const uint32_t e0 = (uint32_t)lane << 3;
-    const uint32_t k0 = h.x == whi ? (((t.x & 0xffffu) << 8) | e0 | (t.x >> 16)) : 0u;
-    const uint32_t k1 = h.y == whi ? (((t.y & 0xffffu) << 8) | (e0 + 2u) | (t.y >> 16)) : 0u;
-    const uint32_t k2 = h.z == whi ? (((t.z & 0xffffu) << 8) | (e0 + 4u) | (t.z >> 16)) : 0u;
-    const uint32_t k3 = h.w == whi ? (((t.w & 0xffffu) << 8) | (e0 + 6u) | (t.w >> 16)) : 0u;
-    const uint32_t wk = redux_max(max(max(k0, k1), max(k2, k3)));
-    const float4 rec = t_rec[(wk >> 1) & 127u];
-    lx = rec.x; ly = rec.y; lz = rec.z;
-    if (TIES && r < tie_rounds && first_tie == 0x7fffffff && whi >= 0) {
-      const int cnt = (h.x == whi) + (h.y == whi) + (h.z == whi) + (h.w == whi);
-      const unsigned holders = __ballot_sync(0xffffffffu, cnt > 0), multi = __ballot_sync(0xffffffffu, cnt > 1);
-      if ((holders & (holders - 1u)) | multi | (wk & 1u)) first_tie = r;
+    PF_TICK(2, 0)
+    // ---- every warp reduces the 16 warp champions: max temp, then max tie key among the holders
+    const int hw = s_whi[par * PW + (lane & (PW - 1))];
+    const uint32_t kw = s_wkey[par * PW + (lane & (PW - 1))];
+    const int whi = redux_max_s32(hw);
+    const uint32_t wk = redux_max(hw == whi ? kw : 0u);
+    const float4 rec = s_wrec[par * PW + ((wk >> 4) & (PW - 1))];   // entry = warp * PS + s: the warp is entry >> 3
+    PF_TICK(3, wk)
+    if (!ABL || !(abl & 4)) { lx = rec.x; ly = rec.y; lz = rec.z; }
+    // keep the pick in vector registers: the compiler would otherwise move these warp-uniform values to uniform
+    // registers (R2UR) on the round's critical chain
+    asm volatile("" : "+f"(lx), "+f"(ly), "+f"(lz));
+    PF_TICK(6, __float_as_int(lx))
+    if (TIES && r < tie_rounds) {  // unique arg-max?  (several champions at the maximal temp, or one that won on its tie key)
+      const unsigned hm = __ballot_sync(0xffffffffu, hw == whi) & 0xffffu;
+      if (whi >= 0 && ((hm & (hm - 1u)) || (wk & 1u))) first_tie = min(first_tie, r);
     }
-    if (warp == (r & (PW - 1)) && lane == 0) oc[r] = tie_key_to_index(wk >> 8);
-    PF_TICK(3)
+    if (tid == 0) oc[r] = (int)(wk >> 8);   // raw tie key; decoded below
+    PF_TICK(7, first_tie)
   }
 #undef PF_TICK
+  __syncthreads();   // thread 0's stores of the raw keys are visible to the block
+  for (int r = tid; r < m; r += PT) oc[r] = r == 0 ? 0 : tie_key_to_index((uint32_t)oc[r]);
   if (TIES && tie_out != nullptr && tid == 0) tie_out[cloud] = first_tie;
   if (PROF && prof != nullptr && lane == 0 && cloud == 0) {
-    pacc[7] = clock64() - t_begin;
-    for (int i = 0; i < 8; ++i) prof[warp * 8 + i] = pacc[i];
+    // [0] bound test -> mask, [1] rescans, [2] barrier, [3] barrier -> winner key, [6] winner key -> pick coordinates,
+    // [7] tie bookkeeping + index store; [4] rescans, [5] rounds with a rescan; then setup and total cycles
+    for (int i = 0; i < 8; ++i) prof[warp * 10 + i] = pacc[i];
+    prof[warp * 10 + 8] = t_setup;
+    prof[warp * 10 + 9] = clock64() - t_begin;
   }
 }
 
 extern long long* g_fps_prof;
+int g_fps_dispatch = 0;  // (unused; kept so that old tuning scripts do not fail)
+int g_fps_ablate = 0;    // tuning "fps_ablate": timing experiments only (wrong results): 1 no rescans, 2 no bound test, 4 fixed pick
 
 int fps_pruned_capacity() { return PCAP; }
 
+template <bool PROF, bool TIES, bool ABL>
+static int launch_pruned(int b, int n, int m, const float* xyz, int* out, const int* flags, long long* prof, int* tie_out,
+                         int tie_rounds, cudaStream_t st, const char* what) {
+  VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<PROF, TIES, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
+  fps_pruned_kernel<PROF, TIES, ABL><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, prof, tie_out, tie_rounds, g_fps_ablate);
+  return check_launch(what);
+}
+
 int launch_fps_pruned(int b, int n, int m, const float* xyz, int* out, const int* flags, int* tie_out, int tie_rounds,
                       cudaStream_t st) {
-  if (g_fps_prof != nullptr && flags == nullptr) {
-    VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
-    fps_pruned_kernel<true, true><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, g_fps_prof, tie_out, tie_rounds);
-    return check_launch("farthest_point_sample (pruned, profiled)");
-  }
-  if (tie_out != nullptr) {
-    VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
-    fps_pruned_kernel<false, true><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, nullptr, tie_out, tie_rounds);
-    return check_launch("farthest_point_sample (pruned, tie tracking)");
-  }
-  VNB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRUNED_SMEM));
-  fps_pruned_kernel<false, false><<<b, PT, PRUNED_SMEM, st>>>(n, m, xyz, out, flags, nullptr, nullptr, 0);
-  return check_launch("farthest_point_sample (pruned)");
+  if (g_fps_prof != nullptr && flags == nullptr)
+    return launch_pruned<true, true, false>(b, n, m, xyz, out, flags, g_fps_prof, tie_out, tie_rounds, st, "farthest_point_sample (pruned, profiled)");
+  if (g_fps_ablate != 0)   // timing experiments only
+    return tie_out != nullptr ? launch_pruned<false, true, true>(b, n, m, xyz, out, flags, nullptr, tie_out, tie_rounds, st, "farthest_point_sample (ablation)")
+                              : launch_pruned<false, false, true>(b, n, m, xyz, out, flags, nullptr, nullptr, 0, st, "farthest_point_sample (ablation)");
+  if (tie_out != nullptr)
+    return launch_pruned<false, true, false>(b, n, m, xyz, out, flags, nullptr, tie_out, tie_rounds, st, "farthest_point_sample (pruned, tie tracking)");
+  return launch_pruned<false, false, false>(b, n, m, xyz, out, flags, nullptr, nullptr, 0, st, "farthest_point_sample (pruned)");
 }
 
 }  // namespace vnb

@@ -1,20 +1,28 @@
-// 3-D NMS for B200: score-rank sort -> warp-ballot IoU bitmask -> greedy pass on the bitmask -> global ordering.
+// Box decode + 3-D NMS for B200: ONE kernel, one CTA per cloud — decode -> score ranking -> exact pair filter ->
+// polygon clip of the surviving pairs -> greedy pass on the suppression bitmask; the last CTA to finish merges the
+// per-cloud kept lists (each already in score order) into the reference's global order.
 //
 // Reference: tf_ops/3d_nms/tf_nms3d.cpp (single CPU thread): candidates = boxes with objectness[1] > objectness[0]
 // (:230), popped from a max-heap on score over the whole batch (:222-234); a candidate is dropped if any
 // already-selected box OF THE SAME CLOUD has IoU3D > thr (:248-255); IoU3D = BEV convex-polygon clip area x
 // y-overlap / union (:178-192).  Greedy NMS is order-dependent only through the score order, so per cloud it is
 // "walk candidates by descending score; keep iff no kept earlier candidate overlaps" — computed here as:
-//   K1  per cloud: rank candidates by (score desc, box index asc)                      [O(k^2) compares, 1 CTA]
-//   K2  bit (p,q), q<p, = IOUGreaterThanThreshold(candidate p, earlier candidate q)    [one warp -> one 32-bit word
-//       via __ballot_sync; argument order (candidate, selected) as at :250 because the clip is not symmetric in float]
-//   K3  per cloud: one warp walks p = 0..ncand-1 with the kept-set as a bitmask in registers
-//   K4  rows (batch, box) of the survivors in global descending-score order (the reference's output order)
+//   1  rank candidates by (score desc, box index asc) on an order-preserving integer key (NaN scores sort last, so
+//      the order is total and every index stays in range — the reference's heap is memory-safe with NaN too)
+//   2  bit (p,q), q<p, = IOUGreaterThanThreshold(candidate p, earlier candidate q); argument order (candidate,
+//      selected) as at :250 because the clip is not symmetric in float.  A cheap EXACT rejection test on per-box
+//      summaries in shared memory drops almost every pair; the survivors are clipped one thread per pair
+//   3  one warp walks p = 0..ncand-1 with the kept-set as a bitmask in registers
+//   4  rows (batch, box) of the survivors in global descending-score order (the reference's output order): a k-way
+//      merge by rank — position in the own list + binary searches in the other lists, O(n log n), no re-sort
 // This translation unit is compiled with -fmad=false: the reference is g++ -O2 for generic x86-64 (no FMA), so
 // every float/double expression below must stay un-fused to reproduce its roundings.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
 #include <math.h>
+
+namespace cg = cooperative_groups;
 
 namespace vnb {
 
@@ -144,197 +152,412 @@ __device__ bool iou_greater_full(const float* bi, const float* bj, float thr) {
   return iou > thr;
 }
 
-// K1: per cloud, rank candidates by (score desc, index asc).  order[b][rank] = box, ncand[b].
-__global__ void nms_rank_kernel(int k, const float* __restrict__ scores, const float* __restrict__ obj,
-                                int* __restrict__ order, int* __restrict__ ncand, uint8_t* __restrict__ keep,
-                                int* __restrict__ out_count) {
-  extern __shared__ float s_sc[];  // k scores, then k candidate flags (as int)
-  int* s_c = reinterpret_cast<int*>(s_sc + k);
-  __shared__ int s_n;
-  const int b = blockIdx.x;
-  if (threadIdx.x == 0) s_n = 0;
-  if (b == 0 && threadIdx.x == 0) *out_count = 0;
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    s_sc[i] = scores[(size_t)b * k + i];
-    s_c[i] = obj[((size_t)b * k + i) * 2 + 1] > obj[((size_t)b * k + i) * 2] ? 1 : 0;  // :230
-    keep[(size_t)b * k + i] = 0;
+// ---------------------------------------------------------------------------------------------------------
+// box decode — model.py:100-129.  NH=12, NS=NC=10 (config.py:2-3).  Every float operation is spelled with a
+// round-to-nearest intrinsic, so the result does not depend on this translation unit's -fmad setting.
+constexpr int NH = 12, NS = 10, NC = 10, PCH = 5 + 2 * NH + 4 * NS + NC;
+__device__ void decode_one(int t, const float* __restrict__ pxyz, const float* __restrict__ pout,
+                           const float* __restrict__ mean_size, float* __restrict__ bboxes, float* __restrict__ scores,
+                           float* __restrict__ objectness, float* __restrict__ class_scores) {
+  const float* po = pout + (size_t)t * PCH;
+  // argmax = first maximal index (tf.argmax), model.py:115,122
+  int sc = 0;
+  float best = po[5 + 2 * NH];
+  for (int i = 1; i < NS; ++i) {
+    float v = po[5 + 2 * NH + i];
+    if (v > best) { best = v; sc = i; }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    if (!s_c[i]) continue;
-    const float si = s_sc[i];
-    int rank = 0;
-    for (int j = 0; j < k; ++j) rank += (s_c[j] && (s_sc[j] > si || (s_sc[j] == si && j < i))) ? 1 : 0;
-    order[(size_t)b * k + rank] = i;
-    atomicAdd(&s_n, 1);
+  int hc = 0;
+  best = po[5];
+  for (int i = 1; i < NH; ++i) {
+    float v = po[5 + i];
+    if (v > best) { best = v; hc = i; }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) ncand[b] = s_n;
+  float size[3];
+  for (int a = 0; a < 3; ++a) {
+    float res = po[5 + 2 * NH + NS + sc * 3 + a];
+    size[a] = __fmul_rn(mean_size[sc * 3 + a], fmaxf(__fadd_rn(1.0f, res), 1e-6f));  // :119
+  }
+  float cx = __fadd_rn(pxyz[t * 3 + 0], po[2]), cy = __fadd_rn(pxyz[t * 3 + 1], po[3]),
+        cz = __fadd_rn(pxyz[t * 3 + 2], po[4]);  // :121
+  float hres = po[5 + NH + hc];
+  const float PI_F = 3.14159265358979323846f;
+  float ang = __fdiv_rn(__fmul_rn(__fadd_rn(__fmul_rn((float)hc, 2.0f), hres), PI_F), (float)NH);
+  const float TWO_PI = __fmul_rn(2.0f, PI_F);
+  // tf.floormod: result takes the sign of the divisor
+  float heading = fmodf(ang, TWO_PI);
+  if (heading < 0.0f) heading = __fadd_rn(heading, TWO_PI);
+  float c = cosf(heading), s = sinf(heading);
+  float l = size[0], w = size[1], h = size[2];  // lwh (x,z,y) order, model.py:108
+  const float sx[8] = {1, 1, -1, -1, 1, 1, -1, -1};
+  const float sy[8] = {1, 1, 1, 1, -1, -1, -1, -1};
+  const float sz[8] = {1, -1, -1, 1, 1, -1, -1, 1};
+  float* bb = bboxes + (size_t)t * 24;
+  for (int k = 0; k < 8; ++k) {
+    float x = __fmul_rn(sx[k], __fmul_rn(l, 0.5f)), y = __fmul_rn(sy[k], __fmul_rn(h, 0.5f)),
+          z = __fmul_rn(sz[k], __fmul_rn(w, 0.5f));
+    // rotation [[c,0,s],[0,1,0],[-s,0,c]] (model.py:107), einsum 'ijkl,ijlm->ijmk'
+    bb[k * 3 + 0] = __fadd_rn(__fadd_rn(__fmul_rn(c, x), __fmul_rn(s, z)), cx);
+    bb[k * 3 + 1] = __fadd_rn(y, cy);
+    bb[k * 3 + 2] = __fadd_rn(__fadd_rn(__fmul_rn(-s, x), __fmul_rn(c, z)), cz);
+  }
+  float mx = po[PCH - NC];
+  for (int i = 0; i < NC; ++i) {
+    float v = po[PCH - NC + i];
+    class_scores[(size_t)t * NC + i] = v;
+    mx = fmaxf(mx, v);
+  }
+  scores[t] = mx;
+  objectness[t * 2 + 0] = po[0];
+  objectness[t * 2 + 1] = po[1];
 }
 
-// K2: mask[b][p][w] bit (q & 31), q = 32 w + lane < p  <=>  candidate p is suppressed by earlier candidate q.
-// The polygon clip is a long divergent chain, but almost every pair is rejected by the cheap exact test above, so the
-// work is split: K2a runs the cheap test for every pair (one warp per candidate p, lanes over q) and compacts the
-// survivors into one global list (warp ballot -> shared list per CTA -> one global reservation per CTA); K2b runs the
-// clip on the dense list, one thread per surviving pair, and sets mask bits with atomicOr (bits are positional, so
-// the list order is irrelevant).
-constexpr int K2A_WARPS = 8;
-__global__ void __launch_bounds__(K2A_WARPS * 32) nms_pairs_kernel(int k, const float* __restrict__ bbox,
-                                                                    const int* __restrict__ order,
-                                                                    const int* __restrict__ ncand,
-                                                                    uint2* __restrict__ pairs, unsigned* __restrict__ npairs) {
-  __shared__ uint32_t s_list[K2A_WARPS * 1024];  // k <= 1024: at most k survivors per candidate
-  __shared__ unsigned s_n, s_base;
-  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int p = blockIdx.x * K2A_WARPS + warp;
-  const int nc = ncand[b];
-  if (blockIdx.x * K2A_WARPS >= nc) return;  // whole CTA
-  if (threadIdx.x == 0) s_n = 0;
-  __syncthreads();
-  if (p < nc) {
-    const float* bi = bbox + ((size_t)b * k + order[(size_t)b * k + p]) * 24;
-    for (int q0 = 0; q0 < p; q0 += 32) {
-      const int q = q0 + lane;
-      const bool sv = q < p && !iou_trivially_false(bi, bbox + ((size_t)b * k + order[(size_t)b * k + q]) * 24);
-      const unsigned m = __ballot_sync(0xffffffffu, sv);
-      unsigned base = 0;
-      if (lane == 0 && m) base = atomicAdd(&s_n, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (sv) s_list[base + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)p << 16) | (uint32_t)q;
+__global__ void decode_kernel(int total, const float* __restrict__ pxyz, const float* __restrict__ pout,
+                              const float* __restrict__ mean_size, float* __restrict__ bboxes,
+                              float* __restrict__ scores, float* __restrict__ objectness,
+                              float* __restrict__ class_scores) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < total) decode_one(t, pxyz, pout, mean_size, bboxes, scores, objectness, class_scores);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Score key: order-preserving map float -> uint32 for non-NaN values (with -0 == +0, as `<` on floats has it);
+// NaN -> 0, below every number.  Comparing keys is a TOTAL order, so the ranks below are a permutation whatever the
+// scores hold (with float comparisons a NaN score left order[] entries unwritten).
+__device__ __forceinline__ uint32_t score_key(float s) {
+  if (s != s) return 0u;
+  const uint32_t u = __float_as_uint(s == 0.f ? 0.f : s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// per-box summary for the exact rejection test (iou_trivially_false on precomputed extrema)
+struct BoxSum { float top, bot, lox, hix, loz, hiz, mag, nan; };
+
+__device__ __forceinline__ BoxSum summarize(const float* bb) {
+  BoxSum s;
+  s.top = bb[1]; s.bot = bb[13];
+  s.lox = bb[0]; s.hix = bb[0]; s.loz = bb[2]; s.hiz = bb[2];
+  bool nan = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i) {
+      s.lox = fminf(s.lox, bb[i * 3]); s.hix = fmaxf(s.hix, bb[i * 3]);
+      s.loz = fminf(s.loz, bb[i * 3 + 2]); s.hiz = fmaxf(s.hiz, bb[i * 3 + 2]);
     }
+    nan = nan || bb[i * 3] != bb[i * 3] || bb[i * 3 + 2] != bb[i * 3 + 2];
   }
-  __syncthreads();
-  const unsigned n = s_n;
-  if (threadIdx.x == 0 && n) s_base = atomicAdd(npairs, n);
-  __syncthreads();
-  for (unsigned t = threadIdx.x; t < n; t += blockDim.x) pairs[s_base + t] = make_uint2((unsigned)b, s_list[t]);
+  s.mag = fmaxf(fmaxf(fabsf(s.lox), fabsf(s.hix)), fmaxf(fabsf(s.loz), fabsf(s.hiz)));
+  s.nan = nan ? 1.f : 0.f;
+  return s;
+}
+// same boolean as iou_trivially_false(bi, bj) — fminf / fmaxf are exact and associative, so the extrema and `mag`
+// are the same floats whether they are folded per box or per pair
+__device__ __forceinline__ bool sum_trivially_false(const BoxSum& a, const BoxSum& b) {
+  const float h = NMS_MIN(a.top, b.top) - NMS_MAX(a.bot, b.bot);
+  if (!(h > 0.f)) return true;
+  const float mag = fmaxf(a.mag, b.mag);
+  const float eps = 1e-4f * mag;
+  if (a.nan != 0.f || b.nan != 0.f || !(mag < 1e30f)) return false;
+  return a.hix + eps < b.lox || b.hix + eps < a.lox || a.hiz + eps < b.loz || b.hiz + eps < a.loz;
 }
 
-__global__ void __launch_bounds__(128) nms_clip_kernel(int k, int W, float thr, const float* __restrict__ bbox,
-                                                        const int* __restrict__ order, const uint2* __restrict__ pairs,
-                                                        const unsigned* __restrict__ npairs, uint32_t* __restrict__ mask) {
-  const unsigned n = *npairs;
-  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    const uint2 pr = pairs[t];
-    const int b = (int)pr.x, p = (int)(pr.y >> 16), q = (int)(pr.y & 0xffffu);
-    const float* bi = bbox + ((size_t)b * k + order[(size_t)b * k + p]) * 24;   // argument order (candidate, selected), :250
-    const float* bj = bbox + ((size_t)b * k + order[(size_t)b * k + q]) * 24;
-    if (iou_greater_full(bi, bj, thr)) atomicOr(&mask[((size_t)b * k + p) * W + (q >> 5)], 1u << (q & 31));
+// Number of entries of a list sorted by descending key that precede an entry with key `key` coming from ANOTHER list:
+// keys greater than it, plus equal keys when the other list is the earlier one (exact score ties are ordered by
+// ascending (batch, box), and an earlier list holds the smaller batch ids).
+template <class KeyAt>
+__device__ __forceinline__ int count_preceding(KeyAt key_at, int n, uint32_t key, bool other_first) {
+  int lo = 0, hi = n;  // first position whose key does not precede
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const uint32_t km = key_at(mid);
+    if (km > key || (other_first && km == key)) lo = mid + 1;
+    else hi = mid;
   }
+  return lo;
 }
 
-// K3: greedy pass.  One CTA per cloud stages the cloud's bitmask rows in shared memory; warp 0 walks them with the
-// kept-set held as W<=32 words, one per lane.
-__global__ void __launch_bounds__(256) nms_greedy_kernel(int k, int W, const int* __restrict__ order,
-                                                          const int* __restrict__ ncand,
-                                                          const uint32_t* __restrict__ mask, uint8_t* __restrict__ keep,
-                                                          uint8_t* __restrict__ kept_pos, int* __restrict__ out_count) {
-  extern __shared__ uint32_t s_mask[];
-  const int b = blockIdx.x;
-  const int nc = ncand[b];
-  for (int t = threadIdx.x; t < nc * W; t += blockDim.x) s_mask[t] = mask[(size_t)b * k * W + t];
-  __syncthreads();
-  if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
-  uint32_t kept = 0;
-  int nkept = 0;
-  for (int p = 0; p < nc; ++p) {
-    uint32_t v = (lane < W) ? (s_mask[p * W + lane] & kept) : 0u;
-    if (!__any_sync(0xffffffffu, v != 0u)) {
-      if (lane == (p >> 5)) kept |= 1u << (p & 31);
-      if (lane == 0) keep[(size_t)b * k + order[(size_t)b * k + p]] = 1;
-      ++nkept;
-    }
-  }
-  (void)kept_pos; (void)out_count; (void)nkept;
-}
+constexpr int NMS_T = 512;          // threads per cloud CTA
+constexpr int NMS_LIST = 8192;      // surviving pairs staged per pass
 
-// K4: global order of the survivors: descending score, exact ties by ascending (batch, box).  Also used to merge an
-// all-gathered set of per-rank records (strided fields, vnb_merge_detections).  Every CTA compacts the kept entries into
-// its shared memory in flat-index order (ballot + prefix; cheap and redundant), then the CTAs split the O(nkept^2)
-// ranking: CTA c ranks compacted entries c*256+tid, (c+G)*256+tid, ...
-__global__ void __launch_bounds__(256) rank_emit_kernel(int world, int per_rank, int k, const char* __restrict__ sc_base,
-                                                          size_t sc_stride, const char* __restrict__ kp_base,
-                                                          size_t kp_stride, int* __restrict__ out_idx,
-                                                          int* __restrict__ out_count) {
-  extern __shared__ __align__(16) char s_dyn[];
-  const int total = world * per_rank;
-  float* s_sc = reinterpret_cast<float*>(s_dyn);
-  int* s_id = reinterpret_cast<int*>(s_sc + total);
-  __shared__ int s_wcnt[8];
-  __shared__ int s_base;
+struct NmsSmem {  // dynamic shared memory layout for k boxes, W = ceil(k/32) mask words per row
+  static __host__ __device__ size_t sum_off() { return 0; }
+  static __host__ __device__ size_t key_off(int k) { return (size_t)k * sizeof(BoxSum); }
+  static __host__ __device__ size_t order_off(int k) { return key_off(k) + (size_t)k * 4; }
+  static __host__ __device__ size_t kept_off(int k) { return order_off(k) + (size_t)k * 4; }
+  static __host__ __device__ size_t mask_off(int k) { return kept_off(k) + (size_t)k * 4; }
+  static __host__ __device__ size_t list_off(int k) { return mask_off(k) + (size_t)k * ((k + 31) / 32) * 4; }
+  static __host__ __device__ size_t bytes(int k) { return list_off(k) + (size_t)NMS_LIST * 4; }
+};
+
+// workspace (global): kept_key u32 [b][k] | kept_box i32 [b][k] | nk i32 [b] | done counter u32
+// A cloud is worked on by a CLUSTER of CTAs (8 for k >= 128, else 1): every CTA ranks the candidates (cheap, redundant),
+// the (candidate, earlier candidate) rows are dealt round-robin to the cluster's warps, and the polygon clips — a long
+// divergent chain, the bulk of the work — run one thread per surviving pair across the whole cluster, setting bits of
+// the suppression mask that lives in the shared memory of the cluster's CTA 0 (distributed shared memory atomics).
+template <bool DECODE>
+__global__ void __launch_bounds__(NMS_T) nms_cloud_kernel(int k, float thr, const float* __restrict__ pxyz,
+                                                           const float* __restrict__ pout,
+                                                           const float* __restrict__ mean_size, float* bbox, float* scores,
+                                                           float* obj, float* class_scores, uint8_t* __restrict__ keep,
+                                                           int* __restrict__ out_idx, uint32_t* __restrict__ out_key,
+                                                           int* __restrict__ out_count, float* __restrict__ bboxes_pred,
+                                                           float* __restrict__ cls_pred, int* __restrict__ batch_idx,
+                                                           uint32_t* ws_key, int* ws_box, int* ws_nk, unsigned* ws_done) {
+  extern __shared__ __align__(16) unsigned char nsm[];
+  BoxSum* s_sum = reinterpret_cast<BoxSum*>(nsm + NmsSmem::sum_off());
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(nsm + NmsSmem::key_off(k));
+  int* s_order = reinterpret_cast<int*>(nsm + NmsSmem::order_off(k));         // rank -> box
+  int* s_kept = reinterpret_cast<int*>(nsm + NmsSmem::kept_off(k));           // candidate flags, later kept rank positions
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(nsm + NmsSmem::mask_off(k));
+  uint32_t* s_list = reinterpret_cast<uint32_t*>(nsm + NmsSmem::list_off(k));
+  __shared__ int s_nc, s_nk, s_nlist, s_last;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
+  const int b = blockIdx.x / CL, ncloud = gridDim.x / CL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int c0 = 0; c0 < total; c0 += 256) {
-    const int e = c0 + tid;
-    bool kept = false;
-    float sc = 0.f;
-    if (e < total) {
-      const int r = e / per_rank, l = e % per_rank;
-      kept = *reinterpret_cast<const uint8_t*>(kp_base + r * kp_stride + l) != 0;
-      sc = *reinterpret_cast<const float*>(sc_base + r * sc_stride + (size_t)l * 4);
-    }
-    const unsigned bm = __ballot_sync(0xffffffffu, kept);
-    if (lane == 0) s_wcnt[warp] = __popc(bm);
-    __syncthreads();
-    int off = s_base;
-    for (int w = 0; w < warp; ++w) off += s_wcnt[w];
-    if (kept) {
-      const int pos = off + __popc(bm & ((1u << lane) - 1u));
-      s_sc[pos] = sc;
-      s_id[pos] = e;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int t = 0;
-      for (int w = 0; w < 8; ++w) t += s_wcnt[w];
-      s_base += t;
-    }
-    __syncthreads();
+  const int W = (k + 31) / 32;
+  float* cb = bbox + (size_t)b * k * 24;
+  if (tid == 0) { s_nc = 0; s_nk = 0; s_nlist = 0; }
+  // ---- decode (fused entry point; every CTA of the cluster writes the same values) + per-box summaries, keys, flags
+  for (int i = tid; i < k; i += NMS_T) {
+    const int t = b * k + i;
+    if (DECODE) decode_one(t, pxyz, pout, mean_size, bbox, scores, obj, class_scores);
+    s_sum[i] = summarize(cb + (size_t)i * 24);
+    const bool cand = obj[(size_t)t * 2 + 1] > obj[(size_t)t * 2];   // :230
+    s_key[i] = score_key(scores[t]);
+    s_kept[i] = cand ? 1 : 0;
   }
-  const int nk = s_base;
-  // rank of entry i = number of entries that precede it; entries are dealt to the CTAs round-robin so every CTA of the
-  // grid has work; the scan reads four entries per shared-memory load (pad entries never precede anything)
-  const bool vec = (total & 3) == 0;
-  const int nk4 = vec ? ((nk + 3) & ~3) : nk;
-  if (tid < nk4 - nk) { s_sc[nk + tid] = -INFINITY; s_id[nk + tid] = 0x7fffffff; }
   __syncthreads();
-  for (int i = (int)blockIdx.x + (int)gridDim.x * tid; i < nk; i += (int)gridDim.x * 256) {
-    const float se = s_sc[i];
-    const int e = s_id[i];
+  // ---- 1. rank of candidate i = candidates that precede it (greater key, or equal key and smaller index)
+  for (int i = tid; i < k; i += NMS_T) {
+    if (!s_kept[i]) continue;
+    const uint32_t ki = s_key[i];
     int rank = 0;
-    if (vec) {
-      for (int j = 0; j < nk4; j += 4) {
-        const float4 sj = *reinterpret_cast<const float4*>(s_sc + j);
-        const int4 ij = *reinterpret_cast<const int4*>(s_id + j);
-        rank += ((sj.x > se) | ((sj.x == se) & (ij.x < e))) + ((sj.y > se) | ((sj.y == se) & (ij.y < e))) +
-                ((sj.z > se) | ((sj.z == se) & (ij.z < e))) + ((sj.w > se) | ((sj.w == se) & (ij.w < e)));
-      }
-    } else {
-      for (int j = 0; j < nk; ++j) rank += (s_sc[j] > se) | ((s_sc[j] == se) & (s_id[j] < e));
-    }
-    out_idx[rank * 2 + 0] = e / k;
-    out_idx[rank * 2 + 1] = e % k;
+    for (int j = 0; j < k; ++j) rank += (s_kept[j] && (s_key[j] > ki || (s_key[j] == ki && j < i))) ? 1 : 0;
+    s_order[rank] = i;
+    atomicAdd(&s_nc, 1);
   }
-  if (tid == 0 && blockIdx.x == 0) *out_count = nk;
+  __syncthreads();
+  const int nc = s_nc;
+  if (cr == 0)
+    for (int t = tid; t < nc * W; t += NMS_T) s_mask[t] = 0u;
+  cluster.sync();   // CTA 0's mask is zeroed before anyone sets a bit in it
+  uint32_t* mask0 = cluster.map_shared_rank(s_mask, 0);
+  // ---- 2. pair filter + clip.  This CTA owns rows p = 1 + cr, 1 + cr + CL, ...; passes of rows whose pairs fit the list
+  for (int p0 = 1 + cr; p0 < nc;) {
+    int p1 = p0, tot = 0;
+    while (p1 < nc && tot + p1 <= NMS_LIST) { tot += p1; p1 += CL; }
+    for (int p = p0 + warp * CL; p < p1; p += (NMS_T / 32) * CL) {
+      const BoxSum sp = s_sum[s_order[p]];
+      for (int q0 = 0; q0 < p; q0 += 32) {
+        const int q = q0 + lane;
+        const bool sv = q < p && !sum_trivially_false(sp, s_sum[s_order[q]]);
+        const unsigned m = __ballot_sync(0xffffffffu, sv);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_nlist, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (sv) s_list[base + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)p << 16) | (uint32_t)q;
+      }
+    }
+    __syncthreads();
+    const int nl = s_nlist;
+    for (int t = tid; t < nl; t += NMS_T) {
+      const int p = (int)(s_list[t] >> 16), q = (int)(s_list[t] & 0xffffu);
+      // argument order (candidate, selected), :250
+      if (iou_greater_full(cb + (size_t)s_order[p] * 24, cb + (size_t)s_order[q] * 24, thr))
+        atomicOr(&mask0[p * W + (q >> 5)], 1u << (q & 31));
+    }
+    __syncthreads();
+    if (tid == 0) s_nlist = 0;
+    p0 = p1;
+    __syncthreads();
+  }
+  cluster.sync();   // every bit is set; CTA 0 finishes the cloud, the others are done
+  if (cr != 0) return;
+  // ---- 3. greedy pass: warp 0, kept-set as W <= 32 words (one per lane); keep mask written by everyone afterwards
+  if (warp == 0) {
+    uint32_t kept = 0;
+    int nk = 0;
+    uint32_t row = (nc > 0 && lane < W) ? s_mask[lane] : 0u;
+    for (int p = 0; p < nc; ++p) {
+      const uint32_t nxt = (p + 1 < nc && lane < W) ? s_mask[(p + 1) * W + lane] : 0u;   // prefetch: independent of `kept`
+      if (!__any_sync(0xffffffffu, (row & kept) != 0u)) {
+        if (lane == (p >> 5)) kept |= 1u << (p & 31);
+        if (lane == 0) s_kept[nk] = p;
+        ++nk;
+      }
+      row = nxt;
+    }
+    if (lane == 0) s_nk = nk;
+  }
+  __syncthreads();
+  const int nk = s_nk;
+  for (int i = tid; i < k; i += NMS_T) keep[(size_t)b * k + i] = 0;
+  __syncthreads();
+  for (int j = tid; j < nk; j += NMS_T) {
+    const int box = s_order[s_kept[j]];
+    keep[(size_t)b * k + box] = 1;
+    ws_key[(size_t)b * k + j] = s_key[box];
+    ws_box[(size_t)b * k + j] = box;
+  }
+  if (tid == 0) ws_nk[b] = nk;
+  // ---- 4. the last CTA to get here merges the per-cloud kept lists into the global order
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(ws_done, 1u) == (unsigned)ncloud - 1u) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int B = ncloud;
+  // stage every list's keys in shared memory when they fit (the mask / list area is free now); else search in L2
+  uint32_t* s_all = reinterpret_cast<uint32_t*>(nsm);
+  const size_t cap = NmsSmem::bytes(k) / 4;
+  int total = 0;
+  for (int c = 0; c < B; ++c) total += __ldcg(ws_nk + c);
+  const bool staged = (size_t)total <= cap;
+  if (staged) {
+    int off = 0;
+    for (int c = 0; c < B; ++c) {
+      const int n = __ldcg(ws_nk + c);
+      for (int j = tid; j < n; j += NMS_T) s_all[off + j] = __ldcg(ws_key + (size_t)c * k + j);
+      off += n;
+    }
+  }
+  __syncthreads();
+  int offc = 0;
+  for (int c = 0; c < B; ++c) {
+    const int n = __ldcg(ws_nk + c);
+    for (int j = tid; j < n; j += NMS_T) {
+      const uint32_t key = staged ? s_all[offc + j] : __ldcg(ws_key + (size_t)c * k + j);
+      int rank = j, off2 = 0;
+      for (int c2 = 0; c2 < B; ++c2) {
+        const int n2 = __ldcg(ws_nk + c2);
+        if (c2 != c) {
+          if (staged) rank += count_preceding([&](int i) { return s_all[off2 + i]; }, n2, key, c2 < c);
+          else rank += count_preceding([&](int i) { return __ldcg(ws_key + (size_t)c2 * k + i); }, n2, key, c2 < c);
+        }
+        off2 += n2;
+      }
+      const int box = __ldcg(ws_box + (size_t)c * k + j);
+      out_idx[rank * 2 + 0] = c;
+      out_idx[rank * 2 + 1] = box;
+      if (out_key != nullptr) out_key[rank] = key;
+      if (batch_idx != nullptr) batch_idx[rank] = c;                                  // model.py:137
+      if (bboxes_pred != nullptr) {                                                   // model.py:135
+        const float4* src = reinterpret_cast<const float4*>(bbox + ((size_t)c * k + box) * 24);
+        float4* dst = reinterpret_cast<float4*>(bboxes_pred + (size_t)rank * 24);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dst[i] = __ldcg(src + i);
+      }
+      if (cls_pred != nullptr) {                                                      // model.py:136
+        const float2* src = reinterpret_cast<const float2*>(class_scores + ((size_t)c * k + box) * 10);
+        float2* dst = reinterpret_cast<float2*>(cls_pred + (size_t)rank * 10);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) dst[i] = __ldcg(src + i);
+      }
+    }
+    offc += n;
+  }
+  if (tid == 0) { *out_count = total; *ws_done = 0u; }   // counter re-armed for the next launch on this workspace
 }
 
-static int launch_rank_emit(int world, int per_rank, int k, const char* sc, size_t scs, const char* kp, size_t kps,
-                            int* out_idx, int* out_count, cudaStream_t st) {
-  const size_t smem = (size_t)world * per_rank * 8;
-  if (smem > 200 * 1024) return set_err(VNB_ERR_INVALID, "nms: more than 25600 boxes in one ordering pass");
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(rank_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_err(VNB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+// Merge `L` lists, each sorted by descending key (rows (batch, box) + keys + count inside a record of `stride` bytes),
+// into the global order; list l holds batches [l*b, (l+1)*b).  Optionally gathers the kept rows' boxes / class scores /
+// batch ids (model.py:135-137).  One thread per entry; every CTA stages all keys in shared memory when they fit.
+__global__ void __launch_bounds__(256) merge_lists_kernel(int L, int b, int k, const char* __restrict__ base, size_t stride,
+                                                          size_t off_idx, size_t off_key, size_t off_count,
+                                                          size_t off_bboxes, size_t off_cls, int* __restrict__ out_idx,
+                                                          int* __restrict__ out_count, float* __restrict__ bboxes_pred,
+                                                          float* __restrict__ cls_pred, int* __restrict__ batch_idx,
+                                                          int smem_words) {
+  extern __shared__ uint32_t s_all[];
+  __shared__ int s_cnt[64];   // L <= 64
+  const int tid = threadIdx.x;
+  if (tid < L) s_cnt[tid] = min(max(*reinterpret_cast<const int*>(base + tid * stride + off_count), 0), b * k);
+  __syncthreads();
+  int total = 0;
+  for (int l = 0; l < L; ++l) total += s_cnt[l];
+  if (blockIdx.x == 0 && tid == 0) *out_count = total;
+  const int e0 = blockIdx.x * 256;
+  if (e0 >= total) return;
+  const bool staged = total <= smem_words;
+  if (staged) {
+    int off = 0;
+    for (int l = 0; l < L; ++l) {
+      const uint32_t* kl = reinterpret_cast<const uint32_t*>(base + l * stride + off_key);
+      for (int j = tid; j < s_cnt[l]; j += 256) s_all[off + j] = kl[j];
+      off += s_cnt[l];
+    }
+    __syncthreads();
   }
-  int grid = (world * per_rank + 63) / 64;
-  if (grid > 32) grid = 32;
-  rank_emit_kernel<<<grid, 256, smem, st>>>(world, per_rank, k, sc, scs, kp, kps, out_idx, out_count);
-  return check_launch("nms3d order");
+  const int e = e0 + tid;
+  if (e >= total) return;
+  int l = 0, j = e, offl = 0;
+  while (j >= s_cnt[l]) { j -= s_cnt[l]; offl += s_cnt[l]; ++l; }
+  const char* rl = base + l * stride;
+  const uint32_t key = staged ? s_all[offl + j] : reinterpret_cast<const uint32_t*>(rl + off_key)[j];
+  int rank = j, off2 = 0;
+  for (int l2 = 0; l2 < L; ++l2) {
+    const int n2 = s_cnt[l2];
+    if (l2 != l) {
+      const uint32_t* k2 = reinterpret_cast<const uint32_t*>(base + l2 * stride + off_key);
+      if (staged) rank += count_preceding([&](int i) { return s_all[off2 + i]; }, n2, key, l2 < l);
+      else rank += count_preceding([&](int i) { return k2[i]; }, n2, key, l2 < l);
+    }
+    off2 += n2;
+  }
+  const int* il = reinterpret_cast<const int*>(rl + off_idx);
+  const int lb = il[j * 2], box = il[j * 2 + 1];
+  out_idx[rank * 2 + 0] = l * b + lb;
+  out_idx[rank * 2 + 1] = box;
+  if (batch_idx != nullptr) batch_idx[rank] = l * b + lb;
+  if (bboxes_pred != nullptr) {
+    const float4* src = reinterpret_cast<const float4*>(rl + off_bboxes + ((size_t)lb * k + box) * 96);
+    float4* dst = reinterpret_cast<float4*>(bboxes_pred + (size_t)rank * 24);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dst[i] = src[i];
+  }
+  if (cls_pred != nullptr) {
+    const float2* src = reinterpret_cast<const float2*>(rl + off_cls + ((size_t)lb * k + box) * 40);
+    float2* dst = reinterpret_cast<float2*>(cls_pred + (size_t)rank * 10);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dst[i] = src[i];
+  }
 }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+template <bool DECODE>
+static int launch_nms_cloud(int b, int k, float thr, const float* pxyz, const float* pout, const float* mean_size,
+                            float* bbox, float* scores, float* obj, float* cls, uint8_t* keep, int* out_idx,
+                            uint32_t* out_key, int* out_count, float* bboxes_pred, float* cls_pred, int* batch_idx,
+                            void* workspace, cudaStream_t st) {
+  char* ws = static_cast<char*>(workspace);
+  uint32_t* ws_key = reinterpret_cast<uint32_t*>(ws);
+  int* ws_box = reinterpret_cast<int*>(ws + align256((size_t)b * k * 4));
+  int* ws_nk = reinterpret_cast<int*>(ws + 2 * align256((size_t)b * k * 4));
+  unsigned* ws_done = reinterpret_cast<unsigned*>(ws + 2 * align256((size_t)b * k * 4) + align256((size_t)b * 4));
+  VNB_CUDA(cudaMemsetAsync(ws_done, 0, sizeof(unsigned), st));   // a memset node, not a launch: the workspace may be fresh
+  const size_t smem = NmsSmem::bytes(k);
+  if (smem > 48 * 1024)
+    VNB_CUDA(cudaFuncSetAttribute(nms_cloud_kernel<DECODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  const int CL = k >= 128 ? 8 : 1;
+  cfg.gridDim = dim3((unsigned)(b * CL));
+  cfg.blockDim = dim3(NMS_T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  VNB_CUDA(cudaLaunchKernelEx(&cfg, nms_cloud_kernel<DECODE>, k, thr, pxyz, pout, mean_size, bbox, scores, obj, cls, keep,
+                              out_idx, out_key, out_count, bboxes_pred, cls_pred, batch_idx, ws_key, ws_box, ws_nk, ws_done));
+  return check_launch(DECODE ? "decode + nms3d" : "nms3d");
+}
 
 }  // namespace vnb
 
@@ -342,53 +565,74 @@ using namespace vnb;
 
 extern "C" size_t vnb_nms3d_workspace_bytes(int b, int k) {
   if (b <= 0 || k <= 0) return 256;
-  size_t W = (size_t)(k + 31) / 32;
-  return align256((size_t)b * k * 4) + align256((size_t)b * 4) + align256((size_t)b * k * W * 4) + 256 /* pair counter */ +
-         align256((size_t)b * k * (size_t)(k > 1 ? k - 1 : 1) / 2 * 8 + 8) /* surviving (candidate, earlier) pairs */;
+  return 2 * align256((size_t)b * k * 4) + align256((size_t)b * 4) + 256;
+}
+
+extern "C" int vnb_decode_boxes(int b, int k, const float* proposals_xyz, const float* proposals_output,
+                                const float* class_mean_size, float* bboxes, float* scores, float* objectness,
+                                float* class_scores, void* stream) {
+  VNB_REQUIRE(b >= 0 && k >= 0, "decode_boxes: bad shape");
+  const int total = b * k;
+  if (total == 0) return VNB_OK;
+  decode_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(total, proposals_xyz, proposals_output, class_mean_size,
+                                                                    bboxes, scores, objectness, class_scores);
+  return check_launch("decode_boxes");
+}
+
+static int nms_args_ok(int b, int k, float thr) {
+  VNB_REQUIRE(b >= 0 && k >= 0, "3D NMS expects (batch_size, nbbox, 8, 3) bbox shape.");            // tf_nms3d.cpp:287
+  VNB_REQUIRE(thr >= 0 && thr <= 1, "iou_threshold must be in [0, 1]");                             // :300
+  VNB_REQUIRE(k <= 1024, "nms3d: at most 1024 boxes per cloud (got %d)", k);
+  return VNB_OK;
 }
 
 extern "C" int vnb_nms3d(int b, int k, const float* bbox, const float* scores, const float* objectiveness,
                          float iou_threshold, uint8_t* keep, int* out_idx, int* out_count, void* workspace,
                          void* stream) {
-  VNB_REQUIRE(b >= 0 && k >= 0, "3D NMS expects (batch_size, nbbox, 8, 3) bbox shape.");            // tf_nms3d.cpp:287
-  VNB_REQUIRE(iou_threshold >= 0 && iou_threshold <= 1, "iou_threshold must be in [0, 1]");        // :300
-  VNB_REQUIRE(k <= 1024, "nms3d: at most 1024 boxes per cloud (got %d)", k);
+  if (int rc = nms_args_ok(b, k, iou_threshold)) return rc;
   cudaStream_t st = as_stream(stream);
   if (b == 0 || k == 0) {
     VNB_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int), st));
     return VNB_OK;
   }
-  const int W = (k + 31) / 32;
-  char* ws = static_cast<char*>(workspace);
-  int* order = reinterpret_cast<int*>(ws);
-  int* ncand = reinterpret_cast<int*>(ws + align256((size_t)b * k * 4));
-  uint32_t* mask = reinterpret_cast<uint32_t*>(ws + align256((size_t)b * k * 4) + align256((size_t)b * 4));
-  nms_rank_kernel<<<b, 256, (size_t)k * 8, st>>>(k, scores, objectiveness, order, ncand, keep, out_count);
-  if (int rc = check_launch("nms3d rank")) return rc;
-  unsigned* npairs = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(mask) + align256((size_t)b * k * W * 4));
-  uint2* pairs = reinterpret_cast<uint2*>(reinterpret_cast<char*>(npairs) + 256);
-  VNB_CUDA(cudaMemsetAsync(mask, 0, align256((size_t)b * k * W * 4) + 256, st));  // mask words + pair counter
-  nms_pairs_kernel<<<dim3((k + K2A_WARPS - 1) / K2A_WARPS, b), K2A_WARPS * 32, 0, st>>>(k, bbox, order, ncand, pairs, npairs);
-  if (int rc = check_launch("nms3d pairs")) return rc;
-  nms_clip_kernel<<<296, 128, 0, st>>>(k, W, iou_threshold, bbox, order, pairs, npairs, mask);
-  if (int rc = check_launch("nms3d clip")) return rc;
-  size_t smem = (size_t)k * W * 4;
-  if (smem > 48 * 1024)
-    VNB_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nms_greedy_kernel<<<b, 256, smem, st>>>(k, W, order, ncand, mask, keep, nullptr, out_count);
-  if (int rc = check_launch("nms3d greedy")) return rc;
-  return launch_rank_emit(1, b * k, k, reinterpret_cast<const char*>(scores), 0, reinterpret_cast<const char*>(keep), 0,
-                          out_idx, out_count, st);
+  return launch_nms_cloud<false>(b, k, iou_threshold, nullptr, nullptr, nullptr, const_cast<float*>(bbox),
+                                 const_cast<float*>(scores), const_cast<float*>(objectiveness), nullptr, keep, out_idx,
+                                 nullptr, out_count, nullptr, nullptr, nullptr, workspace, st);
 }
 
-extern "C" int vnb_merge_detections(int world, int b, int k, const void* gathered, size_t rank_stride,
-                                    size_t off_scores, size_t off_keep, int* out_idx, int* out_count, void* stream) {
-  VNB_REQUIRE(world > 0 && b >= 0 && k >= 0, "merge_detections: bad shape");
+extern "C" int vnb_decode_nms3d(int b, int k, const float* proposals_xyz, const float* proposals_output,
+                                const float* class_mean_size, float iou_threshold, float* bboxes, float* scores,
+                                float* objectness, float* class_scores, uint8_t* keep, int* out_idx, uint32_t* out_key,
+                                int* out_count, float* bboxes_pred, float* class_scores_pred, int* batch_idx,
+                                void* workspace, void* stream) {
+  if (int rc = nms_args_ok(b, k, iou_threshold)) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (b == 0 || k == 0) {
+    VNB_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int), st));
+    return VNB_OK;
+  }
+  return launch_nms_cloud<true>(b, k, iou_threshold, proposals_xyz, proposals_output, class_mean_size, bboxes, scores,
+                                objectness, class_scores, keep, out_idx, out_key, out_count, bboxes_pred, class_scores_pred,
+                                batch_idx, workspace, st);
+}
+
+extern "C" int vnb_merge_detections(int world, int b, int k, const void* gathered, size_t rank_stride, size_t off_idx,
+                                    size_t off_key, size_t off_count, size_t off_bboxes, size_t off_class_scores,
+                                    int* out_idx, int* out_count, float* bboxes_pred, float* class_scores_pred,
+                                    int* batch_idx, void* stream) {
+  VNB_REQUIRE(world > 0 && world <= 64 && b >= 0 && k >= 0, "merge_detections: bad shape (1 <= world <= 64)");
   cudaStream_t st = as_stream(stream);
   if (world * b * k == 0) {
     VNB_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int), st));
     return VNB_OK;
   }
-  const char* g = static_cast<const char*>(gathered);
-  return launch_rank_emit(world, b * k, k, g + off_scores, rank_stride, g + off_keep, rank_stride, out_idx, out_count, st);
+  const long long total = (long long)world * b * k;
+  size_t smem = (size_t)(total < 40960 ? total : 40960) * 4;   // stage every key when they fit in 160 KB
+  if (smem > 48 * 1024)
+    VNB_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)((total + 255) / 256);
+  merge_lists_kernel<<<grid, 256, smem, st>>>(world, b, k, static_cast<const char*>(gathered), rank_stride, off_idx, off_key,
+                                              off_count, off_bboxes, off_class_scores, out_idx, out_count, bboxes_pred,
+                                              class_scores_pred, batch_idx, (int)(smem / 4));
+  return check_launch("merge_detections");
 }

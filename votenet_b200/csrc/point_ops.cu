@@ -231,68 +231,6 @@ __global__ void split2_kernel(long long rows, int ca, int cb, const float* __res
   else b[r * cb + (l - ca)] = in[t];
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// box decode — model.py:100-129.  One thread per proposal.  NH=12, NS=NC=10 (config.py:2-3).
-constexpr int NH = 12, NS = 10, NC = 10, PCH = 5 + 2 * NH + 4 * NS + NC;
-__global__ void decode_kernel(int total, const float* __restrict__ pxyz, const float* __restrict__ pout,
-                              const float* __restrict__ mean_size, float* __restrict__ bboxes,
-                              float* __restrict__ scores, float* __restrict__ objectness,
-                              float* __restrict__ class_scores) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const float* po = pout + (size_t)t * PCH;
-  // argmax = first maximal index (tf.argmax), model.py:115,122
-  int sc = 0;
-  float best = po[5 + 2 * NH];
-  for (int i = 1; i < NS; ++i) {
-    float v = po[5 + 2 * NH + i];
-    if (v > best) { best = v; sc = i; }
-  }
-  int hc = 0;
-  best = po[5];
-  for (int i = 1; i < NH; ++i) {
-    float v = po[5 + i];
-    if (v > best) { best = v; hc = i; }
-  }
-  float size[3];
-  for (int a = 0; a < 3; ++a) {
-    float res = po[5 + 2 * NH + NS + sc * 3 + a];
-    size[a] = __fmul_rn(mean_size[sc * 3 + a], fmaxf(__fadd_rn(1.0f, res), 1e-6f));  // :119
-  }
-  float cx = __fadd_rn(pxyz[t * 3 + 0], po[2]), cy = __fadd_rn(pxyz[t * 3 + 1], po[3]),
-        cz = __fadd_rn(pxyz[t * 3 + 2], po[4]);  // :121
-  float hres = po[5 + NH + hc];
-  const float PI_F = 3.14159265358979323846f;
-  float ang = __fdiv_rn(__fmul_rn(__fadd_rn(__fmul_rn((float)hc, 2.0f), hres), PI_F), (float)NH);
-  const float TWO_PI = __fmul_rn(2.0f, PI_F);
-  // tf.floormod: result takes the sign of the divisor
-  float heading = fmodf(ang, TWO_PI);
-  if (heading < 0.0f) heading = __fadd_rn(heading, TWO_PI);
-  float c = cosf(heading), s = sinf(heading);
-  float l = size[0], w = size[1], h = size[2];  // lwh (x,z,y) order, model.py:108
-  const float sx[8] = {1, 1, -1, -1, 1, 1, -1, -1};
-  const float sy[8] = {1, 1, 1, 1, -1, -1, -1, -1};
-  const float sz[8] = {1, -1, -1, 1, 1, -1, -1, 1};
-  float* bb = bboxes + (size_t)t * 24;
-  for (int k = 0; k < 8; ++k) {
-    float x = __fmul_rn(sx[k], __fmul_rn(l, 0.5f)), y = __fmul_rn(sy[k], __fmul_rn(h, 0.5f)),
-          z = __fmul_rn(sz[k], __fmul_rn(w, 0.5f));
-    // rotation [[c,0,s],[0,1,0],[-s,0,c]] (model.py:107), einsum 'ijkl,ijlm->ijmk'
-    bb[k * 3 + 0] = __fadd_rn(__fadd_rn(__fmul_rn(c, x), __fmul_rn(s, z)), cx);
-    bb[k * 3 + 1] = __fadd_rn(y, cy);
-    bb[k * 3 + 2] = __fadd_rn(__fadd_rn(__fmul_rn(-s, x), __fmul_rn(c, z)), cz);
-  }
-  float mx = po[PCH - NC];
-  for (int i = 0; i < NC; ++i) {
-    float v = po[PCH - NC + i];
-    class_scores[(size_t)t * NC + i] = v;
-    mx = fmaxf(mx, v);
-  }
-  scores[t] = mx;
-  objectness[t * 2 + 0] = po[0];
-  objectness[t * 2 + 1] = po[1];
-}
-
 // Largest float t with sqrtf(t) < radius (host; IEEE sqrt is correctly rounded on both host and device).
 float ball_d2_max(float radius) {
   float t = radius * radius;
@@ -396,18 +334,6 @@ int vnb_split2(int rows, int ca, int cb, const float* in, float* a, float* b, vo
   if (total == 0) return VNB_OK;
   split2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(rows, ca, cb, in, a, b);
   return check_launch("split2");
-}
-
-int vnb_decode_boxes(int b, int k, const float* proposals_xyz, const float* proposals_output,
-                     const float* class_mean_size, float* bboxes, float* scores, float* objectness,
-                     float* class_scores, void* stream) {
-  VNB_REQUIRE(b >= 0 && k >= 0, "decode_boxes: bad shape");
-  int total = b * k;
-  if (total == 0) return VNB_OK;
-  decode_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(total, proposals_xyz, proposals_output,
-                                                                    class_mean_size, bboxes, scores, objectness,
-                                                                    class_scores);
-  return check_launch("decode_boxes");
 }
 
 }  // extern "C"

@@ -7,7 +7,8 @@ Same graph as `model.VoteNetB200.forward` (reference: /root/reference/model.py:3
   * the whole multi-stream forward is captured into one CUDA graph per slot;
   * `slots` independent workspaces (bench.py: 16) keep several forwards in flight: the sa1 FPS of a forward occupies
     8 SMs for 1.5 ms, the other 140 SMs run the feature chains of earlier forwards (DESIGN.md §5);
-  * the nested sampling levels use the provenance hint of the sa1 FPS (no proof kernels when it was tie-free), the FP
+  * the nested sampling levels sample prefixes of sa1's picks: the first one proves the identity prefix in parallel
+    (no tie tracking in the big sampler), the deeper ones and the proposal module are covered by that proof, the FP
     modules and the voting module run as one fused tensor-core kernel per FP level, the SA kernels get the ball
     query's hit counts and skip the padded duplicate rows;
   * detections are written straight into one contiguous record (the all-gather wire layout).
@@ -32,7 +33,9 @@ class DetectionRecord:
     FIELDS = (("bboxes", torch.float32, lambda b, k: (b, k, 8, 3)), ("scores", torch.float32, lambda b, k: (b, k)),
               ("class_scores", torch.float32, lambda b, k: (b, k, NC)), ("objectness", torch.float32, lambda b, k: (b, k, 2)),
               ("keep", torch.uint8, lambda b, k: (b, k)), ("nms_idx", torch.int32, lambda b, k: (b * k, 2)),
-              ("nms_count", torch.int32, lambda b, k: (1,)))
+              ("nms_key", torch.int32, lambda b, k: (b * k,)), ("nms_count", torch.int32, lambda b, k: (1,)))
+    # nms_idx / nms_key / nms_count = this rank's detections as a list sorted by descending score (rows (batch, box)
+    # + order-preserving score keys): what vnb_merge_detections merges across ranks without re-sorting
 
     def __init__(self, b, k, device=None, buf=None):
         self.b, self.k = b, k
@@ -157,9 +160,13 @@ class Engine:
         s.p_h = [E((B * p.npoint, co)) for co in p.mlp2]
         s.rec = DetectionRecord(B, p.npoint, dev)
         s.nms_ws = torch.empty((lib.vnb_nms3d_workspace_bytes(B, p.npoint),), dtype=torch.uint8, device=dev)
+        # the reference's three outputs (model.py:135-137) over this rank's batch; first rec.nms_count rows are valid
+        s.bboxes_pred, s.class_scores_pred = E((B * p.npoint, 8, 3)), E((B * p.npoint, NC))
+        s.batch_idx = E((B * p.npoint,), i32)
+        s.rec.bboxes_pred, s.rec.class_scores_pred, s.rec.batch_idx = s.bboxes_pred, s.class_scores_pred, s.batch_idx
         mmax = max(max(sa.npoint for sa in cfg.sa), cfg.proposal.npoint)
         s.sa_ws = torch.empty((lib.vnb_sa_workspace_bytes(B, mmax, 64),), dtype=torch.uint8, device=dev)
-        s.fps_tie = torch.zeros((B,), dtype=i32, device=dev)   # first non-unique round of the sa1 FPS, per cloud
+        s.fps_tie = torch.zeros((B,), dtype=i32, device=dev)   # rounds of the identity prefix proven at the sa2 level, per cloud
         s.fps_ws = torch.empty((lib.vnb_fps_nested_workspace_bytes(B, max(sa.npoint for sa in cfg.sa)),), dtype=torch.uint8, device=dev)
         s.done = torch.cuda.Event()
         s.samp = torch.cuda.Stream(device=dev)   # sampling chain (FPS + gathers)
@@ -208,9 +215,11 @@ class Engine:
         for li, l in enumerate(s.lv):
             if li == 0:   # the only real search (raw cloud); deeper levels sample an FPS-ordered set
                 if not (self.debug_skip_fps1 and s.used):
-                    check(lib.vnb_farthest_point_sample_ties(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_tie),
-                                                             self.tie_rounds, _sp(samp)))
-            else:  # src = the first l.n picks of sa1's FPS, in order: tie-free parent rounds need no proof
+                    check(lib.vnb_farthest_point_sample(B, l.n, l.m, dptr(src), dptr(l.fps), _sp(samp)))
+            elif li == 1:  # src = sa1's picks in order: PROVE the identity prefix once, keep what was proven per cloud
+                check(lib.vnb_farthest_point_sample_nested_proof(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws),
+                                                                 dptr(s.fps_tie), _sp(samp)))
+            else:  # src = a prefix of the proven set: covered by that proof (include/votenet_b200.h), no check needed
                 check(lib.vnb_farthest_point_sample_nested_hint(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(s.fps_ws),
                                                                 dptr(s.fps_tie), _sp(samp)))
             check(lib.vnb_gather_point(B, l.n, l.m, dptr(src), dptr(l.fps), dptr(l.xyz), _sp(samp)))
@@ -289,10 +298,10 @@ class Engine:
             x = s.p_h[i]
         mark("proposal", main)
         r = s.rec
-        check(lib.vnb_decode_boxes(B, p.npoint, dptr(s.p_xyz), dptr(x), dptr(self.mean_size), dptr(r.bboxes),
-                                   dptr(r.scores), dptr(r.objectness), dptr(r.class_scores), _sp(main)))
-        check(lib.vnb_nms3d(B, p.npoint, dptr(r.bboxes), dptr(r.scores), dptr(r.objectness), float(cfg.nms_iou),
-                            dptr(r.keep), dptr(r.nms_idx), dptr(r.nms_count), dptr(s.nms_ws), _sp(main)))
+        check(lib.vnb_decode_nms3d(B, p.npoint, dptr(s.p_xyz), dptr(x), dptr(self.mean_size), float(cfg.nms_iou),
+                                   dptr(r.bboxes), dptr(r.scores), dptr(r.objectness), dptr(r.class_scores), dptr(r.keep),
+                                   dptr(r.nms_idx), dptr(r.nms_key), dptr(r.nms_count), dptr(s.bboxes_pred),
+                                   dptr(s.class_scores_pred), dptr(s.batch_idx), dptr(s.nms_ws), _sp(main)))
         mark("nms", main)
         # join the side streams back (all their work has been consumed through events; this keeps capture well-formed)
         e1, e2 = ev(), ev()
@@ -302,7 +311,9 @@ class Engine:
     # ------------------------------------------------------------------------------------------------ public API
     def infer_device(self, xyz, feat, stream=None):
         """xyz (B,N,3), feat (B,N,C) CUDA f32 -> DetectionRecord (device views; valid until this slot is reused, i.e.
-        until the call after next).  Asynchronous on `stream` (default: current stream)."""
+        until `slots` calls later).  Besides the wire fields it carries the reference's three outputs over this rank's
+        batch (model.py:135-137): rec.bboxes_pred (B*K,8,3), rec.class_scores_pred (B*K,10), rec.batch_idx (B*K,), first
+        rec.nms_count rows valid.  Asynchronous on `stream` (default: current stream)."""
         with torch.cuda.device(self.device):
             main = stream if stream is not None else torch.cuda.current_stream(self.device)
             s = self._next_slot(main)

@@ -30,6 +30,29 @@ def decode_boxes(proposals_xyz, proposals_output, class_mean_size):
     return bboxes, scores, objectness, class_scores
 
 
+def decode_nms3d(proposals_xyz, proposals_output, class_mean_size, iou_threshold):
+    """model.py:100-137 in one kernel (csrc/nms3d.cu): box decode, NMS3D and the output gathers.  -> dict with
+    dec_bboxes (B,K,8,3), dec_scores (B,K), dec_objectness (B,K,2), dec_class_scores (B,K,10), nms_keep (B,K) u8,
+    nms_idx (B*K,2) rows (batch, box) in global descending-score order, nms_key (B*K,) order-preserving score keys,
+    nms_count (1,), and bboxes_pred (B*K,8,3) / class_scores_pred (B*K,10) / batch_idx (B*K,) (first nms_count rows)."""
+    b, k, _ = proposals_xyz.shape
+    dev = proposals_xyz.device
+    f32, i32 = torch.float32, torch.int32
+    E = lambda shape, dt=f32: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731
+    o = dict(dec_bboxes=E((b, k, 8, 3)), dec_scores=E((b, k)), dec_objectness=E((b, k, 2)), dec_class_scores=E((b, k, NC)),
+             nms_keep=E((b, k), torch.uint8), nms_idx=torch.zeros((max(b * k, 1), 2), dtype=i32, device=dev),
+             nms_key=torch.zeros((max(b * k, 1),), dtype=i32, device=dev), nms_count=torch.zeros((1,), dtype=i32, device=dev),
+             bboxes_pred=E((max(b * k, 1), 8, 3)), class_scores_pred=E((max(b * k, 1), NC)),
+             batch_idx=E((max(b * k, 1),), i32))
+    ws = torch.empty((lib.vnb_nms3d_workspace_bytes(b, k),), dtype=torch.uint8, device=dev)
+    check(lib.vnb_decode_nms3d(b, k, dptr(proposals_xyz, f32), dptr(proposals_output, f32), dptr(class_mean_size, f32),
+                               float(iou_threshold), dptr(o["dec_bboxes"]), dptr(o["dec_scores"]), dptr(o["dec_objectness"]),
+                               dptr(o["dec_class_scores"]), dptr(o["nms_keep"]), dptr(o["nms_idx"]), dptr(o["nms_key"]),
+                               dptr(o["nms_count"]), dptr(o["bboxes_pred"]), dptr(o["class_scores_pred"]),
+                               dptr(o["batch_idx"]), dptr(ws), stream_ptr()))
+    return o
+
+
 class VoteNetB200:
     def __init__(self, cfg: VoteNetConfig, weights, device="cuda", precision=PRECISION_TENSOR):
         self.cfg = cfg
@@ -80,9 +103,10 @@ class VoteNetB200:
                                                       list(p.mlp), list(p.mlp2), False, "proposal",
                                                       sample_xyz=seeds_xyz, weights=W)         # :89-93
         out["proposals_xyz"], out["proposals_output"], out["proposal_idx"] = prop_xyz, prop_out, pidx
-        bboxes, scores, objectness, class_scores = decode_boxes(prop_xyz, prop_out, self.class_mean_size)
-        out.update(dec_bboxes=bboxes, dec_scores=scores, dec_objectness=objectness, dec_class_scores=class_scores)
-        if run_nms:
-            keep, nms_idx, count = tf_nms3d.nms3d_raw(bboxes, scores, objectness, cfg.nms_iou)  # :133
-            out.update(nms_keep=keep, nms_idx=nms_idx, nms_count=count)
+        if not run_nms:
+            bboxes, scores, objectness, class_scores = decode_boxes(prop_xyz, prop_out, self.class_mean_size)
+            out.update(dec_bboxes=bboxes, dec_scores=scores, dec_objectness=objectness, dec_class_scores=class_scores)
+            return out
+        # decode (:100-129) + NMS3D (:133) + the three output gathers (:135-137) in one launch
+        out.update(decode_nms3d(prop_xyz, prop_out, self.class_mean_size, cfg.nms_iou))
         return out

@@ -56,6 +56,20 @@ def farthest_point_sample_nested_hint(npoint, inp, parent_first_tie):
     return out
 
 
+def farthest_point_sample_nested_proof(npoint, inp):
+    """farthest_point_sample_nested that also returns what it proved: (idx (B,npoint) i32, proven (B,) i32) with
+    proven[b] = npoint where the identity prefix was proven, else 0 — a valid `parent_first_tie` hint for
+    farthest_point_sample_nested_hint on any prefix inp[:, :n'] and npoint' <= npoint (include/votenet_b200.h)."""
+    inp = _xyz3(inp, "FarthestPointSample")
+    b, n, _ = inp.shape
+    out = torch.empty((b, int(npoint)), dtype=torch.int32, device=inp.device)
+    proven = torch.empty((b,), dtype=torch.int32, device=inp.device)
+    ws = torch.empty((lib.vnb_fps_nested_workspace_bytes(b, int(npoint)),), dtype=torch.uint8, device=inp.device)
+    check(lib.vnb_farthest_point_sample_nested_proof(b, n, int(npoint), dptr(inp, torch.float32, "inp"), dptr(out), dptr(ws),
+                                                     dptr(proven), stream_ptr()))
+    return out, proven
+
+
 class _GatherPointFn(torch.autograd.Function):
     """GatherPoint with its registered gradient (@tf.RegisterGradient('GatherPoint'), tf_sampling.py:43-47)."""
 
