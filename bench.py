@@ -130,7 +130,7 @@ def run_reference(args, rank, world):
         odense.votenet_forward(x, synth.height_feature(x), w, cfg, synth.CLASS_MEAN_SIZE)
 
     t0 = time.time(); one(0); t1 = time.time() - t0
-    workers = min(cores, CLOUDS_PER_RANK)
+    workers = cores
     # A step of this arm is a bounded sample of the batch: ONE of its 8 clouds through the full forward on one host
     # thread; `workers` steps run concurrently so every host core is busy (the reference's CPU ops are single-threaded).
     per_step = 1
@@ -146,38 +146,41 @@ def run_reference(args, rank, world):
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[3]: full VoteNet fwd, 8 clouds x 20000 pts (xyz+height), CPU oracle of the reference path"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                             "single_thread_value": 1.0 / t1},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 def cpu_baseline(cfg, w, budget_s=20.0):
+    """The CPU restatement of the reference path (oracle/), timed on THIS box's host cores: one cloud per thread on
+    every core the process may use (the reference's CPU ops are single-threaded, tf_interpolate.cpp / tf_nms3d.cpp), plus
+    the single-thread figure."""
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import dense as odense
     from votenet_b200 import synth
 
     cores = len(os.sched_getaffinity(0))
-    workers = min(cores, CLOUDS_PER_RANK)
     torch.set_num_threads(1)
-    clouds = [synth.synthetic_cloud(i, cfg.num_points)[None] for i in range(workers)]
+    base = [synth.synthetic_cloud(i, cfg.num_points)[None] for i in range(CLOUDS_PER_RANK)]
 
     def one(i):
-        odense.votenet_forward(clouds[i], synth.height_feature(clouds[i]), w, cfg, synth.CLASS_MEAN_SIZE)
+        x = base[i % len(base)]
+        odense.votenet_forward(x, synth.height_feature(x), w, cfg, synth.CLASS_MEAN_SIZE)
 
     t0 = time.time(); one(0); t1 = time.time() - t0
-    rounds = max(1, int(budget_s / max(t1, 1e-3) / 1.5))
-    rounds = min(rounds, 4)
-    with ThreadPoolExecutor(workers) as ex:
+    rounds = max(1, min(3, int(budget_s / max(t1, 1e-3) / 2)))
+    with ThreadPoolExecutor(cores) as ex:
         t0 = time.time()
-        for _ in range(rounds):
-            list(ex.map(one, range(workers)))
+        list(ex.map(one, range(cores * rounds)))
         dt = time.time() - t0
     torch.set_num_threads(cores)
-    return {"value": workers * rounds / dt, "unit": UNIT, "cores": workers, "kind": "port",
-            "sample": f"{workers * rounds} clouds of the same workload ({rounds} rounds x {workers} threads, 1 cloud per thread; "
-                      f"single-thread latency {t1:.2f} s/cloud)"}
+    return {"value": cores * rounds / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "single_thread_value": 1.0 / t1,
+            "sample": f"{cores * rounds} clouds of the same workload ({rounds} rounds x {cores} host threads = every core in "
+                      f"sched_getaffinity, 1 cloud per thread); single-thread {1.0 / t1:.3f} clouds/s ({t1:.2f} s/cloud)"}
 
 
 def kernel_table(eng, cfg, peaks, flush):
@@ -208,9 +211,21 @@ def kernel_table(eng, cfg, peaks, flush):
             r["note"] = note
         rows.append(r)
 
-    def tensor(name, ms, fl):
-        rows.append(dict(kernel=name, ms=ms, bound="tensor", algo_flops=fl, achieved=fl / ms / 1e9, peak=peaks["tc_burst"],
-                         unit="TFLOP/s"))
+    def tensor(name, ms, fl, executed=None):
+        r = dict(kernel=name, ms=ms, bound="tensor", algo_flops=fl, achieved=fl / ms / 1e9, peak=peaks["tc_burst"], unit="TFLOP/s")
+        if executed is not None:   # MMA flops the kernels really issue (tile packing drops the padded duplicate rows, layer 1
+            r["executed_flops"] = executed            # of the wide levels runs once per source point instead of per grouped row)
+            r["frac_executed"] = executed / ms / 1e9 / peaks["tc_burst"]
+        rows.append(r)
+
+    def sa_executed(cnt, n_src, cin_feat, widths, hoisted):
+        """Executed tensor-core flops of one fused SA stage: every centroid occupies a slot of 16 / 32 / 64 rows."""
+        c = cnt.clamp(min=1)
+        slot_rows = torch.where(c <= 16, 16, torch.where(c <= 32, 32, 64)).sum().item()
+        c1, c2, c3 = widths
+        if hoisted:   # layer 1 = one (B*n_src, cin_feat) x (cin_feat, c1) GEMM + a rank-3 fp32 update in the producer
+            return 2.0 * (B * n_src * cin_feat * c1 + slot_rows * (c1 * c2 + c2 * c3))
+        return 2.0 * slot_rows * (16 * c1 + c1 * c2 + c2 * c3)   # K of layer 1 padded to 16
 
     def mlp_flops(rows_, cin, widths):
         fl = 0
@@ -241,7 +256,8 @@ def kernel_table(eng, cfg, peaks, flush):
                                                          dptr(l.cnt), dptr(l.bq_ws), sp())))
         hbm(f"ball_query_sa{li + 1}", ms, B * (l.n * 12 + l.m * 12 + l.m * 256 + l.m * 4), "latency-bound (compulsory bytes only)")
         ms = t(lambda: eng._sa(li, src, feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, st, s.sa_ws, l.cnt))
-        tensor(f"sa{li + 1}_group_mlp_max", ms, mlp_flops(B * l.m * 64, 3 + c, sa.mlp))
+        tensor(f"sa{li + 1}_group_mlp_max", ms, mlp_flops(B * l.m * 64, 3 + c, sa.mlp),
+               sa_executed(l.cnt, l.n, c, sa.mlp, eng.sa_layers[li][3] is not None))
         src, feat, c = l.xyz, l.feat, sa.mlp[-1]
     # feature propagation: three_nn + (interpolate/concat + 2 x (1x1 conv + BN + ReLU)); voting module
     from votenet_b200.utils import fp_module_fused
@@ -315,6 +331,63 @@ def kernel_table(eng, cfg, peaks, flush):
     return rows
 
 
+def latency_inflight1(eng, xyz, feat, dev, reps=12):
+    """One forward alone on an idle GPU (graph replay, synchronised on both sides): median latency in ms."""
+    st = torch.cuda.Stream(device=dev)
+    ts = []
+    for _ in range(reps):
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record(st)
+        eng.infer_device(xyz, feat, stream=st)
+        b.record(st)
+        torch.cuda.synchronize(dev)
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts[2:]))
+
+
+def configs1_single_sa(eng, cfg, dev, flush, reps=5):
+    """BASELINE.json configs[1]: ONE set-abstraction layer on the raw clouds — FPS 20000 -> 1024, ball query r = 0.2,
+    nsample 64, group + shared MLP [64, 64, 128] + max-pool — the four launches back to back, L2 flushed before each run."""
+    from votenet_b200._lib import check, dptr, lib, stream_ptr
+
+    B, N, m = eng.B, eng.N, 1024
+    s = eng.slots[0]
+    i32 = torch.int32
+    fps = torch.empty((B, m), dtype=i32, device=dev)
+    nxyz = torch.empty((B, m, 3), device=dev)
+    idx = torch.zeros((B, m, 64), dtype=i32, device=dev)
+    cnt = torch.empty((B, m), dtype=i32, device=dev)
+    out = torch.empty((B, m, cfg.sa[0].mlp[-1]), device=dev)
+    st = torch.cuda.current_stream(dev)
+    ev = {}
+
+    def run(timed):
+        marks = [torch.cuda.Event(True) for _ in range(5)]
+        marks[0].record(st)
+        check(lib.vnb_farthest_point_sample(B, N, m, dptr(s.xyz), dptr(fps), stream_ptr()))
+        marks[1].record(st)
+        check(lib.vnb_gather_point(B, N, m, dptr(s.xyz), dptr(fps), dptr(nxyz), stream_ptr()))
+        check(lib.vnb_query_ball_point_ws(B, N, m, 0.2, 64, dptr(s.xyz), dptr(nxyz), dptr(idx), dptr(cnt), dptr(s.lv[0].bq_ws),
+                                          stream_ptr()))
+        marks[2].record(st)
+        eng._sa(0, s.xyz, s.feat, N, cfg.feature_dim, nxyz, idx, m, None, out, st, s.sa_ws, cnt)
+        marks[3].record(st)
+        torch.cuda.synchronize(dev)
+        if timed:
+            for k, (i, j) in dict(total=(0, 3), fps=(0, 1), ball_query=(1, 2), group_mlp_max=(2, 3)).items():
+                ev.setdefault(k, []).append(marks[i].elapsed_time(marks[j]))
+
+    run(False)
+    for _ in range(reps):
+        flush.zero_()
+        run(True)
+    ms = {k: float(np.median(v)) for k, v in ev.items()}
+    return {"workload": "configs[1]: single SA layer, FPS 20000->1024, ball r=0.2 nsample=64, group + MLP [64,64,128] + max, "
+                        f"{B} clouds (xyz + height)", "ms": ms["total"], "clouds_per_s": B / (ms["total"] / 1e3),
+            "ms_fps": ms["fps"], "ms_ball_query": ms["ball_query"], "ms_group_mlp_max": ms["group_mlp_max"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -330,6 +403,8 @@ def main():
     ap.add_argument("--fps-variant", type=int, default=None, help="0: register/cluster FPS kernel, 1: bucket-pruned (default)")
     ap.add_argument("--fps-threads", type=int, default=None, help="tuning: threads per FPS CTA (256/512/1024)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE", help="vnb_set_tuning knob (repeatable)")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N>1 exchange of the detection records: one-sided pushes over NVLink peer memory, or an NCCL all-gather")
     ap.add_argument("--debug-skip-fps1", action="store_true", help="experiment only: reuse the warm-up step's SA1 FPS result")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -351,7 +426,7 @@ def main():
     from votenet_b200 import synth
     from votenet_b200._lib import lib
     from votenet_b200.config import VoteNetConfig
-    from votenet_b200.dist import DetectionGather, shard_range
+    from votenet_b200.dist import make_gather, shard_range
     from votenet_b200.engine import Engine
     from votenet_b200.weights import make_synthetic_weights
 
@@ -362,6 +437,7 @@ def main():
         _check(lib.vnb_set_tuning(b"fps_threads", args.fps_threads))
     if args.fps_variant is not None:
         _check(lib.vnb_set_tuning(b"fps_variant", args.fps_variant))
+    fps_variant = 1 if args.fps_variant is None else args.fps_variant
     trap_buf = torch.zeros(8, dtype=torch.int32).pin_memory()  # filled by a device-side bounded wait that gives up
     _check(lib.vnb_debug_trap_buffer(trap_buf.data_ptr()))
     global TRAP_BUF
@@ -394,10 +470,12 @@ def main():
     host_feat = [ring_feat[r].cpu().pin_memory() for r in range(HR)]
     host_out = [torch.empty((eng.record_nbytes,), dtype=torch.uint8).pin_memory() for _ in range(HR)]
     h2d = host_xyz[0].numel() * 4 + host_feat[0].numel() * 4
-    d2h = eng.record_nbytes
+    d2h = eng.record_nbytes + (world * B * cfg.proposal.npoint * 8 + 4 if world > 1 else 0)
 
     NS = args.inflight
-    gather = DetectionGather(world, B, cfg.proposal.npoint, dev, slots=NS) if world > 1 else None
+    gather, transport = (make_gather(world, rank, B, cfg.proposal.npoint, dev, slots=NS, transport=args.transport)
+                         if world > 1 else (None, "none"))
+    host_merged = [torch.empty((world * B * cfg.proposal.npoint * 2 + 1,), dtype=torch.int32).pin_memory() for _ in range(HR)] if world > 1 else None
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     ctl = torch.cuda.current_stream(dev)
 
@@ -411,9 +489,12 @@ def main():
     def step_host(i):
         st = streams[eng._step % NS]
         eng.infer_host(host_xyz[i % HR], host_feat[i % HR], host_out[i % HR], stream=st)
-        if world > 1:
+        if world > 1:   # the step's result is the merged (Nnms,2) list of the WHOLE batch + its length: read it back too
             with torch.cuda.stream(st):
-                gather(eng.slots[(eng._step - 1) % NS].rec.buf, slot=(eng._step - 1) % NS)
+                idx, cnt = gather(eng.slots[(eng._step - 1) % NS].rec.buf, slot=(eng._step - 1) % NS)[:2]
+                hm = host_merged[i % HR]
+                hm[:-1].copy_(idx.view(-1), non_blocking=True)
+                hm[-1:].copy_(cnt, non_blocking=True)
 
     def timed(step_fn, K, W):
         for i in range(W):
@@ -463,7 +544,8 @@ def main():
     sampler.stop_flag.set()
     ms_e2e, wall_e2e, enq_e2e = timed(step_host, args.steps, args.warmup)
     lpf = eng.launches_per_forward or 0
-    launches = lpf * args.steps + (args.steps if world > 1 else 0)
+    per_step_extra = 0 if world == 1 else (3 if transport == "peer" else 1)   # push + wait + merge | merge (NCCL's kernel is not ours)
+    launches = (lpf + per_step_extra) * args.steps
 
     value = world * B * args.steps / (ms_dev / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
@@ -483,6 +565,8 @@ def main():
                 # overlap in the timed loop, so ms_per_launch is larger than ms_per_step
                 "share_of_serialised_forward": dom["ms"] / sum(r["ms"] for r in ktab),
                 "note": dom.get("note", "")}
+        lat1 = latency_inflight1(eng, ring_xyz[1], ring_feat[1], dev)
+        cfg1 = configs1_single_sa(eng, cfg, dev, flush)
         cpu = None if args.no_cpu_baseline else cpu_baseline(cfg, w)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -490,13 +574,22 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": "configs[3]: full VoteNet fwd (4 SA + 2 FP + vote + proposal + decode + 3D-NMS), "
                                        f"{B} clouds x {N} pts (xyz+height) per GPU", "clouds_per_gpu": B, "points": N,
-                           "parallelism": f"dp{world} (clouds sharded, 1 all-gather of detections)" if world > 1 else "single GPU",
+                           "parallelism": f"dp{world} (clouds sharded, no data-path collective; per forward ONE all-gather of the detection records, transport: {transport})" if world > 1 else "single GPU",
                            "l2": f"inputs rotate over {RING} device-resident batches ({RING * h2d / 1e6:.0f} MB > 126 MB L2)",
                            "pipelining": f"{NS} steps in flight ({NS} workspaces, {NS} streams): later steps' FPS chains overlap earlier steps' MLP chains",
-                           "cuda_graph": not args.no_graph, "fps_geometry": f"{args.fps_threads or 256} threads x cluster {args.fps_cluster}"},
+                           "cuda_graph": not args.no_graph,
+                           "fps_geometry": ("bucket-pruned sampler, ONE CTA of 512 threads per cloud (8 SMs per batch); nested levels: one "
+                                            "parallel identity-prefix proof at sa2, deeper levels covered by it") if fps_variant == 1
+                                           else f"register/cluster sampler, {args.fps_threads or 256} threads x cluster {args.fps_cluster}",
+                           "float_tolerance": "1e-3 per module on identical inputs, measured as max|a-b| / max|b| (relative to the tensor's scale, "
+                                              "not element-wise); observed per-stage errors: profiles/r2_stage_errors.json (written by tests/test_gpu_forward.py)"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "launches_per_forward": lpf,
+                # one forward alone on the idle GPU: the throughput above needs several forwards in flight (one forward's
+                # sa1 sampler keeps 8 of 148 SMs busy for most of this latency)
+                "latency_ms_inflight1": lat1, "clouds_per_s_inflight1": B / (lat1 / 1e3),
+                "configs1_single_sa_layer": cfg1,
                 "roofline": roof, "kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in ktab],
                 "cpu_baseline": cpu, "clocks": sampler.summary(),
                 "wall_s": {"device_loop": wall_dev, "e2e_loop": wall_e2e},

@@ -169,6 +169,20 @@ int vnb_merge_detections(int world, int b, int k, const void* gathered, size_t r
                          size_t off_key, size_t off_count, size_t off_bboxes, size_t off_class_scores, int* out_idx,
                          int* out_count, float* bboxes_pred, float* class_scores_pred, int* batch_idx, void* stream);
 
+/* One-sided all-gather of the detection records over NVLink peer memory (csrc/peer.cu) — what the multi-GPU path uses
+ * instead of a collective rendezvous.  Every rank owns an inbox of `world` records per slot and `world` int32 sequence
+ * flags per slot; `peer_inbox[p]` / `peer_flags[p]` are device pointers to the slot's buffers in rank p's memory
+ * (CUDA-IPC mappings for p != rank; HOST arrays of `world` pointers, read during the call).
+ *   vnb_peer_push_record: stores this rank's record (nbytes, 16-byte aligned and sized) into row `rank` of every
+ *     peer's inbox, then raises flag[rank] = seq there (system-scope release).  One launch, `world` CTAs.
+ *   vnb_peer_wait: one warp waits until all `world` local flags of the slot have reached seq (acquire); enqueue it
+ *     in front of vnb_merge_detections on the same stream.  A peer that never arrives traps after a few seconds.
+ * seq must increase with every reuse of a slot; a slot may be reused once the merge that consumed it is complete on
+ * every rank (the Python side keeps two inbox slots per in-flight forward, which makes that hold by stream order). */
+int vnb_peer_push_record(int world, int rank, const void* record, size_t nbytes, void* const* peer_inbox,
+                         int* const* peer_flags, int seq, void* stream);
+int vnb_peer_wait(int world, const int* flags, int seq, void* stream);
+
 /* ------------------------------------------------------------------ fused layers (boundary B) --------- */
 /* The dense arithmetic the reference delegates to TensorFlow/Tensorpack (Conv2D 1x1 + BN(EMA) + ReLU + reduce_max,
  * utils.py:120-158,286-292; FullyConnected, model.py:53-61).  BatchNorm is folded into W,b by the host. */

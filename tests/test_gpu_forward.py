@@ -12,6 +12,20 @@ from oracle import dense as D
 pytestmark = pytest.mark.gpu
 
 
+def _record_stage_error(name, err, tol):
+    """Observed errors, kept as evidence (copied to profiles/ after a GPU run): gpurun_out/stage_errors.json."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "gpurun_out", "stage_errors.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    d = json.load(open(path)) if os.path.exists(path) else {
+        "metric": "max|a-b| / max|b| against the fp32 CPU oracle (relative to the tensor's scale, not element-wise)"}
+    d[name] = {"observed": float(err), "bound": float(tol)}
+    json.dump(d, open(path, "w"), indent=1, sort_keys=True)
+
+
 def _run(cuda, cfg, b, precision, seed_cloud=0):
     from votenet_b200 import synth
     from votenet_b200.model import VoteNetB200
@@ -43,6 +57,7 @@ def test_backbone_and_votes(cuda, precision, tol, feature_dim):
     for key in ("sa1_points", "sa2_points", "sa3_points", "sa4_points", "fp1_points", "fp2_points", "votes"):
         e = rel_err(out[key].cpu().numpy(), ref[key].numpy())
         print(f"[e2e precision={precision} feat={feature_dim}] {key}: rel err {e:.3e}")
+        _record_stage_error(f"end_to_end/precision{precision}/feat{feature_dim}/{key}", e, tol)
         assert e < tol, f"{key}: rel err {e:.3e} (precision {precision})"
 
 

@@ -34,6 +34,7 @@ SOURCES = {
     "linear_tc.cu": [],
     "fp_chain.cu": [],
     "grad_ops.cu": [],
+    "peer.cu": [],
 }
 
 

@@ -386,7 +386,7 @@ static int fps_dispatch(int b, int n, int m, const float* xyz, int* out, const i
 
 using namespace vnb;
 
-namespace vnb { extern int g_fps_dispatch, g_fps_ablate; }
+namespace vnb { extern int g_fps_dispatch, g_fps_ablate, g_nms_cluster; }
 extern "C" int vnb_set_tuning(const char* key, int value) {
   std::string_view k(key);
   if (k == "fps_mode") g_fps_mode = value;
@@ -395,6 +395,7 @@ extern "C" int vnb_set_tuning(const char* key, int value) {
   else if (k == "fps_variant") g_fps_variant = value;
   else if (k == "fps_dispatch") vnb::g_fps_dispatch = value;
   else if (k == "fps_ablate") vnb::g_fps_ablate = value;
+  else if (k == "nms_cluster") vnb::g_nms_cluster = (value == 1 || value == 2 || value == 4 || value == 8) ? value : 8;
   else if (k == "ball_query_variant") vnb::g_bq_variant = value;
   else if (k == "bq_grid_min_n") vnb::g_bq_grid_min_n = value;
   else if (k == "sa_variant") vnb::g_sa_variant = value;

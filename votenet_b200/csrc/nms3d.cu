@@ -525,6 +525,8 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(int L, int b, int k, c
   }
 }
 
+int g_nms_cluster = 8;   // tuning "nms_cluster": CTAs per cloud (1, 2, 4 or 8)
+
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 template <bool DECODE>
@@ -542,7 +544,7 @@ static int launch_nms_cloud(int b, int k, float thr, const float* pxyz, const fl
   if (smem > 48 * 1024)
     VNB_CUDA(cudaFuncSetAttribute(nms_cloud_kernel<DECODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
-  const int CL = k >= 128 ? 8 : 1;
+  const int CL = k >= 128 ? g_nms_cluster : 1;
   cfg.gridDim = dim3((unsigned)(b * CL));
   cfg.blockDim = dim3(NMS_T);
   cfg.dynamicSmemBytes = smem;

@@ -89,6 +89,96 @@ class DetectionGather:
         return self.merge(slot)
 
 
+class PeerGather(DetectionGather):
+    """DetectionGather whose all-gather is ONE-SIDED over NVLink peer memory (csrc/peer.cu) instead of an NCCL
+    collective: after a forward, one kernel pushes the rank's record into every peer's inbox and raises a sequence flag;
+    a one-warp kernel waits for the slot's `world` flags in front of the merge.  No rendezvous kernel holds SMs while
+    it waits for the slowest rank, and collectives of different in-flight forwards do not serialise on one communicator.
+
+    The inboxes are plain CUDA allocations shared through CUDA IPC (torch's reductions, exchanged once with
+    all_gather_object).  Every slot has TWO inbox buffers used alternately: rank r pushes use u+2 of a slot only after
+    its own merge of use u+1, which saw every peer's push u+1, which each peer issued after ITS merge of use u (stream
+    order on the slot's stream) — so nobody overwrites a buffer a peer has not merged yet, with no acknowledgement
+    traffic.  `slot` must be bound to one stream, as in bench.py."""
+
+    def __init__(self, world, rank, b, k, device, slots=1, group=None, gather_outputs=False):
+        super().__init__(world, b, k, device, slots=slots, group=group, gather_outputs=gather_outputs)
+        import ctypes as C
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        self.rank, self.device = rank, torch.device(device)
+        nb = self.nbytes
+        self.depth = 2
+        # one allocation per rank: [slots][depth][world][nbytes] records, then [slots][depth][world] int32 flags
+        self.inbox = torch.zeros((slots, self.depth, world, nb), dtype=torch.uint8, device=device)
+        self.flags = torch.zeros((slots, self.depth, world), dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        handles = [None] * world
+        dist.all_gather_object(handles, (reduce_tensor(self.inbox), reduce_tensor(self.flags)), group=group)
+        self._peers = []   # keep the mappings alive
+        inbox_ptr, flags_ptr = [], []
+        for r in range(world):
+            if r == rank:
+                ib, fl = self.inbox, self.flags
+            else:
+                (f1, a1), (f2, a2) = handles[r]
+                ib, fl = f1(*a1), f2(*a2)
+                # touching the mapping from this device makes torch enable peer access between the two GPUs
+                probe = torch.empty((16,), dtype=torch.uint8, device=device)
+                probe.copy_(ib.view(-1)[:16])
+                self._peers.append((ib, fl))
+            inbox_ptr.append(ib.data_ptr())
+            flags_ptr.append(fl.data_ptr())
+        torch.cuda.synchronize(device)
+        # (no barrier needed: every inbox was zeroed before the handle exchange above, itself a collective)
+        # per (slot, depth): host arrays of `world` device pointers
+        self._ptrs = {}
+        for s in range(slots):
+            for d in range(self.depth):
+                off_i = (s * self.depth + d) * world * nb
+                off_f = (s * self.depth + d) * world * 4
+                self._ptrs[(s, d)] = ((C.c_void_p * world)(*[p_ + off_i for p_ in inbox_ptr]),
+                                      (C.c_void_p * world)(*[p_ + off_f for p_ in flags_ptr]))
+        self._uses = [0] * slots
+        from ._lib import lib
+        self._push, self._wait = lib.vnb_peer_push_record, lib.vnb_peer_wait
+
+    def __call__(self, rec_buf, slot=0):
+        from ._lib import check, dptr, stream_ptr
+
+        u = self._uses[slot]
+        self._uses[slot] = u + 1
+        d, seq = u % self.depth, u // self.depth + 1
+        ip, fp = self._ptrs[(slot, d)]
+        st = stream_ptr()
+        check(self._push(self.world, self.rank, dptr(rec_buf), self.nbytes, ip, fp, seq, st))
+        check(self._wait(self.world, dptr(self.flags[slot, d]), seq, st))
+        self.gathered[slot] = self.inbox[slot, d]
+        return self.merge(slot)
+
+
+def make_gather(world, rank, b, k, device, slots=1, group=None, gather_outputs=False, transport="peer"):
+    """The detection exchange of the multi-GPU path: `peer` = one-sided pushes over NVLink peer memory (PeerGather),
+    `nccl` = one all_gather_into_tensor per forward.  Returns (gather, transport actually in use); `peer` falls back to
+    NCCL — loudly, the caller reports it — only when CUDA IPC between the ranks cannot be set up."""
+    if world == 1 or transport == "nccl":
+        return DetectionGather(world, b, k, device, slots=slots, group=group, gather_outputs=gather_outputs), "nccl" if world > 1 else "local"
+    ok, err = 1, ""
+    g = None
+    try:
+        g = PeerGather(world, rank, b, k, device, slots=slots, group=group, gather_outputs=gather_outputs)
+    except Exception as e:  # noqa: BLE001 — any IPC / peer-access failure
+        ok, err = 0, f"{type(e).__name__}: {e}"
+    t = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    if int(t.item()) == 1:
+        return g, "peer"
+    import sys
+    print(f"[votenet_b200.dist] rank {rank}: peer-memory transport unavailable ({err or 'a peer failed'}); using NCCL all-gather",
+          file=sys.stderr, flush=True)
+    return DetectionGather(world, b, k, device, slots=slots, group=group, gather_outputs=gather_outputs), "nccl (peer transport unavailable)"
+
+
 def merge_gathered_host(gathered, b, k):
     """Host (numpy) statement of the same merge — used by the gloo tests and as the checker of the device merge."""
     g = gathered.cpu()
