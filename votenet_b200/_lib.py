@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvotenet_b200.so")
+LIB_PATH = os.environ.get("VNB_LIB", os.path.join(_HERE, "libvotenet_b200.so"))   # VNB_LIB: an instrumented debug build
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

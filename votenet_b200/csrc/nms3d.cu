@@ -230,8 +230,8 @@ __device__ __forceinline__ uint32_t score_key(float s) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// per-box summary for the exact rejection test (iou_trivially_false on precomputed extrema)
-struct BoxSum { float top, bot, lox, hix, loz, hiz, mag, nan; };
+// per-box summary for the exact rejection tests (iou_trivially_false on precomputed extrema + a separating-axis test)
+struct BoxSum { float top, bot, lox, hix, loz, hiz, mag, nan; float cx[4], cz[4]; };
 
 __device__ __forceinline__ BoxSum summarize(const float* bb) {
   BoxSum s;
@@ -240,6 +240,7 @@ __device__ __forceinline__ BoxSum summarize(const float* bb) {
   bool nan = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
+    s.cx[i] = bb[i * 3]; s.cz[i] = bb[i * 3 + 2];
     if (i) {
       s.lox = fminf(s.lox, bb[i * 3]); s.hix = fmaxf(s.hix, bb[i * 3]);
       s.loz = fminf(s.loz, bb[i * 3 + 2]); s.hiz = fmaxf(s.hiz, bb[i * 3 + 2]);
@@ -250,15 +251,38 @@ __device__ __forceinline__ BoxSum summarize(const float* bb) {
   s.nan = nan ? 1.f : 0.f;
   return s;
 }
-// same boolean as iou_trivially_false(bi, bj) — fminf / fmaxf are exact and associative, so the extrema and `mag`
-// are the same floats whether they are folded per box or per pair
+
+// Separating axis d = (dx, dz): the projections of the two top faces are disjoint with a margin.  Sufficient for "the
+// clip has no vertex" by the same argument as the bounding-rectangle test above, for any direction: a gap of
+// 2*eps*(|dx|+|dz|) in projected units is a Euclidean gap > eps = 1e-4 * max|coordinate| between the two quads (the
+// projections are rounded to ~2e-7 * mag * (|dx|+|dz|)), so (i) a corner of one quad is more than eps away from every
+// boundary point of the other, every `px < abscissa` comparison of point_in_polygon (:53-67, abscissa rounded to
+// ~6e-7 * mag) comes out as in exact arithmetic and the parity says "outside"; (ii) seg_intersect's double-precision
+// point (:69-100) is accepted only inside both segments' coordinate ranges, i.e. only for segments that touch to ~1e-9.
+__device__ __forceinline__ bool axis_separates(const BoxSum& a, const BoxSum& b, float dx, float dz, float eps) {
+  float amin = a.cx[0] * dx + a.cz[0] * dz, amax = amin, bmin = b.cx[0] * dx + b.cz[0] * dz, bmax = bmin;
+#pragma unroll
+  for (int i = 1; i < 4; ++i) {
+    const float ta = a.cx[i] * dx + a.cz[i] * dz, tb = b.cx[i] * dx + b.cz[i] * dz;
+    amin = fminf(amin, ta); amax = fmaxf(amax, ta);
+    bmin = fminf(bmin, tb); bmax = fmaxf(bmax, tb);
+  }
+  const float margin = 2.f * eps * (fabsf(dx) + fabsf(dz));
+  return amax + margin < bmin || bmax + margin < amin;
+}
+
+// same boolean as iou_trivially_false(bi, bj) for the first two tests — fminf / fmaxf are exact and associative, so the
+// extrema and `mag` are the same floats whether they are folded per box or per pair — plus the separating-axis test
+// along the edge directions of both top faces (yawed boxes whose bounding rectangles overlap but which do not touch)
 __device__ __forceinline__ bool sum_trivially_false(const BoxSum& a, const BoxSum& b) {
   const float h = NMS_MIN(a.top, b.top) - NMS_MAX(a.bot, b.bot);
   if (!(h > 0.f)) return true;
   const float mag = fmaxf(a.mag, b.mag);
   const float eps = 1e-4f * mag;
   if (a.nan != 0.f || b.nan != 0.f || !(mag < 1e30f)) return false;
-  return a.hix + eps < b.lox || b.hix + eps < a.lox || a.hiz + eps < b.loz || b.hiz + eps < a.loz;
+  if (a.hix + eps < b.lox || b.hix + eps < a.lox || a.hiz + eps < b.loz || b.hiz + eps < a.loz) return true;
+  return axis_separates(a, b, a.cx[1] - a.cx[0], a.cz[1] - a.cz[0], eps) || axis_separates(a, b, a.cx[3] - a.cx[0], a.cz[3] - a.cz[0], eps) ||
+         axis_separates(a, b, b.cx[1] - b.cx[0], b.cz[1] - b.cz[0], eps) || axis_separates(a, b, b.cx[3] - b.cx[0], b.cz[3] - b.cz[0], eps);
 }
 
 // Number of entries of a list sorted by descending key that precede an entry with key `key` coming from ANOTHER list:
@@ -277,15 +301,16 @@ __device__ __forceinline__ int count_preceding(KeyAt key_at, int n, uint32_t key
 }
 
 constexpr int NMS_T = 512;          // threads per cloud CTA
-constexpr int NMS_LIST = 8192;      // surviving pairs staged per pass
+constexpr int NMS_LIST = 4096;      // surviving pairs staged per pass
 
-struct NmsSmem {  // dynamic shared memory layout for k boxes, W = ceil(k/32) mask words per row
+struct NmsSmem {  // dynamic shared memory layout for k boxes, W = ceil(k/32) mask words per row; every array 16-byte aligned
+  static __host__ __device__ size_t al(size_t x) { return (x + 15) / 16 * 16; }
   static __host__ __device__ size_t sum_off() { return 0; }
-  static __host__ __device__ size_t key_off(int k) { return (size_t)k * sizeof(BoxSum); }
-  static __host__ __device__ size_t order_off(int k) { return key_off(k) + (size_t)k * 4; }
-  static __host__ __device__ size_t kept_off(int k) { return order_off(k) + (size_t)k * 4; }
-  static __host__ __device__ size_t mask_off(int k) { return kept_off(k) + (size_t)k * 4; }
-  static __host__ __device__ size_t list_off(int k) { return mask_off(k) + (size_t)k * ((k + 31) / 32) * 4; }
+  static __host__ __device__ size_t key_off(int k) { return al((size_t)k * sizeof(BoxSum)); }
+  static __host__ __device__ size_t order_off(int k) { return key_off(k) + al((size_t)k * 4); }
+  static __host__ __device__ size_t kept_off(int k) { return order_off(k) + al((size_t)k * 4); }
+  static __host__ __device__ size_t mask_off(int k) { return kept_off(k) + al((size_t)k * 4); }
+  static __host__ __device__ size_t list_off(int k) { return mask_off(k) + al((size_t)k * ((k + 31) / 32) * 4); }
   static __host__ __device__ size_t bytes(int k) { return list_off(k) + (size_t)NMS_LIST * 4; }
 };
 
@@ -318,22 +343,48 @@ __global__ void __launch_bounds__(NMS_T) nms_cloud_kernel(int k, float thr, cons
   const int W = (k + 31) / 32;
   float* cb = bbox + (size_t)b * k * 24;
   if (tid == 0) { s_nc = 0; s_nk = 0; s_nlist = 0; }
-  // ---- decode (fused entry point; every CTA of the cluster writes the same values) + per-box summaries, keys, flags
+#ifdef NMS_PROF
+  long long pt[10]; int pi = 0;
+#define NMS_TICK() do { __syncthreads(); pt[pi++] = clock64(); } while (0)
+#else
+#define NMS_TICK() do {} while (0)
+#endif
+  NMS_TICK();
+  // ---- decode (fused entry point): the cluster's CTAs decode disjoint chunks of the cloud's boxes, then everybody reads
+  //      all of them back through L2 for the per-box summaries, keys and candidate flags
+  if (DECODE) {
+    const int chunk = (k + CL - 1) / CL;
+    for (int i = cr * chunk + tid; i < min(k, (cr + 1) * chunk); i += NMS_T)
+      decode_one(b * k + i, pxyz, pout, mean_size, bbox, scores, obj, class_scores);
+    __threadfence();
+    cluster.sync();
+  }
+  unsigned long long* s_rk = reinterpret_cast<unsigned long long*>(s_list);   // rank keys (the pair list is not in use yet)
   for (int i = tid; i < k; i += NMS_T) {
     const int t = b * k + i;
-    if (DECODE) decode_one(t, pxyz, pout, mean_size, bbox, scores, obj, class_scores);
-    s_sum[i] = summarize(cb + (size_t)i * 24);
-    const bool cand = obj[(size_t)t * 2 + 1] > obj[(size_t)t * 2];   // :230
-    s_key[i] = score_key(scores[t]);
-    s_kept[i] = cand ? 1 : 0;
+    float bb[24];
+#pragma unroll
+    for (int v = 0; v < 6; ++v) {
+      const float4 q = __ldcg(reinterpret_cast<const float4*>(cb + (size_t)i * 24) + v);
+      bb[v * 4] = q.x; bb[v * 4 + 1] = q.y; bb[v * 4 + 2] = q.z; bb[v * 4 + 3] = q.w;
+    }
+    s_sum[i] = summarize(bb);
+    const float2 ob = __ldcg(reinterpret_cast<const float2*>(obj) + t);
+    const bool cand = ob.y > ob.x;   // :230
+    const uint32_t key = score_key(__ldcg(scores + t));
+    s_key[i] = key;
+    // candidates: (key, smaller index first) as one 64-bit number, never 0; everything else 0 and never counted
+    s_rk[i] = cand ? (((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i)) : 0ull;
   }
   __syncthreads();
-  // ---- 1. rank of candidate i = candidates that precede it (greater key, or equal key and smaller index)
+  NMS_TICK();
+  // ---- 1. rank of candidate i = number of candidates with a larger rank key
   for (int i = tid; i < k; i += NMS_T) {
-    if (!s_kept[i]) continue;
-    const uint32_t ki = s_key[i];
+    const unsigned long long ki = s_rk[i];
+    if (ki == 0ull) continue;
     int rank = 0;
-    for (int j = 0; j < k; ++j) rank += (s_kept[j] && (s_key[j] > ki || (s_key[j] == ki && j < i))) ? 1 : 0;
+#pragma unroll 8
+    for (int j = 0; j < k; ++j) rank += s_rk[j] > ki ? 1 : 0;
     s_order[rank] = i;
     atomicAdd(&s_nc, 1);
   }
@@ -341,7 +392,9 @@ __global__ void __launch_bounds__(NMS_T) nms_cloud_kernel(int k, float thr, cons
   const int nc = s_nc;
   if (cr == 0)
     for (int t = tid; t < nc * W; t += NMS_T) s_mask[t] = 0u;
+  NMS_TICK();
   cluster.sync();   // CTA 0's mask is zeroed before anyone sets a bit in it
+  NMS_TICK();
   uint32_t* mask0 = cluster.map_shared_rank(s_mask, 0);
   // ---- 2. pair filter + clip.  This CTA owns rows p = 1 + cr, 1 + cr + CL, ...; passes of rows whose pairs fit the list
   for (int p0 = 1 + cr; p0 < nc;) {
@@ -372,25 +425,42 @@ __global__ void __launch_bounds__(NMS_T) nms_cloud_kernel(int k, float thr, cons
     p0 = p1;
     __syncthreads();
   }
+  NMS_TICK();
   cluster.sync();   // every bit is set; CTA 0 finishes the cloud, the others are done
   if (cr != 0) return;
-  // ---- 3. greedy pass: warp 0, kept-set as W <= 32 words (one per lane); keep mask written by everyone afterwards
+  NMS_TICK();
+  // ---- 3. greedy pass, warp 0, in blocks of 32 candidates: lane j owns candidate 32*blk + j.  Suppression by kept
+  //      candidates of EARLIER blocks is a parallel AND over the kept words; inside the block, lane 0 resolves the 32
+  //      candidates in order with register arithmetic (their intra-block mask words come from shared memory, loads
+  //      independent of the running result) — ~15 cycles per candidate instead of a warp vote per candidate.
   if (warp == 0) {
-    uint32_t kept = 0;
+    uint32_t* s_kw = s_list;          // kept words, one per block
+    uint32_t* s_m = s_list + 32;      // intra-block mask words of the current block
     int nk = 0;
-    uint32_t row = (nc > 0 && lane < W) ? s_mask[lane] : 0u;
-    for (int p = 0; p < nc; ++p) {
-      const uint32_t nxt = (p + 1 < nc && lane < W) ? s_mask[(p + 1) * W + lane] : 0u;   // prefetch: independent of `kept`
-      if (!__any_sync(0xffffffffu, (row & kept) != 0u)) {
-        if (lane == (p >> 5)) kept |= 1u << (p & 31);
-        if (lane == 0) s_kept[nk] = p;
-        ++nk;
+    for (int blk = 0; blk * 32 < nc; ++blk) {
+      const int p = blk * 32 + lane;
+      const bool valid = p < nc;
+      bool sup = false;
+      for (int w = 0; w < blk; ++w) sup = sup || (valid && (s_mask[p * W + w] & s_kw[w]) != 0u);
+      const unsigned alive = __ballot_sync(0xffffffffu, valid && !sup);
+      s_m[lane] = valid ? s_mask[p * W + blk] : 0u;
+      __syncwarp();
+      uint32_t kb = 0u;
+      if (lane == 0) {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j)
+          if (((alive >> j) & 1u) && !(s_m[j] & kb)) kb |= 1u << j;
+        s_kw[blk] = kb;
       }
-      row = nxt;
+      kb = __shfl_sync(0xffffffffu, kb, 0);
+      if ((kb >> lane) & 1u) s_kept[nk + __popc(kb & ((1u << lane) - 1u))] = p;
+      nk += __popc(kb);
+      __syncwarp();
     }
     if (lane == 0) s_nk = nk;
   }
   __syncthreads();
+  NMS_TICK();
   const int nk = s_nk;
   for (int i = tid; i < k; i += NMS_T) keep[(size_t)b * k + i] = 0;
   __syncthreads();
@@ -406,58 +476,157 @@ __global__ void __launch_bounds__(NMS_T) nms_cloud_kernel(int k, float thr, cons
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(ws_done, 1u) == (unsigned)ncloud - 1u) ? 1 : 0;
   __syncthreads();
+  NMS_TICK();
+#ifdef NMS_PROF
+  if (tid == 0 && b == 0) printf("nms cloud0 cta0 cycles: decode %lld rank %lld zero %lld csync %lld pairs+clip %lld csync %lld greedy %lld publish %lld\n",
+                                pt[1] - pt[0], pt[2] - pt[1], pt[3] - pt[2], pt[3] - pt[2], pt[4] - pt[3], pt[5] - pt[4], pt[6] - pt[5], pt[7] - pt[6]);
+#endif
   if (!s_last) return;
   __threadfence();
   const int B = ncloud;
-  // stage every list's keys in shared memory when they fit (the mask / list area is free now); else search in L2
-  uint32_t* s_all = reinterpret_cast<uint32_t*>(nsm);
-  const size_t cap = NmsSmem::bytes(k) / 4;
+  // (a) few survivors (the usual case): one 64-bit composite per survivor — score key, then the flat index complemented so
+  //     that equal scores order by ascending (batch, box) — bitonic-sorted in shared memory by the whole CTA;
+  // (b) otherwise a k-way merge by rank: list offsets in shared memory, every list's keys staged too when they fit
+  //     (all of this CTA's dynamic shared memory is free now), else the searches go to L2.
+  __shared__ int s_cnt_small[65];   // exclusive prefix of the list lengths when B <= 64
+  if (B <= 64) {
+    if (tid < B) s_cnt_small[tid + 1] = __ldcg(ws_nk + tid);
+    if (tid == 0) s_cnt_small[0] = 0;
+    __syncthreads();
+    if (tid == 0)
+      for (int c = 0; c < B; ++c) s_cnt_small[c + 1] += s_cnt_small[c];
+    __syncthreads();
+  }
+  if (B <= 64) {
+    const int tot = s_cnt_small[B];
+    // every list is already sorted: lay list c out as a run of kp slots — descending for even c, ascending for odd c,
+    // zero-padded — and run only the MERGE stages of the bitonic network (sizes 2*kp .. npow)
+    int kp = 1, bp = 1;
+    while (kp < k) kp <<= 1;
+    while (bp < B) bp <<= 1;
+    const int npow = kp * bp;
+    if ((size_t)npow * 8 <= NmsSmem::bytes(k)) {
+      unsigned long long* s_srt = reinterpret_cast<unsigned long long*>(nsm);
+      for (int e = tid; e < npow; e += NMS_T) {
+        const int c = e / kp, slot = e - c * kp;
+        const int j = (c & 1) ? kp - 1 - slot : slot;
+        unsigned long long v = 0ull;
+        if (c < B && j < s_cnt_small[c + 1] - s_cnt_small[c]) {
+          const uint32_t flat = (uint32_t)(c * k + __ldcg(ws_box + (size_t)c * k + j));
+          v = ((unsigned long long)__ldcg(ws_key + (size_t)c * k + j) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+        }
+        s_srt[e] = v;
+      }
+      NMS_TICK();
+      __syncthreads();
+      for (int size = 2 * kp; size <= npow; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int t = tid; t < (npow >> 1); t += NMS_T) {
+            const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), hi = lo | stride;
+            const bool desc = (lo & size) == 0;   // descending runs first: the final order is descending
+            const unsigned long long a = s_srt[lo], c2 = s_srt[hi];
+            if ((a < c2) == desc) { s_srt[lo] = c2; s_srt[hi] = a; }
+          }
+          __syncthreads();
+        }
+      NMS_TICK();
+      for (int r = tid; r < tot; r += NMS_T) {
+        const unsigned long long v = s_srt[r];
+        const uint32_t flat = 0xFFFFFFFFu - (uint32_t)v;
+        const int c = (int)(flat / (uint32_t)k), box = (int)(flat % (uint32_t)k);
+        out_idx[r * 2 + 0] = c;
+        out_idx[r * 2 + 1] = box;
+        if (out_key != nullptr) out_key[r] = (uint32_t)(v >> 32);
+        if (batch_idx != nullptr) batch_idx[r] = c;                                   // model.py:137
+        if (bboxes_pred != nullptr) {                                                    // model.py:135
+          const float4* src = reinterpret_cast<const float4*>(bbox + ((size_t)c * k + box) * 24);
+          float4* dst = reinterpret_cast<float4*>(bboxes_pred + (size_t)r * 24);
+          float4 q[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) q[i] = __ldcg(src + i);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) dst[i] = q[i];
+        }
+        if (cls_pred != nullptr) {                                                       // model.py:136
+          const float2* src = reinterpret_cast<const float2*>(class_scores + ((size_t)c * k + box) * 10);
+          float2* dst = reinterpret_cast<float2*>(cls_pred + (size_t)r * 10);
+          float2 q[5];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) q[i] = __ldcg(src + i);
+#pragma unroll
+          for (int i = 0; i < 5; ++i) dst[i] = q[i];
+        }
+      }
+#ifdef NMS_PROF
+      NMS_TICK();
+      if (tid == 0) printf("nms last cta (cloud %d): emit stage %lld sort %lld write %lld cycles, total kept %d npow %d\n", b, pt[pi - 3] - pt[pi - 4], pt[pi - 2] - pt[pi - 3], pt[pi - 1] - pt[pi - 2], tot, npow);
+#endif
+      if (tid == 0) { *out_count = tot; *ws_done = 0u; }
+      return;
+    }
+  }
+  int* s_off = reinterpret_cast<int*>(nsm);                      // [B + 1] exclusive prefix of the list lengths
+  const size_t head = ((size_t)(B + 1) * 4 + 15) / 16 * 16;
+  uint32_t* s_all = reinterpret_cast<uint32_t*>(nsm + head);
+  const size_t cap = (NmsSmem::bytes(k) - head) / 4;
+  const bool offs_fit = head <= NmsSmem::bytes(k);
+  if (tid == 0 && offs_fit) {
+    int acc = 0;
+    for (int c = 0; c < B; ++c) { s_off[c] = acc; acc += __ldcg(ws_nk + c); }
+    s_off[B] = acc;
+  }
+  __syncthreads();
   int total = 0;
-  for (int c = 0; c < B; ++c) total += __ldcg(ws_nk + c);
-  const bool staged = (size_t)total <= cap;
+  if (offs_fit) total = s_off[B];
+  else for (int c = 0; c < B; ++c) total += __ldcg(ws_nk + c);
+  const bool staged = offs_fit && (size_t)total <= cap;
   if (staged) {
-    int off = 0;
-    for (int c = 0; c < B; ++c) {
-      const int n = __ldcg(ws_nk + c);
-      for (int j = tid; j < n; j += NMS_T) s_all[off + j] = __ldcg(ws_key + (size_t)c * k + j);
-      off += n;
+    for (int e = tid; e < total; e += NMS_T) {
+      int c = 0;
+      while (s_off[c + 1] <= e) ++c;
+      s_all[e] = __ldcg(ws_key + (size_t)c * k + (e - s_off[c]));
     }
   }
   __syncthreads();
-  int offc = 0;
-  for (int c = 0; c < B; ++c) {
-    const int n = __ldcg(ws_nk + c);
-    for (int j = tid; j < n; j += NMS_T) {
-      const uint32_t key = staged ? s_all[offc + j] : __ldcg(ws_key + (size_t)c * k + j);
-      int rank = j, off2 = 0;
-      for (int c2 = 0; c2 < B; ++c2) {
-        const int n2 = __ldcg(ws_nk + c2);
-        if (c2 != c) {
-          if (staged) rank += count_preceding([&](int i) { return s_all[off2 + i]; }, n2, key, c2 < c);
-          else rank += count_preceding([&](int i) { return __ldcg(ws_key + (size_t)c2 * k + i); }, n2, key, c2 < c);
-        }
-        off2 += n2;
-      }
-      const int box = __ldcg(ws_box + (size_t)c * k + j);
-      out_idx[rank * 2 + 0] = c;
-      out_idx[rank * 2 + 1] = box;
-      if (out_key != nullptr) out_key[rank] = key;
-      if (batch_idx != nullptr) batch_idx[rank] = c;                                  // model.py:137
-      if (bboxes_pred != nullptr) {                                                   // model.py:135
-        const float4* src = reinterpret_cast<const float4*>(bbox + ((size_t)c * k + box) * 24);
-        float4* dst = reinterpret_cast<float4*>(bboxes_pred + (size_t)rank * 24);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) dst[i] = __ldcg(src + i);
-      }
-      if (cls_pred != nullptr) {                                                      // model.py:136
-        const float2* src = reinterpret_cast<const float2*>(class_scores + ((size_t)c * k + box) * 10);
-        float2* dst = reinterpret_cast<float2*>(cls_pred + (size_t)rank * 10);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) dst[i] = __ldcg(src + i);
-      }
+  for (int e = tid; e < total; e += NMS_T) {
+    int c = 0, j = e;
+    if (offs_fit) { while (s_off[c + 1] <= e) ++c; j = e - s_off[c]; }
+    else { int n; while (j >= (n = __ldcg(ws_nk + c))) { j -= n; ++c; } }
+    const uint32_t key = staged ? s_all[e] : __ldcg(ws_key + (size_t)c * k + j);
+    int rank = j;
+    for (int c2 = 0; c2 < B; ++c2) {
+      if (c2 == c) continue;
+      if (staged) rank += count_preceding([&](int i) { return s_all[s_off[c2] + i]; }, s_off[c2 + 1] - s_off[c2], key, c2 < c);
+      else rank += count_preceding([&](int i) { return __ldcg(ws_key + (size_t)c2 * k + i); }, __ldcg(ws_nk + c2), key, c2 < c);
     }
-    offc += n;
+    const int box = __ldcg(ws_box + (size_t)c * k + j);
+    out_idx[rank * 2 + 0] = c;
+    out_idx[rank * 2 + 1] = box;
+    if (out_key != nullptr) out_key[rank] = key;
+    if (batch_idx != nullptr) batch_idx[rank] = c;                                  // model.py:137
+    if (bboxes_pred != nullptr) {                                                   // model.py:135
+      const float4* src = reinterpret_cast<const float4*>(bbox + ((size_t)c * k + box) * 24);
+      float4* dst = reinterpret_cast<float4*>(bboxes_pred + (size_t)rank * 24);
+      float4 v[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) v[i] = __ldcg(src + i);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) dst[i] = v[i];
+    }
+    if (cls_pred != nullptr) {                                                      // model.py:136
+      const float2* src = reinterpret_cast<const float2*>(class_scores + ((size_t)c * k + box) * 10);
+      float2* dst = reinterpret_cast<float2*>(cls_pred + (size_t)rank * 10);
+      float2 v[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) v[i] = __ldcg(src + i);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) dst[i] = v[i];
+    }
   }
+#ifdef NMS_PROF
+  NMS_TICK();
+  if (tid == 0) printf("nms last cta (cloud %d): emit %lld cycles, total kept %d staged %d\n", b, pt[pi - 1] - pt[pi - 2], total, (int)staged);
+#endif
   if (tid == 0) { *out_count = total; *ws_done = 0u; }   // counter re-armed for the next launch on this workspace
 }
 
