@@ -182,6 +182,17 @@ int vnb_merge_detections(int world, int b, int k, const void* gathered, size_t r
 int vnb_peer_push_record(int world, int rank, const void* record, size_t nbytes, void* const* peer_inbox,
                          int* const* peer_flags, int seq, void* stream);
 int vnb_peer_wait(int world, const int* flags, int seq, void* stream);
+/* Lets kernels of the CURRENT device load / store memory of `peer_device` (cudaDeviceEnablePeerAccess; a no-op when it is
+ * already enabled or peer_device is the current device).  Call once per peer before the first vnb_peer_push_record. */
+int vnb_peer_enable_access(int peer_device);
+/* The inbox memory.  vnb_peer_alloc: a dedicated, zeroed device allocation on the current device + its 64-byte CUDA IPC
+ * handle (exchange it with the peers by any host channel); vnb_peer_open: map a peer's allocation into the CURRENT
+ * device's context (peer-to-peer over NVLink; the exporting process must keep the allocation alive); vnb_peer_close /
+ * vnb_peer_free undo them.  The only entry points of the library that allocate device memory. */
+int vnb_peer_alloc(size_t nbytes, void** dev_ptr, unsigned char* ipc_handle_64);
+int vnb_peer_open(const unsigned char* ipc_handle_64, void** dev_ptr);
+int vnb_peer_close(void* dev_ptr);
+int vnb_peer_free(void* dev_ptr);
 
 /* ------------------------------------------------------------------ fused layers (boundary B) --------- */
 /* The dense arithmetic the reference delegates to TensorFlow/Tensorpack (Conv2D 1x1 + BN(EMA) + ReLU + reduce_max,

@@ -38,6 +38,11 @@ _SIGS = {
     "vnb_merge_detections": ([_i, _i, _i, _p, _sz, _sz, _sz, _sz, _sz, _sz, _p, _p, _p, _p, _p, _p], _i),
     "vnb_peer_push_record": ([_i, _i, _p, _sz, _p, _p, _i, _p], _i),
     "vnb_peer_wait": ([_i, _p, _i, _p], _i),
+    "vnb_peer_enable_access": ([_i], _i),
+    "vnb_peer_alloc": ([_sz, _p, _p], _i),
+    "vnb_peer_open": ([_p, _p], _i),
+    "vnb_peer_close": ([_p], _i),
+    "vnb_peer_free": ([_p], _i),
     "vnb_decode_nms3d": ([_i, _i, _p, _p, _p, _f] + [_p] * 13, _i),
     "vnb_farthest_point_sample": ([_i, _i, _i, _p, _p, _p], _i),
     "vnb_gather_point": ([_i, _i, _i, _p, _p, _p, _p], _i),

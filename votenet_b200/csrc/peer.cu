@@ -11,6 +11,8 @@
 // serialise against each other, and the transfer (world x 0.3 MB per forward) overlaps the other streams' compute.
 #include "common.cuh"
 
+#include <string.h>
+
 namespace vnb {
 
 constexpr int PEER_MAX = 16;
@@ -60,6 +62,52 @@ extern "C" int vnb_peer_push_record(int world, int rank, const void* record, siz
   }
   peer_push_kernel<<<world, 1024, 0, as_stream(stream)>>>(pp, rank, static_cast<const uint4*>(record), nbytes / 16, seq);
   return check_launch("peer_push_record");
+}
+
+extern "C" int vnb_peer_alloc(size_t nbytes, void** dev_ptr, unsigned char* ipc_handle_64) {
+  VNB_REQUIRE(nbytes > 0 && dev_ptr != nullptr && ipc_handle_64 != nullptr, "peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  VNB_CUDA(cudaMalloc(&p, nbytes));          // a dedicated allocation: the handle maps exactly this buffer, offset 0
+  VNB_CUDA(cudaMemset(p, 0, nbytes));
+  VNB_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  VNB_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(ipc_handle_64, &h, 64);
+  *dev_ptr = p;
+  return VNB_OK;
+}
+
+extern "C" int vnb_peer_open(const unsigned char* ipc_handle_64, void** dev_ptr) {
+  VNB_REQUIRE(dev_ptr != nullptr && ipc_handle_64 != nullptr, "peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle_64, 64);
+  // opened in the CURRENT device's context: CUDA sets up the peer mapping to the exporting GPU (NVLink) for this device
+  VNB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return VNB_OK;
+}
+
+extern "C" int vnb_peer_close(void* dev_ptr) {
+  VNB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return VNB_OK;
+}
+
+extern "C" int vnb_peer_free(void* dev_ptr) {
+  VNB_CUDA(cudaFree(dev_ptr));
+  return VNB_OK;
+}
+
+extern "C" int vnb_peer_enable_access(int peer_device) {
+  int cur = -1;
+  VNB_CUDA(cudaGetDevice(&cur));
+  if (peer_device == cur) return VNB_OK;
+  int can = 0;
+  VNB_CUDA(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+  VNB_REQUIRE(can != 0, "peer_enable_access: device %d cannot access device %d over NVLink/PCIe peer-to-peer", cur, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return VNB_OK; }
+  if (e != cudaSuccess) return set_err(VNB_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+  return VNB_OK;
 }
 
 extern "C" int vnb_peer_wait(int world, const int* flags, int seq, void* stream) {

@@ -95,8 +95,9 @@ class PeerGather(DetectionGather):
     a one-warp kernel waits for the slot's `world` flags in front of the merge.  No rendezvous kernel holds SMs while
     it waits for the slowest rank, and collectives of different in-flight forwards do not serialise on one communicator.
 
-    The inboxes are plain CUDA allocations shared through CUDA IPC (torch's reductions, exchanged once with
-    all_gather_object).  Every slot has TWO inbox buffers used alternately: rank r pushes use u+2 of a slot only after
+    The inboxes are dedicated CUDA allocations shared through CUDA IPC (vnb_peer_alloc / vnb_peer_open; the 64-byte
+    handles are exchanged once with all_gather_object) and opened in the CONSUMER device's context, which is what maps
+    them peer-to-peer over NVLink.  Every slot has TWO inbox buffers used alternately: rank r pushes use u+2 of a slot only after
     its own merge of use u+1, which saw every peer's push u+1, which each peer issued after ITS merge of use u (stream
     order on the slot's stream) — so nobody overwrites a buffer a peer has not merged yet, with no acknowledgement
     traffic.  `slot` must be bound to one stream, as in bench.py."""
@@ -104,33 +105,43 @@ class PeerGather(DetectionGather):
     def __init__(self, world, rank, b, k, device, slots=1, group=None, gather_outputs=False):
         super().__init__(world, b, k, device, slots=slots, group=group, gather_outputs=gather_outputs)
         import ctypes as C
-        from torch.multiprocessing.reductions import reduce_tensor
+
+        from ._lib import check, lib
 
         self.rank, self.device = rank, torch.device(device)
         nb = self.nbytes
         self.depth = 2
-        # one allocation per rank: [slots][depth][world][nbytes] records, then [slots][depth][world] int32 flags
-        self.inbox = torch.zeros((slots, self.depth, world, nb), dtype=torch.uint8, device=device)
-        self.flags = torch.zeros((slots, self.depth, world), dtype=torch.int32, device=device)
-        torch.cuda.synchronize(device)
-        handles = [None] * world
-        dist.all_gather_object(handles, (reduce_tensor(self.inbox), reduce_tensor(self.flags)), group=group)
-        self._peers = []   # keep the mappings alive
-        inbox_ptr, flags_ptr = [], []
-        for r in range(world):
-            if r == rank:
-                ib, fl = self.inbox, self.flags
-            else:
-                (f1, a1), (f2, a2) = handles[r]
-                ib, fl = f1(*a1), f2(*a2)
-                # touching the mapping from this device makes torch enable peer access between the two GPUs
-                probe = torch.empty((16,), dtype=torch.uint8, device=device)
-                probe.copy_(ib.view(-1)[:16])
-                self._peers.append((ib, fl))
-            inbox_ptr.append(ib.data_ptr())
-            flags_ptr.append(fl.data_ptr())
-        torch.cuda.synchronize(device)
-        # (no barrier needed: every inbox was zeroed before the handle exchange above, itself a collective)
+        # one dedicated allocation per rank: [slots][depth][world][nbytes] records, then [slots][depth][world] int32 flags
+        n_inbox = slots * self.depth * world * nb
+        n_flags = slots * self.depth * world * 4
+        total = n_inbox + (n_flags + 255) // 256 * 256
+        with torch.cuda.device(self.device):
+            own = C.c_void_p()
+            handle = (C.c_ubyte * 64)()
+            check(lib.vnb_peer_alloc(total, C.byref(own), handle))
+            self._own = own.value
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            bases = []
+            self._opened = []
+            for r in range(world):
+                if r == rank:
+                    bases.append(self._own)
+                else:
+                    p_ = C.c_void_p()
+                    check(lib.vnb_peer_open((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p_)))
+                    self._opened.append(p_.value)
+                    bases.append(p_.value)
+        inbox_ptr = bases
+        flags_ptr = [p_ + n_inbox for p_ in bases]
+
+        class _Raw:   # zero-copy torch views of this rank's own allocation
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+        self.inbox = torch.as_tensor(_Raw(self._own, (slots, self.depth, world, nb), "|u1"), device=self.device)
+        self.flags = torch.as_tensor(_Raw(self._own + n_inbox, (slots, self.depth, world), "<i4"), device=self.device)
+        assert self.inbox.data_ptr() == self._own and self.flags.data_ptr() == self._own + n_inbox
         # per (slot, depth): host arrays of `world` device pointers
         self._ptrs = {}
         for s in range(slots):
