@@ -267,6 +267,53 @@ int vnb_fp_module_fused(int b, int n, int m, int c1, int c2, const float* dist, 
                         const float* vote_w0_xyz_f32, const float* seeds_xyz, float* votes_xyz, float* votes_feat,
                         void* stream);
 
+/* ------------------------------------------------------------------ evaluator -- */
+
+/* iou_3d(bbox1, bbox2)                                            evaluator.py:26-39
+ * boxes_a, boxes_b (n,8,3) f32 corner boxes (corners 0..3 = top face, y of corner 0 > y of corner 4) -> out (n) f64:
+ * BEV intersection area of the two top-face quadrilaterals (exact convex clipping in double precision; the reference
+ * calls shapely) x height overlap / union of volumes. */
+int vnb_iou3d_pairs(int n, const float* boxes_a, const float* boxes_b, double* out, void* stream);
+
+/* eval_det_cls(pred, gt, ovthresh)                                evaluator.py:77-151 (+ voc_ap :42-74)
+ * One class.  Detections: det_boxes (nd,8,3), det_scores (nd), det_img (nd) i32 image index in [0, nimg);
+ * ground truth: gt_boxes (ng,8,3) grouped by image, gt_offsets (nimg+1) i32 (image i owns rows gt_offsets[i] ..
+ * gt_offsets[i+1]-1).  Outputs, all f64 and in descending-confidence order (equal confidences in input order):
+ * rec (nd), prec (nd), ap (1).  npos = ng.  workspace: vnb_eval_det_cls_workspace_bytes(nd, ng). */
+size_t vnb_eval_det_cls_workspace_bytes(int nd, int ng);
+int vnb_eval_det_cls(int nd, int ng, int nimg, const float* det_boxes, const float* det_scores, const int* det_img,
+                     const float* gt_boxes, const int* gt_offsets, double ovthresh, double* rec, double* prec,
+                     double* ap, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------ input stage */
+
+/* Point subsampling + upright-depth -> upright-camera axis flip + training augmentation, fused.
+ * dataset.py:185-190 (subsample, flip_axis_to_camera sunutils.py:70-77), :219-231,302-308 (x / z flips, rotation about
+ * y, scale).  raw_upright_depth (b,n_raw,3) f32; choice (b,n) i32 indices into the raw cloud (NULL: the first n points);
+ * per cloud and all optional (NULL = skip): flip_x, flip_z (b) u8, roty_angle (b) f64 radians, scale (b) f64 — the
+ * host's random draws.  -> xyz (b,n,3) f32 and, if not NULL, height (b,n) f32 = floor_y - y (the height-above-floor
+ * input feature BASELINE.json names).  Arithmetic in double, one rounding to float. */
+int vnb_prepare_input(int b, int n_raw, int n, const float* raw_upright_depth, const int* choice,
+                      const unsigned char* flip_x, const unsigned char* flip_z, const double* roty_angle,
+                      const double* scale, float* xyz, float* height, double floor_y, void* stream);
+
+/* ------------------------------------------------------------------ losses ---- */
+
+/* Label assignment + training losses (forward values)              model.py:62-84, 141-231
+ * seeds_xyz, votes_xyz (b,n_seed,3); proposals_xyz (b,n_prop,3); proposals_output (b,n_prop,79); dense ground truth as
+ * the reference feeds it: bboxes_xyz, bboxes_lwh (b,n_box,3), bboxes_roty (b,n_box), semantic / heading / size labels
+ * (b,n_box) i32, heading_residuals (b,n_box), size_residuals (b,n_box,3); thresholds config.py:4-5 (0.3 / 0.6).
+ * -> out14 (14) f64: total_cost, vote_reg_loss, obj_cls_loss, box_loss, center_loss (incl. the dual term),
+ *    heading_cls_loss, heading_residual_loss, size_cls_loss, size_residual_loss, sem_cls_loss, obj_accuracy,
+ *    sem_accuracy, number of positive proposals, number of negative proposals.  Means over empty sets are NaN (as
+ *    tf.reduce_mean).  workspace: 128 bytes. */
+int vnb_votenet_losses(int b, int n_seed, int n_prop, int n_box, const float* seeds_xyz, const float* votes_xyz,
+                       const float* proposals_xyz, const float* proposals_output, const float* bboxes_xyz,
+                       const float* bboxes_lwh, const float* bboxes_roty, const int* semantic_labels,
+                       const int* heading_labels, const float* heading_residuals, const int* size_labels,
+                       const float* size_residuals, float positive_thres, float negative_thres, double* out14,
+                       void* workspace_128_bytes, void* stream);
+
 /* ------------------------------------------------------------------ backward ops ---- */
 
 /* scatteraddpointLauncher(b,n,m,out_g,idx,inp_g)              tf_ops/sampling/tf_sampling_g.cu:183-192,209-211

@@ -36,6 +36,11 @@ _SIGS = {
     "vnb_query_ball_point_workspace_bytes": ([_i, _i], _sz),
     "vnb_query_ball_point_ws": ([_i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p], _i),
     "vnb_merge_detections": ([_i, _i, _i, _p, _sz, _sz, _sz, _sz, _sz, _sz, _p, _p, _p, _p, _p, _p], _i),
+    "vnb_votenet_losses": ([_i, _i, _i, _i] + [_p] * 12 + [_f, _f, _p, _p, _p], _i),
+    "vnb_prepare_input": ([_i, _i, _i] + [_p] * 8 + [C.c_double, _p], _i),
+    "vnb_iou3d_pairs": ([_i, _p, _p, _p, _p], _i),
+    "vnb_eval_det_cls_workspace_bytes": ([_i, _i], _sz),
+    "vnb_eval_det_cls": ([_i, _i, _i, _p, _p, _p, _p, _p, C.c_double, _p, _p, _p, _p, _p], _i),
     "vnb_peer_push_record": ([_i, _i, _p, _sz, _p, _p, _i, _p], _i),
     "vnb_peer_wait": ([_i, _p, _i, _p], _i),
     "vnb_peer_enable_access": ([_i], _i),

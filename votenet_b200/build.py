@@ -35,6 +35,9 @@ SOURCES = {
     "fp_chain.cu": [],
     "grad_ops.cu": [],
     "peer.cu": [],
+    "losses.cu": ["-fmad=false"],
+    "input_stage.cu": ["-fmad=false"],
+    "eval_ap.cu": ["-fmad=false"],
 }
 
 
