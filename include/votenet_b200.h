@@ -6,7 +6,8 @@
  *   - every pointer is a DEVICE pointer to dense, row-major, contiguous data; inputs are const;
  *   - the CALLER allocates every output and workspace buffer; the library never allocates or frees;
  *   - launches are asynchronous on the given `stream` (a cudaStream_t passed as void*); no hidden host sync;
- *     every entry point is re-entrant, stateless and CUDA-graph capturable;
+ *     every entry point is re-entrant and CUDA-graph capturable; the only process-global state is the experiment knobs of
+ *     vnb_set_tuning (documented there as not synchronised) and the debugging hooks;
  *   - return 0 on success; VNB_ERR_INVALID for a shape / attribute violation (where the reference op raises
  *     errors::InvalidArgument), VNB_ERR_CUDA for a CUDA launch error (which the reference never checks).
  *     vnb_last_error() returns a thread-local message for the last non-zero return.
@@ -32,12 +33,17 @@ int vnb_abi_version(void);
 const char* vnb_last_error(void);
 /* number of kernel launches this library has issued in this process (all threads); bench.py reports it */
 unsigned long long vnb_launch_count(void);
-/* Tuning knobs for experiments (defaults are what bench.py uses): "fps_mode" 0 = cluster barrier / 1 = tagged slots,
- * "fps_cluster" 0 = auto or a forced cluster size, "ball_query_variant" 0 = exhaustive scan / 1 = grid + bitmap. */
+/* Tuning knobs for experiments (defaults are what bench.py uses) — PROCESS-GLOBAL and not synchronised: set them before
+ * launching from several threads, never concurrently with calls (the entry points themselves keep no other state and are
+ * re-entrant).  "fps_variant" 1 = bucket-pruned sampler for 2048 < n <= 20480 (default) / 0 = register-cluster sampler only,
+ * "fps_cluster" CTAs per cluster of the latter (0 = auto), "ball_query_variant" 0 = exhaustive scan / 1 = grid + bitmap,
+ * "bq_grid_min_n", "sa_variant" 2 = MMA issuers park (default) / 3 = poll, "sa_sms", "sa_split", "sa_min_tpc" (fewest
+ * tiles per CTA of the fused SA kernels), "nms_cluster" CTAs per cloud of the NMS kernel (1, 2, 4, 8), "fps_ablate"
+ * (timing experiments only: wrong results).  Unknown keys return VNB_ERR_INVALID. */
 int vnb_set_tuning(const char* key, int value);
-/* Debugging aid: when given a device buffer of 16 x 8 int64, the next cluster-FPS launches (256 threads x 10 points)
- * accumulate per-phase cycle counts of warp 0 of every CTA of cloud 0 into it; NULL switches it off. */
-int vnb_debug_fps_profile(void* device_buffer_16x8_i64);
+/* Debugging aid: when given a device buffer of 16 x 10 int64, the next bucket-pruned FPS launches accumulate, per warp of
+ * cloud 0, dependency-anchored cycle counts of the round's phases into it (scripts/gpu_fps_phases.py); NULL = off. */
+int vnb_debug_fps_profile(void* device_buffer_16x10_i64);
 /* Debugging aid: when given a device buffer of 8 x 64 x 2 int64, CTA 0 of the next fused-SA launches stamps clock64() at
  * the start / end of every pipeline stage (roles P, M1, M2, M3, E1, E2, E3a, E3b) of its first 64 tiles; NULL = off. */
 int vnb_debug_sa_trace(void* device_buffer_8x64x2_i64);

@@ -26,10 +26,8 @@ SOURCES = {
     "nms3d.cu": ["-fmad=false"],
     "mlp_simt.cu": [],
     "mlp_tc.cu": [],
-    "sa_ws.cu": [],
     "sa_ws2.cu": [],
     "sa_pack.cu": [],
-    "sa1_ws.cu": [],
     "sa1_ws2.cu": [],
     "linear_tc.cu": [],
     "fp_chain.cu": [],

@@ -311,28 +311,12 @@ static int launch_fps(int b, int n, int m, int CL, const float* xyz, int* out, c
 
 long long* g_fps_prof = nullptr;  // debugging: device buffer of 16*8 cycle counters (vnb_debug_fps_profile)
 
-static int launch_fps_prof(int b, int n, int m, int CL, const float* xyz, int* out, cudaStream_t st) {
-  auto kern = fps_cluster_kernel<256, 10, 1, false, true>;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(b * CL));
-  cfg.blockDim = dim3(256);
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  const int* noflags = nullptr;
-  VNB_CUDA(cudaLaunchKernelEx(&cfg, kern, n, m, CL, xyz, out, noflags, g_fps_prof));
-  return check_launch("farthest_point_sample (profiled)");
-}
-
+// Instances of the register / cluster sampler that are kept (it is the general fallback — clouds beyond the pruned
+// kernel's 20 480 points, the small nested levels when their identity proof fails — not the benchmarked path):
+//   one CTA of 512 threads, xyz in shared memory, for n <= 8192;  clusters of 256-thread CTAs (tagged slots) above.
 template <int T, int P>
 static int launch_fps_mode(int b, int n, int m, int CL, const float* xyz, int* out, const int* flags, cudaStream_t st) {
-  if (g_fps_prof != nullptr && T == 256 && P == 10 && CL > 1 && CL <= 8 && flags == nullptr)
-    return launch_fps_prof(b, n, m, CL, xyz, out, st);
   if (CL == 1) return launch_fps<T, P, 1, true>(b, n, m, CL, xyz, out, flags, st);
-  if (g_fps_mode == 0) return launch_fps<T, P, 0, false>(b, n, m, CL, xyz, out, flags, st);
   return launch_fps<T, P, 1, false>(b, n, m, CL, xyz, out, flags, st);
 }
 
@@ -342,43 +326,27 @@ static int fps_dispatch_t(int b, int n, int m, int CL, const float* xyz, int* ou
   if (per <= 1) return launch_fps_mode<T, 1>(b, n, m, CL, xyz, out, flags, st);
   if (per <= 2) return launch_fps_mode<T, 2>(b, n, m, CL, xyz, out, flags, st);
   if (per <= 4) return launch_fps_mode<T, 4>(b, n, m, CL, xyz, out, flags, st);
-  if (per <= 5) return launch_fps_mode<T, 5>(b, n, m, CL, xyz, out, flags, st);
   if (per <= 8) return launch_fps_mode<T, 8>(b, n, m, CL, xyz, out, flags, st);
-  if (per <= 10) return launch_fps_mode<T, 10>(b, n, m, CL, xyz, out, flags, st);
-  if constexpr (T <= 512) {
-    if (per <= 16) return launch_fps_mode<T, 16>(b, n, m, CL, xyz, out, flags, st);
-    if constexpr (T <= 256) {
-      if (per <= 20) return launch_fps_mode<T, 20>(b, n, m, CL, xyz, out, flags, st);
-    }
+  if (per <= 16) return launch_fps_mode<T, 16>(b, n, m, CL, xyz, out, flags, st);
+  if constexpr (T <= 256) {
+    if (per <= 20) return launch_fps_mode<T, 20>(b, n, m, CL, xyz, out, flags, st);
   }
   return set_err(VNB_ERR_INVALID, "farthest_point_sample: %d points per thread do not fit (cluster %d x %d threads)", per, CL, T);
 }
 
-// Geometry: T threads per CTA (g_fps_threads: 256 / 512 / 1024) x CL CTAs per cluster (g_fps_cl or automatic).  Few big
-// CTAs minimise the SM footprint of one call (better throughput when several calls overlap); many small CTAs minimise
-// the latency of one call.  CL*T must be a multiple of 512 (per-thread tie rule, see the header comment).
+// Geometry of the fallback sampler: n <= 8192 -> one CTA of 512 threads; above, clusters of 256-thread CTAs
+// (g_fps_cl CTAs per cluster, or as many as ~10 points per thread need; at most 16).
 static int fps_dispatch(int b, int n, int m, const float* xyz, int* out, const int* flags, cudaStream_t st,
                         int* tie_out = nullptr, int tie_rounds = 0) {
   if (n <= fps_pruned_capacity() && ((g_fps_variant == 1 && n > 2048) || g_fps_variant == 2))
     return launch_fps_pruned(b, n, m, xyz, out, flags, tie_out, tie_rounds, st);
   // the register / cluster kernels do not track ties: report "round 0" (no round is known to be tie-free)
   if (tie_out != nullptr) VNB_CUDA(cudaMemsetAsync(tie_out, 0, sizeof(int) * (size_t)b, st));
-  int T = g_fps_threads;
-  int CL = g_fps_cl;
-  if (n <= 2048 && CL <= 1) {  // small clouds: one CTA of 512 threads
-    T = 512; CL = 1;
-  } else {
-    if (T != 256 && T != 512 && T != 1024) T = 256;
-    const int pmax = T == 256 ? 20 : (T == 512 ? 16 : 10);
-    if (CL < 1) CL = 1;
-    if (T == 256 && CL < 2) CL = 2;
-    while (CL < 16 && (long long)CL * T * pmax < n) CL *= 2;
-    if (g_fps_cl == 0) {  // automatic: ~10 points per thread
-      while (CL < 8 && (long long)CL * T * 10 < n) CL *= 2;
-    }
-  }
-  if (T == 1024) return fps_dispatch_t<1024>(b, n, m, CL, xyz, out, flags, st);
-  if (T == 512) return fps_dispatch_t<512>(b, n, m, CL, xyz, out, flags, st);
+  if (n <= 8192 && g_fps_cl <= 1) return fps_dispatch_t<512>(b, n, m, 1, xyz, out, flags, st);
+  int CL = g_fps_cl < 2 ? 2 : g_fps_cl;
+  while (CL < 16 && (long long)CL * 256 * 20 < n) CL *= 2;
+  if (g_fps_cl == 0)
+    while (CL < 8 && (long long)CL * 256 * 10 < n) CL *= 2;
   return fps_dispatch_t<256>(b, n, m, CL, xyz, out, flags, st);
 }
 

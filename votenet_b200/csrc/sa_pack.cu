@@ -71,6 +71,32 @@ __global__ void __launch_bounds__(PK_T) sa_pack_tiles_kernel(int total, const in
   }
 }
 
+// relative coordinates (utils.py:51) and flat source-row index of every grouped row: rel[(g*64+s)] = {xyz[idx]-c, row}
+// pts_cnt (optional): rows beyond the centroid's slot (16 / 32 / 64 rows, sa_pack.cu) are never read and are skipped.
+__global__ void group_rel_kernel(int n, int m, long long total_rows, const float* __restrict__ xyz,
+                                 const float* __restrict__ new_xyz, const int* __restrict__ idx,
+                                 const int* __restrict__ pts_cnt, float4* __restrict__ rel) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_rows) return;
+  const int g = (int)(t >> 6);
+  if (pts_cnt != nullptr) {
+    const int c = pts_cnt[g];
+    const int slot = (c <= 0 || c > 32) ? 64 : (c > 16 ? 32 : 16);
+    if ((int)(t & 63) >= slot) return;
+  }
+  const int bi = g / m;
+  const int pid = idx[t];
+  const float* pp = xyz + ((size_t)bi * n + pid) * 3;
+  const float* cc = new_xyz + (size_t)g * 3;
+  rel[t] = make_float4(pp[0] - cc[0], pp[1] - cc[1], pp[2] - cc[2], __int_as_float(bi * n + pid));
+}
+
+void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx,
+                      const int* pts_cnt, void* rel, cudaStream_t st) {
+  group_rel_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(n, m, rows, xyz, new_xyz, idx, pts_cnt,
+                                                                   static_cast<float4*>(rel));
+}
+
 // workspace layout of the fused SA path: [rel: rows * 16 B][hdr: 256 B][tile_cid: (total/2 + 4) * 32 B]
 size_t sa_rel_bytes(long long rows) { return ((size_t)rows * 16 + 255) / 256 * 256; }
 size_t sa_tile_table_bytes(int total_centroids) { return 256 + ((size_t)total_centroids / 2 + 4) * 32; }
