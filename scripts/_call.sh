@@ -1,10 +1,7 @@
-for IF in 16 20 24 32; do
-for ST in 20 600; do
-timeout 300 python bench.py --steps $ST --warmup 5 --no-cpu-baseline --inflight $IF > gpurun_out/sweep.json 2> gpurun_out/sweep.err || tail -2 gpurun_out/sweep.err
-python - <<PY
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 6
+timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; echo "bench exit=$?"; tail -2 gpurun_out/r2_bench_default.err
+python - <<'PY'
 import json
-d = json.loads(open('gpurun_out/sweep.json').read().strip().splitlines()[-1])
-print('inflight $IF steps $ST: value', round(d['value'], 1), 'ms/step', round(d['ms_per_step'], 4), 'e2e', round(d['e2e']['value'], 1), 'lat1', round(d['latency_ms_inflight1'],3))
+d = json.loads(open('gpurun_out/r2_bench_default.json').read().strip().splitlines()[-1])
+print('default: value', round(d['value'], 1), 'ms/step', round(d['ms_per_step'], 4), 'e2e', round(d['e2e']['value'], 1), 'lat1', d['latency_ms_inflight1'])
 PY
-done
-done
