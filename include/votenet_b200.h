@@ -4,7 +4,8 @@
  * C-ABI twin of one reference launcher or CPU loop (cited per function; paths relative to the reference repo
  * qq456cvb/VoteNet).  Conventions, all mirroring the reference's native side:
  *   - every pointer is a DEVICE pointer to dense, row-major, contiguous data; inputs are const;
- *   - the CALLER allocates every output and workspace buffer; the library never allocates or frees;
+ *   - the CALLER allocates every output and workspace buffer; the library never allocates or frees (the one exception
+ *     is the explicit vnb_peer_alloc / vnb_peer_free pair of the multi-GPU exchange);
  *   - launches are asynchronous on the given `stream` (a cudaStream_t passed as void*); no hidden host sync;
  *     every entry point is re-entrant and CUDA-graph capturable; the only process-global state is the experiment knobs of
  *     vnb_set_tuning (documented there as not synchronised) and the debugging hooks;
@@ -144,6 +145,10 @@ int vnb_three_interpolate(int b, int m, int c, int n, const float* points, const
  *   out_count (1)     i32  number of valid rows in out_idx
  * workspace: vnb_nms3d_workspace_bytes(b,k) bytes of device memory. */
 size_t vnb_nms3d_workspace_bytes(int b, int k);
+/* After a vnb_nms3d / vnb_decode_nms3d call the u32 at this byte offset of its workspace holds the number of clipped
+ * pairs whose IoU fell within 1e-5 of iou_threshold — the only pairs on which a last-bit difference from the reference's
+ * x86 arithmetic could change the keep mask (0 on every parity-test input). */
+size_t vnb_nms3d_near_threshold_offset(int b, int k);
 int vnb_nms3d(int b, int k, const float* bbox, const float* scores, const float* objectiveness, float iou_threshold,
               uint8_t* keep, int* out_idx, int* out_count, void* workspace, void* stream);
 
@@ -340,6 +345,19 @@ int vnb_group_point_grad(int b, int n, int c, int m, int nsample, const float* g
  * rounding of a different summation order. */
 int vnb_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx, const float* weight,
                                float* grad_points, void* stream);
+
+/* Backward of the fused set-abstraction layer (vnb_sa_group_mlp_max): the gradients TensorFlow autodiff produces for
+ * utils.py:49-55,120-132 (group -> 3 x (1x1 conv + ReLU) -> reduce_max), including the GroupPointGrad scatter
+ * (tf_grouping_g.cu:61-78), in one kernel that rematerialises the forward per centroid in fp32 (csrc/sa_backward.cu).
+ * w1 (3+c,c1), w2 (c1,c2), w3 (c2,c3) BN-folded, row-major; w1_t (c1,3+c), w2_t (c2,c1) their transposes;
+ * grad_out (b,m,c3).  Every grad_* output must be ZEROED by the caller and is accumulated into (float reductions):
+ * grad_feat (b,n,c), grad_xyz (b,n,3), grad_new_xyz (b,m,3) — any of the three may be NULL — and grad_w1..3 / grad_b1..3 shaped like the weights. */
+int vnb_sa_group_mlp_max_backward(int b, int n, int c, int m, int nsample, const float* xyz, const float* feat,
+                                  const float* new_xyz, const int* idx, int c1, int c2, int c3, const float* w1,
+                                  const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
+                                  const float* w1_t, const float* w2_t, const float* grad_out, float* grad_feat,
+                                  float* grad_xyz, float* grad_new_xyz, float* grad_w1, float* grad_b1, float* grad_w2,
+                                  float* grad_b2, float* grad_w3, float* grad_b3, void* stream);
 
 /* row-wise concat / split helpers: out (rows, ca+cb) = [a (rows,ca), b (rows,cb)]  and the inverse */
 int vnb_concat2(int rows, int ca, int cb, const float* a, const float* b, float* out, void* stream);

@@ -129,3 +129,32 @@ def test_trainable_fp_gradients(cuda):
     assert (out.detach().cpu().double() - h.detach()).abs().max().item() < 1e-4
     assert (p2.grad.cpu().double() - p2c.grad).abs().max().item() < 1e-4 * p2c.grad.abs().max().item()
     assert (p1.grad.cpu().double() - p1c.grad).abs().max().item() < 1e-4 * p1c.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("b,n,c,m,dims,r", [(2, 1500, 16, 128, (64, 64, 128), 0.25), (1, 900, 128, 64, (128, 128, 256), 0.3),
+                                            (2, 700, 1, 40, (64, 64, 128), 0.2)])
+def test_fused_sa_backward_kernel(cuda, b, n, c, m, dims, r):
+    """vnb_sa_group_mlp_max_backward (one rematerialising kernel) against the composed autograd path (validated above
+    against float64 CPU autograd): gradients w.r.t. features, xyz and all six parameters."""
+    from votenet_b200.train import pointnet_sa_module_fused_trainable, pointnet_sa_module_trainable
+
+    rng = np.random.default_rng(c)
+    xyz_np = rng.random((b, n, 3)).astype(np.float32)
+    pts_np = rng.standard_normal((b, n, c)).astype(np.float32)
+    g_np = None
+    grads = []
+    for fn in (pointnet_sa_module_trainable, pointnet_sa_module_fused_trainable):
+        layers = _params(np.random.default_rng(1), [3 + c] + list(dims), cuda)
+        xyz = torch.as_tensor(xyz_np, device=cuda).requires_grad_(True)
+        pts = torch.as_tensor(pts_np, device=cuda).requires_grad_(True)
+        _, out, idx = fn(xyz, pts, m, r, 64, layers)
+        if g_np is None:
+            g_np = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+        out.backward(torch.as_tensor(g_np, device=cuda))
+        grads.append((out.detach(), [pts.grad, xyz.grad] + [t.grad for Wb in layers for t in Wb]))
+    (o_ref, g_ref), (o_got, g_got) = grads
+    assert (o_ref - o_got).abs().max().item() < 2e-5 * o_ref.abs().max().item()
+    names = ["d points", "d xyz", "dW1", "db1", "dW2", "db2", "dW3", "db3"]
+    for nme, a, bb in zip(names, g_ref, g_got):
+        scale = max(a.abs().max().item(), 1e-6)
+        assert (a - bb).abs().max().item() < 2e-4 * scale, (nme, (a - bb).abs().max().item(), scale)

@@ -36,6 +36,7 @@ _SIGS = {
     "vnb_query_ball_point_workspace_bytes": ([_i, _i], _sz),
     "vnb_query_ball_point_ws": ([_i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p], _i),
     "vnb_merge_detections": ([_i, _i, _i, _p, _sz, _sz, _sz, _sz, _sz, _sz, _p, _p, _p, _p, _p, _p], _i),
+    "vnb_sa_group_mlp_max_backward": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i] + [_p] * 18 + [_p], _i),
     "vnb_votenet_losses": ([_i, _i, _i, _i] + [_p] * 12 + [_f, _f, _p, _p, _p], _i),
     "vnb_prepare_input": ([_i, _i, _i] + [_p] * 8 + [C.c_double, _p], _i),
     "vnb_iou3d_pairs": ([_i, _p, _p, _p, _p], _i),
@@ -56,6 +57,7 @@ _SIGS = {
     "vnb_three_nn": ([_i, _i, _i, _p, _p, _p, _p, _p], _i),
     "vnb_three_interpolate": ([_i, _i, _i, _i, _p, _p, _p, _p, _p], _i),
     "vnb_nms3d_workspace_bytes": ([_i, _i], _sz),
+    "vnb_nms3d_near_threshold_offset": ([_i, _i], _sz),
     "vnb_nms3d": ([_i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p], _i),
     "vnb_weight_image_bytes": ([_i, _i], _sz),
     "vnb_pack_weight_f16": ([_i, _i, _p, _p, _p], _i),

@@ -33,6 +33,7 @@ SOURCES = {
     "fp_chain.cu": [],
     "grad_ops.cu": [],
     "peer.cu": [],
+    "sa_backward.cu": [],
     "losses.cu": ["-fmad=false"],
     "input_stage.cu": ["-fmad=false"],
     "eval_ap.cu": ["-fmad=false"],

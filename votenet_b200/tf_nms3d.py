@@ -23,7 +23,15 @@ def nms3d_raw(bboxes, scores, objectiveness, iou_threshold):
     check(lib.vnb_nms3d(b, k, dptr(bboxes, torch.float32, "bboxes"), dptr(scores, torch.float32, "scores"),
                         dptr(objectiveness, torch.float32, "objectiveness"), thr, dptr(keep), dptr(idx), dptr(count),
                         dptr(ws), stream_ptr()))
+    nms3d_raw.last_workspace = (ws, lib.vnb_nms3d_near_threshold_offset(b, k))
     return keep, idx, count
+
+
+def near_threshold_pairs():
+    """Number of clipped pairs of the LAST nms3d_raw call whose IoU lay within 1e-5 of the threshold (one host sync): 0
+    means no pair was close enough for a last-bit arithmetic difference to change the keep mask."""
+    ws, off = nms3d_raw.last_workspace
+    return int(ws[off:off + 4].view(torch.int32).item())
 
 
 def NMS3D(bboxes, scores, objectiveness, iou_threshold):

@@ -66,3 +66,59 @@ def pointnet_fp_module_trainable(xyz1, xyz2, points1, points2, layers):
     for W, b in layers:                                                                      # :291-292
         h = _dense(h, W, b, True)
     return h
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The set-abstraction layer as ONE differentiable op: fused forward kernel + fused backward kernel (csrc/sa_backward.cu)
+class _FusedSAFn(torch.autograd.Function):
+    """out (B,m,C3) = max_r relu(relu(relu([xyz[idx]-new_xyz, feat[idx]] W1+b1) W2+b2) W3+b3) with hand-written forward AND
+    backward kernels: forward = the fp32 fused kernel (vnb_sa_group_mlp_max, precision 0); backward rematerialises the
+    forward per centroid and returns gradients for feat, xyz, new_xyz and the six parameters in one launch."""
+
+    @staticmethod
+    def forward(ctx, xyz, feat, new_xyz, idx, W1, b1, W2, b2, W3, b3):
+        from ._lib import check, dptr, lib, stream_ptr
+
+        b, n, _ = xyz.shape
+        c, m, ns = feat.shape[2], idx.shape[1], idx.shape[2]
+        args = [t.detach().contiguous() for t in (xyz, feat, new_xyz, W1, b1, W2, b2, W3, b3)]
+        xyz_, feat_, new_xyz_, W1_, b1_, W2_, b2_, W3_, b3_ = args
+        out = torch.empty((b, m, W3_.shape[1]), dtype=torch.float32, device=xyz.device)
+        check(lib.vnb_sa_group_mlp_max(b, n, c, m, ns, dptr(xyz_), dptr(feat_), dptr(new_xyz_), dptr(idx), W1_.shape[1],
+                                       W2_.shape[1], W3_.shape[1], dptr(W1_), dptr(b1_), dptr(W2_), dptr(b2_), dptr(W3_), dptr(b3_),
+                                       None, None, None, None, dptr(out), 0, None, stream_ptr()))
+        ctx.save_for_backward(xyz_, feat_, new_xyz_, idx, W1_, b1_, W2_, b2_, W3_, b3_)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from ._lib import check, dptr, lib, stream_ptr
+
+        xyz, feat, new_xyz, idx, W1, b1, W2, b2, W3, b3 = ctx.saved_tensors
+        b, n, _ = xyz.shape
+        c, m, ns = feat.shape[2], idx.shape[1], idx.shape[2]
+        Z = torch.zeros_like
+        g_feat, g_xyz, g_new = Z(feat), Z(xyz), Z(new_xyz)
+        gW1, gb1, gW2, gb2, gW3, gb3 = Z(W1), Z(b1), Z(W2), Z(b2), Z(W3), Z(b3)
+        check(lib.vnb_sa_group_mlp_max_backward(b, n, c, m, ns, dptr(xyz), dptr(feat), dptr(new_xyz), dptr(idx), W1.shape[1],
+                                                W2.shape[1], W3.shape[1], dptr(W1), dptr(b1), dptr(W2), dptr(b2), dptr(W3),
+                                                dptr(b3), dptr(W1.t().contiguous()), dptr(W2.t().contiguous()),
+                                                dptr(grad_out.contiguous()), dptr(g_feat), dptr(g_xyz), dptr(g_new), dptr(gW1),
+                                                dptr(gb1), dptr(gW2), dptr(gb2), dptr(gW3), dptr(gb3), stream_ptr()))
+        return g_xyz, g_feat, g_new, None, gW1, gb1, gW2, gb2, gW3, gb3
+
+
+def pointnet_sa_module_fused_trainable(xyz, points, npoint, radius, nsample, layers, sample_xyz=None):
+    """pointnet_sa_module (utils.py:93-158, three-layer mlp, max pooling) as fused forward + fused backward kernels.
+    `layers` = [(W1,b1),(W2,b2),(W3,b3)].  -> (new_xyz, new_points (B,m,C3), idx); differentiable w.r.t. points, xyz and
+    the parameters."""
+    fps_in = sample_xyz if sample_xyz is not None else xyz
+    with torch.no_grad():
+        fps = tf_sampling.farthest_point_sample_nested if fps_in.shape[1] <= 4096 else tf_sampling.farthest_point_sample
+        fps_idx = fps(npoint, fps_in.detach())
+    new_xyz = tf_sampling.gather_point(xyz, fps_idx)
+    with torch.no_grad():
+        idx, _ = tf_grouping.query_ball_point(radius, nsample, xyz.detach(), new_xyz.detach())
+    (W1, b1), (W2, b2), (W3, b3) = layers
+    out = _FusedSAFn.apply(xyz, points, new_xyz, idx, W1, b1, W2, b2, W3, b3)
+    return new_xyz, out, idx
