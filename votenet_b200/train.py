@@ -100,10 +100,12 @@ class _FusedSAFn(torch.autograd.Function):
         Z = torch.zeros_like
         g_feat, g_xyz, g_new = Z(feat), Z(xyz), Z(new_xyz)
         gW1, gb1, gW2, gb2, gW3, gb3 = Z(W1), Z(b1), Z(W2), Z(b2), Z(W3), Z(b3)
+        # named, so that they outlive the launch (a temporary freed at once would be handed to the next allocation)
+        W1t, W2t, gout = W1.t().contiguous(), W2.t().contiguous(), grad_out.contiguous()
         check(lib.vnb_sa_group_mlp_max_backward(b, n, c, m, ns, dptr(xyz), dptr(feat), dptr(new_xyz), dptr(idx), W1.shape[1],
                                                 W2.shape[1], W3.shape[1], dptr(W1), dptr(b1), dptr(W2), dptr(b2), dptr(W3),
-                                                dptr(b3), dptr(W1.t().contiguous()), dptr(W2.t().contiguous()),
-                                                dptr(grad_out.contiguous()), dptr(g_feat), dptr(g_xyz), dptr(g_new), dptr(gW1),
+                                                dptr(b3), dptr(W1t), dptr(W2t),
+                                                dptr(gout), dptr(g_feat), dptr(g_xyz), dptr(g_new), dptr(gW1),
                                                 dptr(gb1), dptr(gW2), dptr(gb2), dptr(gW3), dptr(gb3), stream_ptr()))
         return g_xyz, g_feat, g_new, None, gW1, gb1, gW2, gb2, gW3, gb3
 
