@@ -73,26 +73,29 @@ __device__ __forceinline__ uint32_t spread4(uint32_t v) {  // abcd -> a00b00c00d
 // champion (first maximum in descending tie-key order = the reference's per-thread rule), its coordinates, and how many
 // of the lane's points share that maximum.
 template <int S, bool TIES>
-__device__ __forceinline__ void rescan_head(const float2* __restrict__ sxy, const float* __restrict__ sz, int tid,
+__device__ __forceinline__ void rescan_head(const float2* __restrict__ sxy, const float* __restrict__ sz,
+                                            const uint16_t* __restrict__ stie, int tid,
                                             const float (&zr)[PZR], float (&td)[PP],
                                             float lx, float ly, float lz, float& best, int& bq, int& same, float& bx,
-                                            float& by, float& bz) {
+                                            float& by, float& bz, uint32_t& btk) {
   float xs[PQ], ys[PQ], z[PQ];
+  uint32_t tks[PQ];   // the lane's tie keys, loaded beside the coordinates so that the election never waits for them
 #pragma unroll
   for (int q = 0; q < PQ; ++q) {
     const int i = S * PQ + q;
     const float2 v = sxy[i * PT + tid];
+    tks[q] = stie[i * PT + tid];
     xs[q] = v.x; ys[q] = v.y;
     z[q] = i < PZR ? zr[i < PZR ? i : 0] : sz[(i - PZR) * PT + tid];
     td[i] = fminf(d2_ref_gpu(v.x - lx, v.y - ly, z[q] - lz), td[i]);
   }
   best = fmaxf(fmaxf(fmaxf(td[S * PQ], td[S * PQ + 1]), fmaxf(td[S * PQ + 2], td[S * PQ + 3])), td[S * PQ + 4]);
   bq = PQ - 1;
-  bx = xs[PQ - 1]; by = ys[PQ - 1]; bz = z[PQ - 1];
+  bx = xs[PQ - 1]; by = ys[PQ - 1]; bz = z[PQ - 1]; btk = tks[PQ - 1];
   same = 0;
 #pragma unroll
   for (int q = PQ - 2; q >= 0; --q)
-    if (td[S * PQ + q] == best) { bq = q; bx = xs[q]; by = ys[q]; bz = z[q]; }
+    if (td[S * PQ + q] == best) { bq = q; bx = xs[q]; by = ys[q]; bz = z[q]; btk = tks[q]; }
   if (TIES) {
 #pragma unroll
     for (int q = 0; q < PQ; ++q) same += td[S * PQ + q] == best ? 1 : 0;
@@ -286,8 +289,7 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
     if (PROF && mask) { pacc[4] += __popc(mask); pacc[5] += 1; }
     // ---- rescan the active sub-buckets of this warp, then re-elect the warp's champion
     if (!ABL && mask) {   // (the ablation variant has no rescan code at all: measures the loop without its bulk)
-      auto elect = [&](int s, float best, int bq, int same, float bx, float by, float bz) {
-        const uint32_t tkm = stie[(s * PQ + bq) * PT + tid];    // in flight beside the first reduction
+      auto elect = [&](int s, float best, int bq, int same, float bx, float by, float bz, uint32_t tkm) {
         const int whi = redux_max_s32(__float_as_int(best));
         const bool mine = __float_as_int(best) == whi;
         const uint32_t wk = redux_max(mine ? ((tkm << 5) | (uint32_t)lane) : 0u);
@@ -306,10 +308,11 @@ __global__ void __launch_bounds__(PT, 1) fps_pruned_kernel(int n, int m, const f
       };
       float best, bx, by, bz;
       int bq, same;
-#define VNB_RESCAN(S)                                                                        \
-      if (mask & (1u << S)) {                                                                  \
-        rescan_head<S, TIES>(sxy, sz, tid, zr, td, lx, ly, lz, best, bq, same, bx, by, bz);    \
-        elect(S, best, bq, same, bx, by, bz);                                                  \
+      uint32_t btk;
+#define VNB_RESCAN(S)                                                                               \
+      if (mask & (1u << S)) {                                                                         \
+        rescan_head<S, TIES>(sxy, sz, stie, tid, zr, td, lx, ly, lz, best, bq, same, bx, by, bz, btk);  \
+        elect(S, best, bq, same, bx, by, bz, btk);                                                    \
       }
       VNB_RESCAN(0) VNB_RESCAN(1) VNB_RESCAN(2) VNB_RESCAN(3) VNB_RESCAN(4) VNB_RESCAN(5) VNB_RESCAN(6) VNB_RESCAN(7)
 #undef VNB_RESCAN
