@@ -79,7 +79,7 @@ int vnb_farthest_point_sample_nested(int b, int n, int m, const float* xyz, int*
  * of the first n picks of such a parent call (new_xyz of the previous level, utils.py:42-45): if the parent's first
  * tie round is >= m, every round j < m had a unique arg-max p_j over the parent's superset, p_j is in the subset, the
  * running distances are the same floats, hence the subset's FPS picks position j — the identity prefix holds with no
- * check at all.  Clouds whose hint is smaller fall back to the parallel proof, then to the sequential sampler.  The
+ * check at all.  Clouds whose hint is smaller go to the sequential sampler.  The
  * caller vouches for the provenance (wrong provenance = wrong indices); results are otherwise bit-identical. */
 int vnb_farthest_point_sample_ties(int b, int n, int m, const float* xyz, int* out_idx, int* first_tie_round,
                                    int track_rounds, void* stream);

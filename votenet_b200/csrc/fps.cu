@@ -404,6 +404,13 @@ extern "C" size_t vnb_fps_nested_workspace_bytes(int b, int m) {
   return (size_t)(b > 0 ? b : 1) * (2 * sizeof(int) + (size_t)(m > 0 ? m : 1) * sizeof(float)) + 256;
 }
 
+__global__ void fps_hint_identity_kernel(int b, int m, const int* __restrict__ hint, int* __restrict__ out, int* __restrict__ done) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < b) done[t] = hint[t] >= m ? 1 : 0;
+  if (t >= b * m) return;
+  if (hint[t / m] >= m) out[t] = t % m;
+}
+
 __global__ void fps_fill_kernel(int b, int* __restrict__ v, int value) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < b) v[t] = value;
@@ -422,6 +429,13 @@ static int fps_nested_impl(int b, int n, int m, const float* xyz, int* out_idx, 
   int* fail = static_cast<int*>(workspace);
   int* done = fail + b;
   float* R = reinterpret_cast<float*>(static_cast<char*>(workspace) + (((size_t)b * 2 * sizeof(int) + 255) / 256) * 256);
+  if (hint != nullptr) {
+    // Hinted level: clouds covered by the hint get the identity prefix, the others (a proof failed upstream: exact float
+    // ties, rare) go straight to the sequential sampler — two launches instead of the proof's four.
+    fps_hint_identity_kernel<<<(b * m + 255) / 256, 256, 0, st>>>(b, m, hint, out_idx, done);
+    if (int rc = check_launch("fps identity (hinted)")) return rc;
+    return fps_dispatch(b, n, m, xyz, out_idx, done, st);
+  }
   VNB_CUDA(cudaMemsetAsync(fail, 0, sizeof(int) * (size_t)b, st));
   if ((size_t)m * 12 > 48 * 1024)
     VNB_CUDA(cudaFuncSetAttribute(fps_prefix_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)m * 12)));

@@ -42,7 +42,7 @@ __global__ void peer_wait_kernel(int world, const int* __restrict__ flags, int s
       asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
       if (v - seq >= 0) break;
       __nanosleep(200);
-      if (++spins > (1u << 24)) trap_at(__LINE__);   // a peer died: trap instead of hanging the GPU (~seconds)
+      if (++spins > (1u << 27)) trap_at(__LINE__);   // a peer died: trap instead of hanging the GPU (after ~30 s)
     } while (true);
   }
 }
