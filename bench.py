@@ -131,17 +131,18 @@ def run_reference(args, rank, world):
 
     t0 = time.time(); one(0); t1 = time.time() - t0
     workers = cores
-    # A step of this arm is a bounded sample of the batch: ONE of its 8 clouds through the full forward on one host
-    # thread; `workers` steps run concurrently so every host core is busy (the reference's CPU ops are single-threaded).
-    per_step = 1
+    # A step of this arm is the SAME batch as the GPU arm's: 8 clouds through the full forward, one cloud per host thread
+    # (the reference's CPU ops are single-threaded); the clouds of all steps are fed to a pool of every host core, so the
+    # cores stay busy across step boundaries.
+    per_step = CLOUDS_PER_RANK
     with ThreadPoolExecutor(workers) as ex:
-        list(ex.map(one, range(max(args.warmup, workers))))
+        list(ex.map(one, range(min(args.warmup, 2) * per_step)))
         t0 = time.time()
-        list(ex.map(one, range(args.steps)))
+        list(ex.map(one, range(args.steps * per_step)))
         dt = time.time() - t0
     value = per_step * args.steps / dt
-    sample = (f"1 of {CLOUDS_PER_RANK} clouds per step (full forward incl. NMS, 20000 pts), {workers} steps in flight on "
-              f"{workers} host threads; single-thread latency {t1:.2f} s/cloud")
+    sample = (f"{args.steps} steps x {CLOUDS_PER_RANK} clouds (full forward incl. NMS, 20000 pts), one cloud per thread on a pool of "
+              f"{workers} host threads (every core in sched_getaffinity); single-thread {1.0 / t1:.3f} clouds/s ({t1:.2f} s/cloud)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
