@@ -111,10 +111,18 @@ int vnb_query_ball_point(int b, int n, int m, float radius, int nsample, const f
 
 /* Same outputs, bit for bit, computed through a uniform grid + per-query index bitmap instead of the exhaustive scan
  * (see csrc/ball_query_grid.cu).  workspace: vnb_query_ball_point_workspace_bytes(b,n) bytes; with workspace == NULL
- * (or n < 4096) this is vnb_query_ball_point. */
+ * (or n < 1024, tuning knob bq_grid_min_n) this is vnb_query_ball_point. */
 size_t vnb_query_ball_point_workspace_bytes(int b, int n);
 int vnb_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
                             int* idx, int* pts_cnt, void* workspace, void* stream);
+
+/* vnb_query_ball_point_ws in two halves.  _prepare bins the searched set xyz1 into the workspace (it needs neither the
+ * queries nor nsample, so it can run while the sampler that produces xyz2 is still working; a no-op whenever the _ws call
+ * would take the exhaustive scan); _prepared answers the queries from a workspace prepared with the same b, n, radius
+ * and xyz1.  _ws == _prepare followed by _prepared on the same stream. */
+int vnb_query_ball_point_prepare(int b, int n, float radius, const float* xyz1, void* workspace, void* stream);
+int vnb_query_ball_point_prepared(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
+                                  int* idx, int* pts_cnt, void* workspace, void* stream);
 
 /* groupPointLauncher(b,n,c,m,nsample,points,idx,out)            tf_grouping_g.cu:133-136
  * points (b,n,c), idx (b,m,nsample) -> out (b,m,nsample,c). */

@@ -295,11 +295,12 @@ def test_ball_query_grid_matches_scan(cuda, n, m, r, ns, kind):
     assert np.array_equal(gc.cpu().numpy(), want_c)
     assert np.array_equal(gi.cpu().numpy(), want_i)
     try:
-        check(lib.vnb_set_tuning(b"ball_query_variant", 0))
-        si, sc = query_ball_point(r, ns, T(x, cuda), T(q, cuda))
+        for variant in (0, 1):   # exhaustive scan; grid + dense bitmap (the default, 2, is the sparse-aware bitmap)
+            check(lib.vnb_set_tuning(b"ball_query_variant", variant))
+            si, sc = query_ball_point(r, ns, T(x, cuda), T(q, cuda))
+            assert torch.equal(si, gi) and torch.equal(sc, gc), variant
     finally:
-        check(lib.vnb_set_tuning(b"ball_query_variant", 1))
-    assert torch.equal(si, gi) and torch.equal(sc, gc)
+        check(lib.vnb_set_tuning(b"ball_query_variant", 2))
 
 
 def test_nms_nan_inf_scores_stay_in_range(cuda):

@@ -35,6 +35,8 @@ _SIGS = {
     "vnb_farthest_point_sample_nested_proof": ([_i, _i, _i, _p, _p, _p, _p, _p], _i),
     "vnb_query_ball_point_workspace_bytes": ([_i, _i], _sz),
     "vnb_query_ball_point_ws": ([_i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p], _i),
+    "vnb_query_ball_point_prepare": ([_i, _i, _f, _p, _p, _p], _i),
+    "vnb_query_ball_point_prepared": ([_i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p], _i),
     "vnb_merge_detections": ([_i, _i, _i, _p, _sz, _sz, _sz, _sz, _sz, _sz, _p, _p, _p, _p, _p, _p], _i),
     "vnb_sa_group_mlp_max_backward": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i] + [_p] * 18 + [_p], _i),
     "vnb_votenet_losses": ([_i, _i, _i, _i] + [_p] * 12 + [_f, _f, _p, _p, _p], _i),

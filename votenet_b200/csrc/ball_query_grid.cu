@@ -210,6 +210,112 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) grid_query_kernel(int n, int m,
   if (lane == 0) pts_cnt[(size_t)cloud * m + j] = min(total, nsample);
 }
 
+// Second-generation query (g_bq_variant 2, the default).  The first one cleared and re-read the whole n-bit bitmap for
+// every query (2 x 20 shared accesses per lane at n = 20000) and walked the nine x-runs through dependent loads; ncu showed
+// it issue-bound (77 % issue-active, ~1700 warp instructions per query).  Here
+//   * the nine (start, end) pairs are loaded by lanes 0..8 at once and handed out by shuffles;
+//   * the bitmap is SPARSE-AWARE: lane l owns the `per` words [l * per, (l + 1) * per), per = ceil(words / 32); with
+//     per > GQ_DIRECT it also owns a summary word whose bit i says "word l * per + i is non-zero" (every hit sets it with
+//     a second fire-and-forget atomic — an atomic whose result is awaited costs a shared-memory round trip per step of
+//     the candidate loop).  Counting, emitting and clearing touch only non-zero words, so the bitmap is zeroed once per
+//     warp and left clean by every query.
+// Bit order = index order, so the emitted row is still "the first nsample hits of the index-ordered scan".
+constexpr int GQ_DIRECT = 4;   // up to this many words per lane the lane simply reads its words (no summary)
+template <bool SUMMARY>
+__global__ void __launch_bounds__(GQ_WARPS * 32) grid_query2_kernel(int n, int m, float d2_max, int nsample, int per,
+                                                                     uint32_t inv /* ceil(65536 / per) */,
+                                                                     const float* __restrict__ xyz2,
+                                                                     const char* __restrict__ ws, size_t slice,
+                                                                     int* __restrict__ idx, int* __restrict__ pts_cnt) {
+  extern __shared__ uint32_t s_bm[];  // GQ_WARPS x (32 summary words + 32 * per bitmap words)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cloud = blockIdx.y;
+  uint32_t* summ = s_bm + (size_t)warp * (32 + 32 * per);
+  uint32_t* bm = summ + 32;
+  const char* base = ws + (size_t)cloud * slice;
+  const GridHdr g = *reinterpret_cast<const GridHdr*>(base);
+  const int* cell_start = reinterpret_cast<const int*>(base + 32);
+  const float4* rec = reinterpret_cast<const float4*>(base + 32 + (size_t)CS_INTS * 4 + (size_t)GRID_MAX_CELLS * 4);
+  for (int w = lane * 4; w < 32 + 32 * per; w += 128) *reinterpret_cast<uint4*>(summ + w) = make_uint4(0u, 0u, 0u, 0u);
+  __syncwarp();
+  uint32_t* own = bm + lane * per;
+  for (int j = blockIdx.x * GQ_WARPS + warp; j < m; j += gridDim.x * GQ_WARPS) {
+    const float* q = xyz2 + ((size_t)cloud * m + j) * 3;
+    const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+    // the query itself may lie outside the source points' bounding box: clamp like the builder does; a cell more than
+    // one step away from the unclamped coordinate cannot hold a hit, but visiting it is harmless (exact test below)
+    const int cx = cell_coord(qx, g.ox, g.inv, g.nx), cy = cell_coord(qy, g.oy, g.inv, g.ny), cz = cell_coord(qz, g.oz, g.inv, g.nz);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+    int rs = 0, re = 0;  // lane r < 9: candidate records [rs, re) of x-run r (cells x0..x1 of one (y, z) are contiguous)
+    {
+      const int z = cz - 1 + lane / 3, y = cy - 1 + lane % 3;
+      if (lane < 9 && z >= 0 && z < g.nz && y >= 0 && y < g.ny) {
+        const int rowc = (z * g.ny + y) * g.nx;
+        rs = __ldg(cell_start + rowc + x0);
+        re = __ldg(cell_start + rowc + x1 + 1);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int s = __shfl_sync(0xffffffffu, rs, r), e = __shfl_sync(0xffffffffu, re, r);
+      for (int t = s + lane; t < e; t += 32) {
+        const float4 c = __ldg(rec + t);
+        if (d2_ref_gpu(qx - c.x, qy - c.y, qz - c.z) <= d2_max) {
+          const uint32_t k = (uint32_t)__float_as_int(c.w), w = k >> 5;
+          atomicOr(&bm[w], 1u << (k & 31u));
+          if (SUMMARY) {
+            const uint32_t l = (w * inv) >> 16;   // == w / per for w < 1024 (per <= 32)
+            atomicOr(&summ[l], 1u << (w - l * (uint32_t)per));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---- count, then emit the set bits in ascending order; only non-zero words are visited, and they are cleared on the way
+    uint32_t flags = 0u;
+    if (SUMMARY) {
+      flags = summ[lane];
+    } else {
+#pragma unroll
+      for (int i = 0; i < GQ_DIRECT; ++i)
+        if (i < per && own[i] != 0u) flags |= 1u << i;
+    }
+    int mine = 0;
+    for (uint32_t f = flags; f; f &= f - 1u) mine += __popc(own[__ffs(f) - 1]);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int pos = incl - mine;
+    int* row = idx + ((size_t)cloud * m + j) * nsample;
+    int first_local = -1;
+    for (uint32_t f = flags; f; f &= f - 1u) {
+      const int wi = __ffs(f) - 1;
+      uint32_t bits = own[wi];
+      own[wi] = 0u;
+      const int kbase = (lane * per + wi) << 5;
+      if (first_local < 0) first_local = kbase + __ffs(bits) - 1;
+      while (bits && pos < nsample) {
+        row[pos++] = kbase + __ffs(bits) - 1;
+        bits &= bits - 1u;
+      }
+    }
+    if (SUMMARY) summ[lane] = 0u;
+    // first hit overall = first hit of the lowest lane that has any (lanes own ascending index ranges)
+    const unsigned havem = __ballot_sync(0xffffffffu, mine > 0);
+    if (total > 0) {
+      const int first = __shfl_sync(0xffffffffu, first_local, __ffs(havem) - 1);
+      const int cnt = min(total, nsample);
+      for (int l = cnt + lane; l < nsample; l += 32) row[l] = first;   // pad with the first hit (tf_grouping_g.cu:26-29)
+    }
+    if (lane == 0) pts_cnt[(size_t)cloud * m + j] = min(total, nsample);
+    __syncwarp();  // the cleared words / summary are visible before the next query's atomics
+  }
+}
+
 float ball_d2_max(float radius);  // point_ops.cu
 
 }  // namespace vnb
@@ -221,9 +327,24 @@ extern "C" size_t vnb_query_ball_point_workspace_bytes(int b, int n) {
   return (size_t)b * grid_slice_bytes(n);
 }
 
-extern "C" int vnb_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float* xyz1,
-                                       const float* xyz2, int* idx, int* pts_cnt, void* workspace, void* stream) {
-  if (workspace == nullptr || g_bq_variant == 0 || n < g_bq_grid_min_n || radius <= 1e-20f)
+static bool bq_grid_path(int n, float radius, const void* workspace) {
+  return workspace != nullptr && g_bq_variant != 0 && n >= g_bq_grid_min_n && radius > 1e-20f;
+}
+
+// Build half of vnb_query_ball_point_ws: needs the searched set only, so a caller can run it before the queries exist
+// (the engine runs it beside the FPS that produces them).  A no-op when the _ws call would take the scan path.
+extern "C" int vnb_query_ball_point_prepare(int b, int n, float radius, const float* xyz1, void* workspace, void* stream) {
+  VNB_REQUIRE(radius > 0, "QueryBallPoint expects positive radius");          // tf_grouping.cpp:71
+  VNB_REQUIRE(b >= 0 && n >= 0, "QueryBallPoint expects (batch_size, ndataset, 3) xyz1 shape.");
+  if (!bq_grid_path(n, radius, workspace) || b == 0) return VNB_OK;
+  grid_build_kernel<<<b, BT, 0, as_stream(stream)>>>(n, radius * 1.01f, xyz1, static_cast<char*>(workspace), grid_slice_bytes(n));
+  return check_launch("query_ball_point grid build");
+}
+
+// Query half: `workspace` was filled by vnb_query_ball_point_prepare(b, n, radius, xyz1, ...) with the same b, n, radius, xyz1.
+extern "C" int vnb_query_ball_point_prepared(int b, int n, int m, float radius, int nsample, const float* xyz1,
+                                             const float* xyz2, int* idx, int* pts_cnt, void* workspace, void* stream) {
+  if (!bq_grid_path(n, radius, workspace))
     return vnb_query_ball_point(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, stream);
   VNB_REQUIRE(radius > 0, "QueryBallPoint expects positive radius");          // tf_grouping.cpp:71
   VNB_REQUIRE(nsample > 0, "QueryBallPoint expects positive nsample");        // tf_grouping.cpp:74
@@ -231,9 +352,20 @@ extern "C" int vnb_query_ball_point_ws(int b, int n, int m, float radius, int ns
   if (b == 0 || m == 0) return VNB_OK;
   cudaStream_t st = as_stream(stream);
   const size_t slice = grid_slice_bytes(n);
-  grid_build_kernel<<<b, BT, 0, st>>>(n, radius * 1.01f, xyz1, static_cast<char*>(workspace), slice);
-  if (int rc = check_launch("query_ball_point grid build")) return rc;
-  const size_t smem = (size_t)GQ_WARPS * ((n + 31) / 32) * 4;
+  const int nw = (n + 31) / 32;
+  if (g_bq_variant >= 2) {
+    const int per = (nw + 31) / 32;   // bitmap words per lane
+    const size_t smem = (size_t)GQ_WARPS * (32 + 32 * per) * 4;
+    VNB_REQUIRE(per <= 32 && smem <= 200 * 1024, "query_ball_point: n too large for the bitmap path");
+    const uint32_t inv = (uint32_t)((65536 + per - 1) / per);
+    auto kern = per > GQ_DIRECT ? grid_query2_kernel<true> : grid_query2_kernel<false>;
+    if (smem > 48 * 1024) VNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((m + GQ_WARPS - 1) / GQ_WARPS, b);   // one query per warp; the kernel's loop accepts any smaller grid
+    kern<<<grid, GQ_WARPS * 32, smem, st>>>(n, m, ball_d2_max(radius), nsample, per, inv, xyz2,
+                                            static_cast<const char*>(workspace), slice, idx, pts_cnt);
+    return check_launch("query_ball_point grid query");
+  }
+  const size_t smem = (size_t)GQ_WARPS * nw * 4;
   VNB_REQUIRE(smem <= 200 * 1024, "query_ball_point: n too large for the bitmap path");
   if (smem > 48 * 1024)  // (never lower the limit below the default: a profiler that patches the kernel needs the headroom)
     VNB_CUDA(cudaFuncSetAttribute(grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -241,4 +373,15 @@ extern "C" int vnb_query_ball_point_ws(int b, int n, int m, float radius, int ns
   grid_query_kernel<<<grid, GQ_WARPS * 32, smem, st>>>(n, m, ball_d2_max(radius), nsample, xyz2,
                                                        static_cast<const char*>(workspace), slice, idx, pts_cnt);
   return check_launch("query_ball_point grid query");
+}
+
+extern "C" int vnb_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float* xyz1,
+                                       const float* xyz2, int* idx, int* pts_cnt, void* workspace, void* stream) {
+  if (!bq_grid_path(n, radius, workspace))
+    return vnb_query_ball_point(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, stream);
+  VNB_REQUIRE(nsample > 0, "QueryBallPoint expects positive nsample");        // tf_grouping.cpp:74
+  VNB_REQUIRE(b >= 0 && n >= 0 && m >= 0, "QueryBallPoint expects (batch_size, ndataset, 3) xyz1 shape.");
+  if (b == 0 || m == 0) return VNB_OK;
+  if (int rc = vnb_query_ball_point_prepare(b, n, radius, xyz1, workspace, stream)) return rc;
+  return vnb_query_ball_point_prepared(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, workspace, stream);
 }

@@ -64,6 +64,7 @@ struct Params {
   float* fp_out;                         // (rows, 256) output of the fp module (= seed features), fp32
   float* votes_xyz;                      // (rows, 3)                       (vote only)
   float* votes_feat;                     // (rows, 256)                     (vote only)
+  long long* trace;                      // debugging (vnb_debug_sa_trace): CTA 0 stamps clock64() per stage, see FP_STAMP
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -96,6 +97,11 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = (int)blockIdx.x * 128;
   const int L = P.n_layers;
+  // stage trace of CTA 0: slot 0 kernel start; 1 prologue done; 8 + 2c / 9 + 2c loader chunk c loads issued / stored;
+  // 32 + 4l .. : layer l first MMA issued, last MMA issued, accumulator seen by the epilogue, epilogue done
+  const bool tr = P.trace != nullptr && blockIdx.x == 0 && lane == 0;
+#define FP_STAMP(slot) if (tr) P.trace[slot] = clock64();
+  if (warp == 0) { FP_STAMP(0) }
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -114,6 +120,7 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
   __syncthreads();  // barriers initialised before anyone touches them
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_ptr;
+  if (warp == 0) { FP_STAMP(1) }
 
   if (warp == 8) {
     // ================================================================ weight ring: all sub-chunks of all layers, in order
@@ -161,6 +168,7 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
           const int rws = min(128, npad - 128 * j);
           const uint32_t idesc = make_idesc_f16_f32(128, (uint32_t)rws);
           const uint32_t b0 = smem_u32(sW) + (uint32_t)s * PANEL;
+          if (c == 0 && j == 0) { FP_STAMP(32 + 4 * l) }
           if (elect_one()) {
             for (int ks = 0; ks < kc / 16; ++ks)
               mma_f16_ss(tmem + (uint32_t)(128 * j), make_desc_sw128(a0 + (uint32_t)ks * 32),
@@ -170,6 +178,7 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
             if (c == nch - 1 && j == npc - 1) mma_commit(acc_full);
           }
           __syncwarp();
+          if (c == nch - 1 && j == npc - 1) { FP_STAMP(33 + 4 * l) }
         }
       }
     }
@@ -240,6 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
                                        pack_h2(v[p][1].x, v[p][1].y), pack_h2(v[p][1].z, v[p][1].w))
                           : make_uint4(0, 0, 0, 0);
         }
+        if (warp == 0) { FP_STAMP(8 + 2 * c) }
         if (c >= 2) mbar_wait(&a_empty[s], (uint32_t)(((c >> 1) - 1) & 1));  // the MMAs of chunk c-2 have read the slot
         uint8_t* dst = sY + s * PANEL;
 #pragma unroll
@@ -247,6 +257,7 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
           *reinterpret_cast<uint4*>(dst + sw128_offset((uint32_t)(rsub + 32 * p), (uint32_t)(8 * c8))) = pk[p];
         fence_proxy_async_smem();
         mbar_arrive(&a_full[s]);
+        if (warp == 0) { FP_STAMP(9 + 2 * c) }
       }
     }
     // ---- epilogues: thread = (row = TMEM lane 32 q + lane, column half hf)
@@ -263,6 +274,7 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
     for (int l = 0; l < L; ++l) {
       mbar_wait(acc_full, (uint32_t)(l & 1));
       tc_fence_after_sync();
+      if (warp == 0) { FP_STAMP(34 + 4 * l) }
       const bool last = l == L - 1;
       const bool vote_out = last && L > 2;          // [features | xyz] + residual -> votes
       const bool fp_store = l == 1;                 // output of the fp module, fp32 (seed features)
@@ -345,8 +357,10 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
         tc_fence_before_sync();     // ... and overwrite the accumulator these loads have drained
         mbar_arrive(act_full);
       }
+      if (warp == 0) { FP_STAMP(35 + 4 * l) }
     }
   }
+#undef FP_STAMP
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TM_COLS);
@@ -354,7 +368,11 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
 
 }  // namespace fpc
 
-int fp_chain_launch(const fpc::Params& p, cudaStream_t st) {
+extern long long* g_sa_trace;  // sa1_ws2.cu (vnb_debug_sa_trace)
+
+int fp_chain_launch(const fpc::Params& p0, cudaStream_t st) {
+  fpc::Params p = p0;
+  p.trace = g_sa_trace;
   VNB_CUDA(cudaFuncSetAttribute(fpc::fp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fpc::SMEM));
   const int grid = (p.rows_total + 127) / 128;
   fpc::fp_chain_kernel<<<grid, fpc::THREADS, fpc::SMEM, st>>>(p);

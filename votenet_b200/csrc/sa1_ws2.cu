@@ -6,8 +6,8 @@
 //
 //   warps 0-3 / 4-7      EPILOGUE1 (even / odd tiles)  D1[s] -> ReLU, fp16 -> H1[t%4]        (thread = tile row = TMEM lane)
 //   warps 8-11 / 12-15   EPILOGUE2 (even / odd tiles)  D2[s] -> ReLU, fp16 -> H2[t%4]        (biases b1, b2 ride on the MMAs)
-//   warps 16-19 / 20-23  EPILOGUE3 (even / odd tiles)  D3[s] (channel per lane) -> max over each centroid's 64 samples,
-//                        +b3, ReLU -> out
+//   warps 16-19 / 20-23  EPILOGUE3 (column half 0 / 1 of EVERY tile)  D3[s] (channel per lane) -> max over each centroid's
+//                        samples, +b3, ReLU -> out
 //   warps 24-27          PRODUCER   one grouped row per thread: {rel_xyz, source row} from the helper kernel's table, c
 //                        feature floats; table rows prefetched two tiles ahead and features one tile ahead so no global
 //                        latency is exposed; fp16, swizzled 32-byte row of A0[s]
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
   uint64_t* m1_done = bars + 3;    // [2]  commit
   uint64_t* d1_empty = bars + 5;   // [2]  128 E1 arrivals
   uint64_t* d2_empty = bars + 7;   // [2]  128 E2 arrivals
-  uint64_t* d3_empty = bars + 9;   // [2]  128 E3 arrivals
+  uint64_t* d3_empty = bars + 9;   // [2]  256 E3 arrivals (both column halves)
   uint64_t* h1_full = bars + 11;   // [NH] 128 E1 arrivals                              (slot t&3, parity (t>>2)&1)
   uint64_t* m2_done = bars + 15;   // [NH] commit: D2[t&1] ready, H1[t&3] free again
   uint64_t* h2_full = bars + 19;   // [NH] 128 E2 arrivals
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
     mbar_init(bar_w, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a0_full[s], 128); mbar_init(&m1_done[s], 1); mbar_init(&d1_empty[s], 128); mbar_init(&d2_empty[s], 128);
-      mbar_init(&d3_empty[s], 128);
+      mbar_init(&d3_empty[s], 256);
     }
     for (int k = 0; k < NH; ++k) {
       mbar_init(&h1_full[k], 128); mbar_init(&m2_done[k], 1); mbar_init(&h2_full[k], 128); mbar_init(&m3_done[k], 1);
@@ -190,42 +190,52 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
       // value it needs is a chain of DEPENDENT global loads away (tile table -> table row -> feature row): centroid ids
       // are requested FIVE tiles ahead, table rows FOUR and feature rows TWO, so each load has at least a tile period
       // (usually two) to land; ~30 registers of look-ahead state.
-      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, r3 = r0;   // table rows of tiles t .. t+3
-      float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4];  // features of tiles t, t+1 (, t+2)
-      int c4 = -1;                                                              // centroid of this row in tile t+4
-      if (my_tiles > 0) r0 = __ldg(rel + src_row(first_tile, cid_of(first_tile)));
-      if (my_tiles > 1) r1 = __ldg(rel + src_row(first_tile + 1, cid_of(first_tile + 1)));
-      if (my_tiles > 2) r2 = __ldg(rel + src_row(first_tile + 2, cid_of(first_tile + 2)));
-      if (my_tiles > 3) r3 = __ldg(rel + src_row(first_tile + 3, cid_of(first_tile + 3)));
-      if (my_tiles > 4) c4 = cid_of(first_tile + 4);
+      // The look-ahead state lives in RINGS indexed by t & 3 with the loop unrolled four times, so every slot is a fixed
+      // register and a prefetched value is first touched by the instruction that needs it.  (Rotating named registers —
+      // r0 = r1; r1 = r2; ... — made each value wait for its load one iteration after it was issued: the kernel's tile
+      // period was pinned to one L2 round trip, 1235 cycles, with every other stage idle half of the time.)  A slot is
+      // refilled after its last use, i.e. behind the tile's arrive.
+      float4 R[4];        // table rows of tiles t .. t+3            (slot = tile & 3)
+      float F[4][4];      // features of tiles t, t+1 (, t+2)          (slot = tile & 3)
+      int C[2];           // centroid of this row in tiles t+4, t+5    (slot = tile & 1)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        R[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < my_tiles) R[k] = __ldg(rel + src_row(first_tile + k, cid_of(first_tile + k)));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) F[k][i] = 0.f;
+      }
+      C[0] = 4 < my_tiles ? cid_of(first_tile + 4) : -1;
+      C[1] = 5 < my_tiles ? cid_of(first_tile + 5) : -1;
       auto load_feat = [&](const float4& r, float (&f)[4]) {
         const float* fp = feat + (size_t)__float_as_int(r.w) * c;
 #pragma unroll
         for (int i = 0; i < 4; ++i) f[i] = i < c ? __ldg(fp + i) : 0.f;
       };
-      if (my_tiles > 0) load_feat(r0, f0);
-      if (my_tiles > 1) load_feat(r1, f1);
-      for (int t = 0; t < my_tiles; ++t) {
-        const int s = t & 1;
-        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t + 4 < my_tiles) r4 = __ldg(rel + src_row(first_tile + t + 4, c4));
-        if (t + 5 < my_tiles) c4 = cid_of(first_tile + t + 5);
+      if (my_tiles > 0) load_feat(R[0], F[0]);
+      if (my_tiles > 1) load_feat(R[1], F[1]);
+      for (int t0 = 0; t0 < my_tiles; t0 += 4) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) f2[i] = 0.f;
-        if (t + 2 < my_tiles) load_feat(r2, f2);
-        if (t >= 2) mbar_wait(&m1_done[s], par_of(t - 2));  // M1(t-2) finished reading A0[s]
-        if (warp == 24) { S1_STAMP(0, t, 0) }
-        uint8_t* a0 = sA0 + s * A0_BYTES;
-        *reinterpret_cast<uint4*>(a0 + sw128_offset((uint32_t)pt, 0)) =
-            make_uint4(pack2(r0.x, r0.y), pack2(r0.z, f0[0]), pack2(f0[1], f0[2]), pack2(f0[3], 0.f));
-        *reinterpret_cast<uint4*>(a0 + sw128_offset((uint32_t)pt, 8)) =
-            make_uint4(0u, 0u, 0u, pack2(1.f, 1.f));  // k = 14, 15: the constant 1 that multiplies b1 (hi, lo)
-        fence_proxy_async_smem();
-        mbar_arrive(&a0_full[s]);
-        if (warp == 24) { S1_STAMP(0, t, 1) }
-        r0 = r1; r1 = r2; r2 = r3; r3 = r4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { f0[i] = f1[i]; f1[i] = f2[i]; }
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + u;
+          if (t >= my_tiles) break;
+          const int s = u & 1;   // == t & 1
+          if (t >= 2) mbar_wait(&m1_done[s], par_of(t - 2));  // M1(t-2) finished reading A0[s]
+          if (warp == 24) { S1_STAMP(0, t, 0) }
+          uint8_t* a0 = sA0 + s * A0_BYTES;
+          *reinterpret_cast<uint4*>(a0 + sw128_offset((uint32_t)pt, 0)) =
+              make_uint4(pack2(R[u].x, R[u].y), pack2(R[u].z, F[u][0]), pack2(F[u][1], F[u][2]), pack2(F[u][3], 0.f));
+          *reinterpret_cast<uint4*>(a0 + sw128_offset((uint32_t)pt, 8)) =
+              make_uint4(0u, 0u, 0u, pack2(1.f, 1.f));  // k = 14, 15: the constant 1 that multiplies b1 (hi, lo)
+          fence_proxy_async_smem();
+          mbar_arrive(&a0_full[s]);
+          if (warp == 24) { S1_STAMP(0, t, 1) }
+          // look-ahead: features of tile t+2 (its table row was requested four tiles ago), table row of tile t+4 (its
+          // centroid id two tiles ago), centroid id of tile t+6
+          if (t + 2 < my_tiles) load_feat(R[(u + 2) & 3], F[(u + 2) & 3]);
+          if (t + 4 < my_tiles) R[u] = __ldg(rel + src_row(first_tile + t + 4, C[u & 1]));
+          if (t + 6 < my_tiles) C[u & 1] = cid_of(first_tile + t + 6);
+        }
       }
     } else {
     float4 r_cur = make_float4(0.f, 0.f, 0.f, 0.f), r_nxt = r_cur;   // table rows of tiles t, t+1
@@ -379,35 +389,36 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
     }
   } else if (warp < 24) {
     // ================================================================ EPILOGUE 3: D3 -> max-pool -> out
-    // warp (16 + 4*s + q): tiles of parity s, TMEM lane quadrant q (channels 32q..32q+31), both centroids of the tile
-    const int q = warp & 3, s = (warp >> 2) & 1;
-    const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + TM_D3 + s * C3;
+    // warp (16 + 4*g + q): EVERY tile, TMEM lane quadrant q (channels 32q..32q+31), column half g (samples 64g..64g+63).
+    // (Two groups that alternated whole tiles held a D3 buffer for eight dependent TMEM round trips; halving the columns
+    // per warp halves that hold time — with two D3 buffers it bounds the tile period — at the same work per warp.)
+    const int q = warp & 3, g = (warp >> 2) & 1;
     const int ch = q * 32 + lane;
     const float bias3 = sB3[ch];
-    for (int t = s; t < my_tiles; t += 2) {
+    for (int t = 0; t < my_tiles; ++t) {
+      const int s = t & 1;
       const int tile = first_tile + t;
       const int shift = shift_of(tile);
-      // the tile's eight slot entries, requested BEFORE the wait for the accumulator so the (L2) latency hides behind it
-      const int4 ca = __ldg(reinterpret_cast<const int4*>(tile_cid + (size_t)tile * 8));
-      const int4 cb = __ldg(reinterpret_cast<const int4*>(tile_cid + (size_t)tile * 8) + 1);
+      const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + TM_D3 + s * C3 + g * 64;
+      // this half's four slot entries, requested BEFORE the wait for the accumulator so the (L2) latency hides behind it
+      // (64-row slots: entry g; 32-row: entries 2g, 2g+1; 16-row: entries 4g..4g+3)
+      const int4 cc = __ldg(reinterpret_cast<const int4*>(tile_cid + (size_t)tile * 8) + (shift == 4 ? g : 0));
       mbar_wait(&m3_done[t & 3], par4(t));
       tc_fence_after_sync();
-      if (q == 0) { S1_STAMP(6 + s, t, 0) }
-      // eight 16-column blocks; the load of block k+1 is in flight while block k is reduced (two 16-register buffers —
-      // left to itself ptxas stopped hoisting the next load once the per-slot reduction was added, and eight exposed
-      // TMEM round trips made this stage pace the whole kernel)
-      float mbv[8];
+      if (q == 0) { S1_STAMP(6 + g, t, 0) }
+      // four 16-column blocks; the load of block k+1 is in flight while block k is reduced
+      float mb[4];
       {
         uint32_t v[2][16];
         tmem_ld_x16(tacc, v[0]);
 #pragma unroll
-        for (int blk = 0; blk < 8; ++blk) {
+        for (int blk = 0; blk < 4; ++blk) {
           tmem_ld_wait();
-          if (blk + 1 < 8) {
+          if (blk + 1 < 4) {
             tmem_ld_x16(tacc + (blk + 1) * 16, v[(blk + 1) & 1]);
           } else {
             tc_fence_before_sync();
-            mbar_arrive(&d3_empty[s]);  // D3[s] has been read
+            mbar_arrive(&d3_empty[s]);  // this warp's part of D3[s] has been read
           }
           const uint32_t* w = v[blk & 1];
           float a0 = fmaxf(__uint_as_float(w[0]), __uint_as_float(w[4])), a1 = fmaxf(__uint_as_float(w[1]), __uint_as_float(w[5]));
@@ -416,34 +427,24 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
           a1 = fmaxf(fmaxf(a1, __uint_as_float(w[9])), __uint_as_float(w[13]));
           a2 = fmaxf(fmaxf(a2, __uint_as_float(w[10])), __uint_as_float(w[14]));
           a3 = fmaxf(fmaxf(a3, __uint_as_float(w[11])), __uint_as_float(w[15]));
-          mbv[blk] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+          mb[blk] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
         }
       }
+      // bias + ReLU commute with the max
+      if (shift == 6) {
+        const int cid = g == 0 ? cc.x : cc.y;
+        if (cid >= 0) out[(size_t)cid * C3 + ch] = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])) + bias3, 0.f);
+      } else if (shift == 5) {
+        const int c0 = g == 0 ? cc.x : cc.z, c1 = g == 0 ? cc.y : cc.w;
+        if (c0 >= 0) out[(size_t)c0 * C3 + ch] = fmaxf(fmaxf(mb[0], mb[1]) + bias3, 0.f);
+        if (c1 >= 0) out[(size_t)c1 * C3 + ch] = fmaxf(fmaxf(mb[2], mb[3]) + bias3, 0.f);
+      } else {
+        const int cid[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        // centroids whose samples sit in this half of the tile: one (64-row slots), two (32) or four (16)
-        int cid[4];
-        if (shift == 6) {
-          cid[0] = g == 0 ? ca.x : ca.y; cid[1] = cid[2] = cid[3] = -1;
-        } else if (shift == 5) {
-          cid[0] = g == 0 ? ca.x : ca.z; cid[1] = g == 0 ? ca.y : ca.w; cid[2] = cid[3] = -1;
-        } else {
-          cid[0] = g == 0 ? ca.x : cb.x; cid[1] = g == 0 ? ca.y : cb.y; cid[2] = g == 0 ? ca.z : cb.z; cid[3] = g == 0 ? ca.w : cb.w;
-        }
-        const float* mb = &mbv[4 * g];
-        // bias + ReLU commute with the max
-        if (shift == 6) {
-          if (cid[0] >= 0) out[(size_t)cid[0] * C3 + ch] = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])) + bias3, 0.f);
-        } else if (shift == 5) {
-          if (cid[0] >= 0) out[(size_t)cid[0] * C3 + ch] = fmaxf(fmaxf(mb[0], mb[1]) + bias3, 0.f);
-          if (cid[1] >= 0) out[(size_t)cid[1] * C3 + ch] = fmaxf(fmaxf(mb[2], mb[3]) + bias3, 0.f);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (cid[k] >= 0) out[(size_t)cid[k] * C3 + ch] = fmaxf(mb[k] + bias3, 0.f);
-        }
+        for (int k = 0; k < 4; ++k)
+          if (cid[k] >= 0) out[(size_t)cid[k] * C3 + ch] = fmaxf(mb[k] + bias3, 0.f);
       }
-      if (q == 0) { S1_STAMP(6 + s, t, 1) }
+      if (q == 0) { S1_STAMP(6 + g, t, 1) }
     }
   }
 #undef S1_STAMP

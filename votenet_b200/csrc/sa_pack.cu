@@ -73,28 +73,51 @@ __global__ void __launch_bounds__(PK_T) sa_pack_tiles_kernel(int total, const in
 
 // relative coordinates (utils.py:51) and flat source-row index of every grouped row: rel[(g*64+s)] = {xyz[idx]-c, row}
 // pts_cnt (optional): rows beyond the centroid's slot (16 / 32 / 64 rows, sa_pack.cu) are never read and are skipped.
-__global__ void group_rel_kernel(int n, int m, long long total_rows, const float* __restrict__ xyz,
-                                 const float* __restrict__ new_xyz, const int* __restrict__ idx,
-                                 const int* __restrict__ pts_cnt, float4* __restrict__ rel) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total_rows) return;
-  const int g = (int)(t >> 6);
-  if (pts_cnt != nullptr) {
-    const int c = pts_cnt[g];
-    const int slot = (c <= 0 || c > 32) ? 64 : (c > 16 ? 32 : 16);
-    if ((int)(t & 63) >= slot) return;
+// Latency-bound (three dependent loads per row: count -> index -> point), so every thread carries GR_U independent rows,
+// 256 * k apart: each step of the chain is issued for all of them before the first result is needed.
+constexpr int GR_U = 4;
+__global__ void __launch_bounds__(256) group_rel_kernel(int n, int m, long long total_rows, const float* __restrict__ xyz,
+                                                        const float* __restrict__ new_xyz, const int* __restrict__ idx,
+                                                        const int* __restrict__ pts_cnt, float4* __restrict__ rel) {
+  const long long t0 = (long long)blockIdx.x * (256 * GR_U) + threadIdx.x;
+  bool live[GR_U];
+  int pid[GR_U];
+#pragma unroll
+  for (int u = 0; u < GR_U; ++u) {
+    const long long t = t0 + 256 * u;
+    live[u] = t < total_rows;
+    if (live[u] && pts_cnt != nullptr) {
+      const int c = __ldg(pts_cnt + (t >> 6));
+      const int slot = (c <= 0 || c > 32) ? 64 : (c > 16 ? 32 : 16);
+      live[u] = (int)(t & 63) < slot;
+    }
   }
-  const int bi = g / m;
-  const int pid = idx[t];
-  const float* pp = xyz + ((size_t)bi * n + pid) * 3;
-  const float* cc = new_xyz + (size_t)g * 3;
-  rel[t] = make_float4(pp[0] - cc[0], pp[1] - cc[1], pp[2] - cc[2], __int_as_float(bi * n + pid));
+#pragma unroll
+  for (int u = 0; u < GR_U; ++u) pid[u] = live[u] ? __ldg(idx + t0 + 256 * u) : 0;
+  float px[GR_U], py[GR_U], pz[GR_U], cx[GR_U], cy[GR_U], cz[GR_U];
+#pragma unroll
+  for (int u = 0; u < GR_U; ++u) {
+    px[u] = py[u] = pz[u] = cx[u] = cy[u] = cz[u] = 0.f;
+    if (!live[u]) continue;
+    const int g = (int)((t0 + 256 * u) >> 6);
+    const float* pp = xyz + ((size_t)(g / m) * n + pid[u]) * 3;
+    const float* cc = new_xyz + (size_t)g * 3;
+    px[u] = __ldg(pp); py[u] = __ldg(pp + 1); pz[u] = __ldg(pp + 2);
+    cx[u] = __ldg(cc); cy[u] = __ldg(cc + 1); cz[u] = __ldg(cc + 2);
+  }
+#pragma unroll
+  for (int u = 0; u < GR_U; ++u) {
+    if (!live[u]) continue;
+    const long long t = t0 + 256 * u;
+    const int bi = (int)(t >> 6) / m;
+    rel[t] = make_float4(px[u] - cx[u], py[u] - cy[u], pz[u] - cz[u], __int_as_float(bi * n + pid[u]));
+  }
 }
 
 void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx,
                       const int* pts_cnt, void* rel, cudaStream_t st) {
-  group_rel_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(n, m, rows, xyz, new_xyz, idx, pts_cnt,
-                                                                   static_cast<float4*>(rel));
+  group_rel_kernel<<<(unsigned)((rows + 256 * GR_U - 1) / (256 * GR_U)), 256, 0, st>>>(n, m, rows, xyz, new_xyz, idx, pts_cnt,
+                                                                                     static_cast<float4*>(rel));
 }
 
 // workspace layout of the fused SA path: [rel: rows * 16 B][hdr: 256 B][tile_cid: (total/2 + 4) * 32 B]

@@ -79,8 +79,13 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
                                                             const char* __restrict__ w2_img,
                                                             const char* __restrict__ w3_img,
                                                             const __half* __restrict__ q, float* __restrict__ out,
-                                                            int min_tpc) {
+                                                            int min_tpc, long long* __restrict__ trace) {
   using K = Cfg<C1, C2, C3>;
+  // debugging aid (vnb_debug_sa_trace): CTA 0 stamps clock64() at the start (after its input wait) and the end of every
+  // stage of its first 64 tiles: trace[(role * 64 + t) * 2 + {0,1}], roles 0 P, 1 M2, 2 E2, 3 M3, 4 E3
+  const bool tr = trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
+#define S2_STAMP(role, t, ph) \
+  if (tr && (t) < 64) trace[((role) * 64 + (t)) * 2 + (ph)] = clock64();
   constexpr int NCH = K::NCHUNK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align_1024(smem_raw);
@@ -172,6 +177,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
       for (int i = 0; i < 8; ++i)  // all gathers first: 8 independent 16-byte loads in flight per thread
         raw[i] = __ldg(reinterpret_cast<const uint4*>(q + (size_t)__float_as_int(srel[rsub + 16 * i].w) * C1) + chunk);
       if (t >= 2) mbar_wait(&m2_done[s], (uint32_t)(((t >> 1) - 1) & 1));  // M2(t-2) finished reading H1[s]
+      if (warp == 12) { S2_STAMP(0, t, 0) }
       uint8_t* h1 = sH1 + s * K::H1_BYTES;
       float4 rl_next = srel[rsub];
 #pragma unroll
@@ -195,6 +201,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
       }
       fence_proxy_async_smem();
       mbar_arrive(&h1_full[s]);
+      if (warp == 12) { S2_STAMP(0, t, 1) }
       if (pt < 128 && t + 1 < my_tiles) {
         // relreg holds row pt of the NEXT tile by now: pull its q row (C1 halves = 2 lines) into L1, so the next
         // iteration's gathers are L1 hits instead of L2 round trips (no registers are held across the tile for it)
@@ -213,6 +220,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
         mbar_wait(&h1_full[s], (uint32_t)((t >> 1) & 1));
         if (t >= 2) mbar_wait(&d2_empty[s], (uint32_t)(((t >> 1) - 1) & 1));  // E2(t-2) drained D2[s]
         tc_fence_after_sync();
+        S2_STAMP(1, t, 0)
         const uint32_t a0 = smem_u32(sH1 + s * K::H1_BYTES), b0 = smem_u32(sW2);
 #pragma unroll
         for (int ks = 0; ks < C1 / 16; ++ks) {
@@ -221,6 +229,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
                      make_desc_sw128(b0 + pan * (C2 * 128) + kin * 32), idesc2, ks > 0 ? 1u : 0u);
         }
         mma_commit(&m2_done[s]);
+        S2_STAMP(1, t, 1)
       }
     }
   } else if (warp == 21) {
@@ -236,6 +245,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
         for (int c = 0; c < NCH; ++c) {
           mbar_wait(&h2c_full[c], par);
           tc_fence_after_sync();
+          if (c == 0) { S2_STAMP(3, t, 0) }
 #pragma unroll
           for (int k2 = 0; k2 < 2; ++k2) {
             const uint32_t ks = (uint32_t)(2 * c + k2), pan = ks >> 2, kin = ks & 3;
@@ -245,6 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
                          make_desc_sw128(b0 + pan * (128 * 128) + kin * 32), idesc3, ks > 0 ? 1u : 0u);
           }
           mma_commit(&m3c_done[c]);
+          if (c == NCH - 1) { S2_STAMP(3, t, 1) }
         }
       }
     }
@@ -255,6 +266,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
       const int s = t & 1;
       mbar_wait(&m2_done[s], (uint32_t)((t >> 1) & 1));
       tc_fence_after_sync();
+      if (warp == 0) { S2_STAMP(2, t, 0) }
       uint32_t v[2][32];
       tmem_ld_x32(tmem + lane_base + K::TM_D2 + s * C2, v[0]);
 #pragma unroll
@@ -290,6 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
         fence_proxy_async_smem();
         mbar_arrive(&h2c_full[c]);
       }
+      if (warp == 0) { S2_STAMP(2, t, 1) }
     }
   } else if (warp < 12) {
     // ================================================================ EPILOGUE 3: D3 -> max-pool -> out
@@ -311,6 +324,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
       }
       mbar_wait(&m3c_done[NCH - 1], (uint32_t)(t & 1));  // the last chunk's commit == D3(t) complete
       tc_fence_after_sync();
+      if (warp == 4) { S2_STAMP(4, t, 0) }
 #pragma unroll
       for (int hh = 0; hh < C3 / 128; ++hh) {
         uint32_t v[2][32];
@@ -347,8 +361,10 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
           if (emit && cid[k] >= 0) out[(size_t)cid[k] * C3 + ch] = fmaxf(mb[k] + bias3[hh], 0.f);
         }
       }
+      if (warp == 4) { S2_STAMP(4, t, 1) }
     }
   }
+#undef S2_STAMP
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, K::TM_COLS);
@@ -357,6 +373,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
 }  // namespace s2v2
 
 extern int g_sa_sms, g_sa_split, g_sa_min_tpc;  // mlp_tc.cu
+extern long long* g_sa_trace;                   // sa1_ws2.cu (vnb_debug_sa_trace)
 size_t sa_rel_bytes(long long rows);                                                                  // sa_pack.cu
 int launch_sa_pack(int total_centroids, const int* pts_cnt, int* hdr, int* tile_cid, cudaStream_t st);  // sa_pack.cu
 void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx,
@@ -385,7 +402,7 @@ static int s2v2_launch(int b, int n, int m, const float* xyz, const float* new_x
   const int grid = sms < cap ? sms : cap;             // one wave: contiguous chunks of the (device-side) tile count
   kern<<<grid, s2v2::THREADS, K::SMEM, st>>>(hdr, tile_cid, static_cast<const float4*>(workspace), w1x, b2, b3,
                                              static_cast<const char*>(w2_img), static_cast<const char*>(w3_img),
-                                             static_cast<const __half*>(q), out, g_sa_min_tpc);
+                                             static_cast<const __half*>(q), out, g_sa_min_tpc, g_sa_trace);
   return check_launch("sa_group_mlp_max (tcgen05, warp-specialised v2)");
 }
 

@@ -235,10 +235,14 @@ class Engine:
         # ---- neighbour searches (xyz + centroids only)
         e_bq = []
         src = s.xyz
+        # the raw cloud's search grid needs xyz only: it is built while the sa1 FPS runs
+        check(lib.vnb_query_ball_point_prepare(B, s.lv[0].n, float(cfg.sa[0].radius), dptr(src), dptr(s.lv[0].bq_ws), _sp(aux)))
         for li, l in enumerate(s.lv):
             aux.wait_event(e_lv[li])
-            check(lib.vnb_query_ball_point_ws(B, l.n, l.m, float(cfg.sa[li].radius), 64, dptr(src), dptr(l.xyz),
-                                              dptr(l.idx), dptr(l.cnt), dptr(l.bq_ws), _sp(aux)))
+            if li > 0:
+                check(lib.vnb_query_ball_point_prepare(B, l.n, float(cfg.sa[li].radius), dptr(src), dptr(l.bq_ws), _sp(aux)))
+            check(lib.vnb_query_ball_point_prepared(B, l.n, l.m, float(cfg.sa[li].radius), 64, dptr(src), dptr(l.xyz),
+                                                    dptr(l.idx), dptr(l.cnt), dptr(l.bq_ws), _sp(aux)))
             e = ev(); e.record(aux); e_bq.append(e)
             mark(f"bq{li + 1}", aux)
             src = l.xyz
