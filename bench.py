@@ -275,7 +275,7 @@ def kernel_table(eng, cfg, peaks, flush):
                                        [eng.store.layer(f"fp1/conv_{i}") for i in range(2)], f1.h[-1], stream=st))
         tensor("fp1_interpolate_mlp_fused", ms, fl_fp1)
         ms = t(lambda: fp_module_fused(f2.dist, f2.idx, s.lv[1].feat, f1.h[-1].view(B, f1.n, -1),
-                                       [eng.store.layer(f"fp2/conv_{i}") for i in range(2)], f2.h[-1],
+                                       [eng.store.layer(f"fp2/conv_{i}") for i in range(2)], None,   # as the engine calls it
                                        vote=(eng.vote_fused, eng.vote_x0, s.lv[1].xyz, s.votes_xyz, s.votes_feat), stream=st))
         tensor("fp2_interpolate_mlp_vote_fused", ms, fl_fp2 + fl_vote)
     else:

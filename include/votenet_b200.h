@@ -277,6 +277,9 @@ int vnb_fp_interpolate_concat(int b, int n, int m, int c1, int c2, const float* 
  *     (K = 256; its xyz rows 0..2 are passed as vote_w0_xyz_f32 (3,256) f32 and applied as an fp32 rank-3 update);
  *     vote_w_img[2] / vote_bias[2] = last FC with its 259 output columns permuted [3..258, 0..2];
  *     seeds_xyz (b*n,3) -> votes_xyz (b*n,3) = seeds_xyz + offset[:, :3], votes_feat (b*n,256) = fp_out + offset[:, 3:].
+ *     The residual never leaves the SM (it is parked in tensor memory), so with the voting module fused fp_out may be NULL
+ *     when the caller does not need the seed features.
+ * points1, points2, fp_out and votes_feat must be 32-byte aligned (256-bit global accesses).
  * The pointer arrays are HOST arrays of device pointers (read during the call).  Tensor-core path only (fp16
  * operands, fp32 accumulation); other widths return VNB_ERR_INVALID (use the unfused entry points). */
 int vnb_fp_module_fused(int b, int n, int m, int c1, int c2, const float* dist, const int* idx, const float* points1,

@@ -176,6 +176,12 @@ def test_fp_vote_fused(cuda, b, n, m):
     assert rel_err(fp_out.cpu().numpy(), seeds_feat.numpy()) < TOL_TC
     assert rel_err(vf.cpu().numpy(), votes[..., 3:]) < TOL_TC
     assert np.abs(vx.cpu().numpy() - votes[..., :3]).max() < TOL_TC * max(1.0, np.abs(votes[..., :3]).max())
+    # the vote residual lives in tensor memory: without a seed-feature buffer (the engine's call) the votes are the same bits
+    vx2 = torch.empty_like(vx); vf2 = torch.empty_like(vf)
+    U.fp_module_fused(dist, idx, tp1, tp2, [store.layer("fp2/conv_0"), store.layer("fp2/conv_1")], None,
+                      vote=(vl, x0, txyz1, vx2, vf2))
+    torch.cuda.synchronize()
+    assert torch.equal(vf2, vf) and torch.equal(vx2, vx)
     # fp-only form of the same kernel == what pointnet_fp_module dispatches to; and the unfused kernels agree to 1e-3
     a = U.pointnet_fp_module(txyz1, txyz2, tp1, tp2, [256, 256], "fp2", weights=store)
     U.FUSE_FP = False

@@ -57,6 +57,40 @@ struct TrapRegistration {
 }  // namespace
 #endif
 
+#ifdef __CUDACC__
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  A thread of the tensor-core epilogues / loaders owns a ROW, so a warp-wide access
+// touches 32 different lines whatever its width; with 32 bytes per lane every access fills whole 32-byte sectors — half the
+// LSU transactions of the 16-byte form for the same bytes (the fp32 row stores / residual loads of the epilogues were
+// LSU-bound: 11 500 cycles for a 128 KB tile).  Pointers must be 32-byte aligned.
+struct __align__(32) f32x8 { float v[8]; };
+__device__ __forceinline__ f32x8 ldg_f32x8(const float* p) {
+  f32x8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ f32x8 ld_f32x8(const float* p) {   // coherent form (data written earlier by this kernel)
+  f32x8 r;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_f32x8(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f),
+               "f"(g), "f"(h)
+               : "memory");
+}
+__device__ __forceinline__ void st_b32x8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                         uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+               "r"(g), "r"(h)
+               : "memory");
+}
+#endif
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

@@ -47,6 +47,8 @@ constexpr int OFF_BIAS = OFF_BAR + 512; // float [MAX_LAYERS][BIAS_LD] biases | 
 constexpr int SMEM = OFF_BIAS + (MAX_LAYERS * BIAS_LD + 3 * CW) * 4 + 1024;
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 constexpr int TM_COLS = 512;
+constexpr int TM_RES = 272;             // TMEM columns TM_RES..511: the vote residual (fp32 output of the fp module), parked
+constexpr int RES_TM_COLS = TM_COLS - TM_RES;   // 240 of its 256 columns fit behind the 272 accumulator columns
 
 struct Params {
   int rows_total, n, m;                  // rows_total = b * n unknown points, m known points per cloud
@@ -102,6 +104,30 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
   const bool tr = P.trace != nullptr && blockIdx.x == 0 && lane == 0;
 #define FP_STAMP(slot) if (tr) P.trace[slot] = clock64();
   if (warp == 0) { FP_STAMP(0) }
+  // Interpolation indices / weights of this thread's four rows (loader role: 8 threads per row, 4 rows per thread),
+  // requested before the prologue: the first chunk of layer 0 waits on a chain of two global round trips (idx -> points2),
+  // the first of them now overlaps the barrier / bias / TMEM set-up.
+  const int c8 = tid & 7, rsub = tid >> 3;
+  int gi[4][3];
+  float gw[4][3];
+  bool ok[4];
+  const float* p2base[4];
+  if (warp < 8) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int gr = row0 + rsub + 32 * p;
+      ok[p] = gr < P.rows_total;
+      const int r = ok[p] ? gr : 0;
+      const float d1 = fmaxf(__ldg(P.dist + (size_t)r * 3), 1e-10f), d2 = fmaxf(__ldg(P.dist + (size_t)r * 3 + 1), 1e-10f),
+                  d3 = fmaxf(__ldg(P.dist + (size_t)r * 3 + 2), 1e-10f);  // utils.py:279
+      const float r1 = __fdiv_rn(1.0f, d1), r2 = __fdiv_rn(1.0f, d2), r3 = __fdiv_rn(1.0f, d3);
+      const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);  // utils.py:280-282
+      gw[p][0] = __fdiv_rn(r1, norm); gw[p][1] = __fdiv_rn(r2, norm); gw[p][2] = __fdiv_rn(r3, norm);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gi[p][i] = __ldg(P.idx + (size_t)r * 3 + i);
+      p2base[p] = P.points2 + (size_t)(r / P.n) * P.m * CW;
+    }
+  }
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -186,67 +212,38 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
     // ================================================================ workers: layer-0 loader, then the epilogues
     // ---- layer 0: [interpolated (256) | points1 (256)] in 64-column chunks; 8 threads per row, 4 rows per thread
     {
-      const int c8 = tid & 7, rsub = tid >> 3;
-      int gi[4][3];
-      float gw[4][3];
-      bool ok[4];
-      const float* p2base[4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int gr = row0 + rsub + 32 * p;
-        ok[p] = gr < P.rows_total;
-        const int r = ok[p] ? gr : 0;
-        const float d1 = fmaxf(__ldg(P.dist + (size_t)r * 3), 1e-10f), d2 = fmaxf(__ldg(P.dist + (size_t)r * 3 + 1), 1e-10f),
-                    d3 = fmaxf(__ldg(P.dist + (size_t)r * 3 + 2), 1e-10f);  // utils.py:279
-        const float r1 = __fdiv_rn(1.0f, d1), r2 = __fdiv_rn(1.0f, d2), r3 = __fdiv_rn(1.0f, d3);
-        const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);  // utils.py:280-282
-        gw[p][0] = __fdiv_rn(r1, norm); gw[p][1] = __fdiv_rn(r2, norm); gw[p][2] = __fdiv_rn(r3, norm);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) gi[p][i] = __ldg(P.idx + (size_t)r * 3 + i);
-        p2base[p] = P.points2 + (size_t)(r / P.n) * P.m * CW;
-      }
       for (int c = 0; c < 8; ++c) {
         const int s = c & 1;
         uint4 pk[4];
         if (c < 4) {  // interpolated columns 64c + 8 c8 .. + 8   (tf_interpolate.cpp:107-127)
           const int col = 64 * c + 8 * c8;
-          float4 v[4][3][2];  // all 24 independent 16-byte loads of the chunk in flight before the first use
+          f32x8 v[4][3];  // all 12 independent 32-byte loads of the chunk in flight before the first use
 #pragma unroll
           for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              const float4* src = reinterpret_cast<const float4*>(p2base[p] + (size_t)gi[p][i] * CW + col);
-              v[p][i][0] = __ldg(src);
-              v[p][i][1] = __ldg(src + 1);
-            }
+            for (int i = 0; i < 3; ++i) v[p][i] = ldg_f32x8(p2base[p] + (size_t)gi[p][i] * CW + col);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             float o[8];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float4 a = v[p][0][e], b = v[p][1][e], d = v[p][2][e];
-              o[4 * e + 0] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, gw[p][0]), __fmul_rn(b.x, gw[p][1])), __fmul_rn(d.x, gw[p][2]));
-              o[4 * e + 1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, gw[p][0]), __fmul_rn(b.y, gw[p][1])), __fmul_rn(d.y, gw[p][2]));
-              o[4 * e + 2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, gw[p][0]), __fmul_rn(b.z, gw[p][1])), __fmul_rn(d.z, gw[p][2]));
-              o[4 * e + 3] = __fadd_rn(__fadd_rn(__fmul_rn(a.w, gw[p][0]), __fmul_rn(b.w, gw[p][1])), __fmul_rn(d.w, gw[p][2]));
-            }
+            for (int e = 0; e < 8; ++e)
+              o[e] = __fadd_rn(__fadd_rn(__fmul_rn(v[p][0].v[e], gw[p][0]), __fmul_rn(v[p][1].v[e], gw[p][1])),
+                               __fmul_rn(v[p][2].v[e], gw[p][2]));
             pk[p] = ok[p] ? make_uint4(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]))
                           : make_uint4(0, 0, 0, 0);
           }
         } else {  // skip features, columns 64 (c-4) + 8 c8 .. + 8 of points1
           const int col = 64 * (c - 4) + 8 * c8;
-          float4 v[4][2];
+          f32x8 v[4];
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const int gr = ok[p] ? row0 + rsub + 32 * p : 0;
-            const float4* src = reinterpret_cast<const float4*>(P.points1 + (size_t)gr * CW + col);
-            v[p][0] = __ldg(src);
-            v[p][1] = __ldg(src + 1);
+            v[p] = ldg_f32x8(P.points1 + (size_t)gr * CW + col);
           }
 #pragma unroll
           for (int p = 0; p < 4; ++p)
-            pk[p] = ok[p] ? make_uint4(pack_h2(v[p][0].x, v[p][0].y), pack_h2(v[p][0].z, v[p][0].w),
-                                       pack_h2(v[p][1].x, v[p][1].y), pack_h2(v[p][1].z, v[p][1].w))
+            pk[p] = ok[p] ? make_uint4(pack_h2(v[p].v[0], v[p].v[1]), pack_h2(v[p].v[2], v[p].v[3]),
+                                       pack_h2(v[p].v[4], v[p].v[5]), pack_h2(v[p].v[6], v[p].v[7]))
                           : make_uint4(0, 0, 0, 0);
         }
         if (warp == 0) { FP_STAMP(8 + 2 * c) }
@@ -266,6 +263,9 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
     const int grow = row0 + row;
     const bool live = grow < P.rows_total;
     const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16);
+    float res_tail[16];   // vote residual columns 240..255 (held by the hf == 1 threads from layer 1 to the last layer)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) res_tail[i] = 0.f;
     float sx = 0.f, sy = 0.f, sz = 0.f;
     if (L > 2 && live) {
       sx = __ldg(P.seeds_xyz + (size_t)grow * 3); sy = __ldg(P.seeds_xyz + (size_t)grow * 3 + 1);
@@ -287,11 +287,18 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
 #pragma unroll
       for (int cb = 0; cb < 4; ++cb) {  // 4 x 32 columns of this thread's half; the next TMEM load is in flight during the math
         const int col0 = hf * 128 + cb * 32;
-        float4 rsd[8];
-        if (vote_out && live) {  // residual = the fp output this very thread stored in layer 1's epilogue; all loads first
-          const float4* rs = reinterpret_cast<const float4*>(P.fp_out + (size_t)grow * CW + col0);
+        // residual of the vote output = the fp module's output, parked in TMEM (columns TM_RES..511) and in res_tail by
+        // this very thread in layer 1's epilogue: no trip through global memory
+        uint32_t rsd[32];
+        if (vote_out) {
+          if (col0 + 32 <= RES_TM_COLS) {
+            tmem_ld_x32(tacc + (uint32_t)(TM_RES + col0), rsd);
+          } else {
+            uint32_t r16[16];
+            tmem_ld_x16(tacc + (uint32_t)(TM_RES + col0), r16);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) rsd[i] = rs[i];
+            for (int i = 0; i < 16; ++i) { rsd[i] = r16[i]; rsd[16 + i] = __float_as_uint(res_tail[i]); }
+          }
         }
         tmem_ld_wait();
         if (cb + 1 < 4) tmem_ld_x32(tacc + (uint32_t)(col0 + 32), v[(cb + 1) & 1]);
@@ -320,16 +327,34 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
         }
         if (vote_out) {
           if (live) {
-            float4* o = reinterpret_cast<float4*>(P.votes_feat + (size_t)grow * CW + col0);
+            float* o = P.votes_feat + (size_t)grow * CW + col0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              o[i] = make_float4(x[4 * i] + rsd[i].x, x[4 * i + 1] + rsd[i].y, x[4 * i + 2] + rsd[i].z, x[4 * i + 3] + rsd[i].w);
+            for (int i = 0; i < 4; ++i)
+              st_f32x8(o + 8 * i, x[8 * i] + __uint_as_float(rsd[8 * i]), x[8 * i + 1] + __uint_as_float(rsd[8 * i + 1]),
+                       x[8 * i + 2] + __uint_as_float(rsd[8 * i + 2]), x[8 * i + 3] + __uint_as_float(rsd[8 * i + 3]),
+                       x[8 * i + 4] + __uint_as_float(rsd[8 * i + 4]), x[8 * i + 5] + __uint_as_float(rsd[8 * i + 5]),
+                       x[8 * i + 6] + __uint_as_float(rsd[8 * i + 6]), x[8 * i + 7] + __uint_as_float(rsd[8 * i + 7]));
           }
         } else {
-          if (fp_store && live) {
-            float4* o = reinterpret_cast<float4*>(P.fp_out + (size_t)grow * CW + col0);
+          if (fp_store && L > 2) {   // park the vote residual on chip (the last 16 columns do not fit: registers)
+            uint32_t xr[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            for (int i = 0; i < 32; ++i) xr[i] = __float_as_uint(x[i]);
+            if (col0 + 32 <= RES_TM_COLS) {
+              tmem_st_x32(tacc + (uint32_t)(TM_RES + col0), xr);
+            } else {
+              uint32_t r16[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { r16[i] = xr[i]; res_tail[i] = x[16 + i]; }
+              tmem_st_x16(tacc + (uint32_t)(TM_RES + col0), r16);
+            }
+          }
+          if (fp_store && live && P.fp_out != nullptr) {
+            float* o = P.fp_out + (size_t)grow * CW + col0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              st_f32x8(o + 8 * i, x[8 * i], x[8 * i + 1], x[8 * i + 2], x[8 * i + 3], x[8 * i + 4], x[8 * i + 5], x[8 * i + 6],
+                       x[8 * i + 7]);
           }
           if (!last) {
 #pragma unroll
@@ -352,6 +377,7 @@ __global__ void __launch_bounds__(THREADS, 1) fp_chain_kernel(const Params P) {
           P.votes_xyz[(size_t)grow * 3 + 2] = sz + (__uint_as_float(v16[2]) + bias[258]);
         }
       }
+      if (fp_store && L > 2) tmem_st_wait();
       if (!last) {
         fence_proxy_async_smem();   // the next layer's MMAs read `dst` through the async proxy
         tc_fence_before_sync();     // ... and overwrite the accumulator these loads have drained
@@ -395,8 +421,12 @@ extern "C" int vnb_fp_module_fused(int b, int n, int m, int c1, int c2, const fl
   VNB_REQUIRE(n_vote_layers == 0 || (n_vote_layers == 3 && vote_cout[0] == fpc::CW && vote_cout[1] == fpc::CW &&
                                      vote_cout[2] == fpc::CW + 3),
               "fp_module_fused: vote units must be [256, 256, 259]");
-  VNB_REQUIRE(dist && idx && points1 && points2 && fp_out, "fp_module_fused: null buffer");
+  VNB_REQUIRE(dist && idx && points1 && points2, "fp_module_fused: null buffer");
+  VNB_REQUIRE(fp_out != nullptr || n_vote_layers > 0, "fp_module_fused: fp_out may be NULL only with the voting module fused behind");
   if (n_vote_layers) VNB_REQUIRE(vote_w0_xyz_f32 && seeds_xyz && votes_xyz && votes_feat, "fp_module_fused: null vote buffer");
+  auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };   // 256-bit global accesses
+  VNB_REQUIRE(al32(points1) && al32(points2) && al32(fp_out) && al32(votes_feat),
+              "fp_module_fused: points1 / points2 / fp_out / votes_feat must be 32-byte aligned");
   if (b == 0) return VNB_OK;
   fpc::Params p = {};
   p.rows_total = b * n; p.n = n; p.m = m;

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(LT_THREADS, 3) linear_tc_kernel(int rows, int 
   const int c8 = tid & 7;     // 16-byte (8 x fp16) chunk of the 64-wide K chunk
   const int rsub = tid >> 3;  // rows rsub, rsub+32, rsub+64, rsub+96
   const bool vec_in = (cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  const bool vec8_in = (cin % 8 == 0) && ((reinterpret_cast<uintptr_t>(in) & 31) == 0);   // one 256-bit load per 8 floats
 
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1;
@@ -88,7 +89,11 @@ __global__ void __launch_bounds__(LT_THREADS, 3) linear_tc_kernel(int rows, int 
       for (int p = 0; p < 4; ++p) {  // all loads first (4 independent 32-byte reads per thread)
         const int gr = row0 + rsub + 32 * p;
         const float* src = in + (size_t)gr * cin + kb;
-        if (gr < rows && vec_in && kb + 8 <= cin) {
+        if (gr < rows && vec8_in && kb + 8 <= cin) {
+          const f32x8 a = ldg_f32x8(src);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[p][i] = a.v[i];
+        } else if (gr < rows && vec_in && kb + 8 <= cin) {
           const float4 a = __ldg(reinterpret_cast<const float4*>(src));
           const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
           v[p][0] = a.x; v[p][1] = a.y; v[p][2] = a.z; v[p][3] = a.w;
@@ -131,6 +136,8 @@ __global__ void __launch_bounds__(LT_THREADS, 3) linear_tc_kernel(int rows, int 
                       ((reinterpret_cast<uintptr_t>(res) & 15) == 0);
     const bool ok16 = (cout % 8 == 0) && ((reinterpret_cast<uintptr_t>(out_f16) & 15) == 0);
     const bool use_vec = ((out_f32 == nullptr && res == nullptr) || ok32) && (out_f16 == nullptr || ok16);
+    const bool wide32 = (cout % 8 == 0) && ((reinterpret_cast<uintptr_t>(out_f32) & 31) == 0);   // 256-bit stores
+    const bool wide16 = (cout % 16 == 0) && ((reinterpret_cast<uintptr_t>(out_f16) & 31) == 0);
     for (int blk = b0; blk < b1; ++blk) {
       const int cc = blk * 16;
       uint32_t v[16];
@@ -154,16 +161,26 @@ __global__ void __launch_bounds__(LT_THREADS, 3) linear_tc_kernel(int rows, int 
           }
         }
         if (out_f32 != nullptr) {
+          if (wide32) {   // whole 32-byte sectors per lane (a lane owns a row: every access touches 32 lines anyway)
+            st_f32x8(out_f32 + o, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            st_f32x8(out_f32 + o + 8, x[8], x[9], x[10], x[11], x[12], x[13], x[14], x[15]);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            reinterpret_cast<float4*>(out_f32 + o)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(out_f32 + o)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          }
         }
         if (out_f16 != nullptr) {
+          if (wide16) {
+            st_b32x8(out_f16 + o, lt_pack_h2(x[0], x[1]), lt_pack_h2(x[2], x[3]), lt_pack_h2(x[4], x[5]), lt_pack_h2(x[6], x[7]),
+                     lt_pack_h2(x[8], x[9]), lt_pack_h2(x[10], x[11]), lt_pack_h2(x[12], x[13]), lt_pack_h2(x[14], x[15]));
+          } else {
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
-            reinterpret_cast<uint4*>(out_f16 + o)[i] =
-                make_uint4(lt_pack_h2(x[8 * i], x[8 * i + 1]), lt_pack_h2(x[8 * i + 2], x[8 * i + 3]),
-                           lt_pack_h2(x[8 * i + 4], x[8 * i + 5]), lt_pack_h2(x[8 * i + 6], x[8 * i + 7]));
+            for (int i = 0; i < 2; ++i)
+              reinterpret_cast<uint4*>(out_f16 + o)[i] =
+                  make_uint4(lt_pack_h2(x[8 * i], x[8 * i + 1]), lt_pack_h2(x[8 * i + 2], x[8 * i + 3]),
+                             lt_pack_h2(x[8 * i + 4], x[8 * i + 5]), lt_pack_h2(x[8 * i + 6], x[8 * i + 7]));
+          }
         }
       } else {
 #pragma unroll

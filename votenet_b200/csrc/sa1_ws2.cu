@@ -69,6 +69,18 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// BULK (c <= 4): the helper kernel has written the finished fp16 operand rows (group_a0_kernel, sa_pack.cu); a tile's A0 is
+// staged by one bulk copy per slot into a ring of NB un-swizzled 2 KB buffers (K columns 0..7), K columns 8..15 — zeros and
+// the two constant ones that carry b1 — are ONE constant block every buffer's descriptor points at (its LBO).  No register
+// ever holds prefetched data: the register-gathering producer was pinned to one L2 round trip per tile (1235 cycles —
+// ptxas multiplexes the look-ahead loads of several tiles onto six scoreboards, so waiting for the oldest waits for all).
+constexpr int NB = 4;                       // A0 ring buffers (BULK)
+constexpr int A0B_BYTES = 128 * 16;         // one buffer: 128 rows x 8 halves
+constexpr int OFF_A0K1 = NB * A0B_BYTES;    // constant K-half block, relative to OFF_A0
+constexpr int OFF_CID = OFF_A0K1 + A0B_BYTES;            // this CTA's slice of the tile table, relative to OFF_A0
+constexpr int CIDCAP = (2 * A0_BYTES - OFF_CID) / 32;    // tiles cached (the rest is read from global memory)
+
+template <bool BULK>
 __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* __restrict__ hdr,
                                                              const int* __restrict__ tile_cid,
                                                              const float4* __restrict__ rel,
@@ -107,7 +119,10 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
   uint64_t* m2_done = bars + 15;   // [NH] commit: D2[t&1] ready, H1[t&3] free again
   uint64_t* h2_full = bars + 19;   // [NH] 128 E2 arrivals
   uint64_t* m3_done = bars + 23;   // [NH] commit: D3[t&1] ready, H2[t&3] free again
+  uint64_t* a0r_full = bars + 27;  // [NB] BULK: expect_tx arrive of the producer + the bytes of the tile's bulk copies
+  uint64_t* a0r_free = bars + 31;  // [NB] BULK: commit: M1 has read the ring buffer
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 36);
+  int* sCid = reinterpret_cast<int*>(sA0 + OFF_CID);  // BULK: tile table rows of this CTA's first CIDCAP tiles
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -132,6 +147,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
     for (int k = 0; k < NH; ++k) {
       mbar_init(&h1_full[k], 128); mbar_init(&m2_done[k], 1); mbar_init(&h2_full[k], 128); mbar_init(&m3_done[k], 1);
     }
+    for (int k = 0; k < NB; ++k) { mbar_init(&a0r_full[k], 1); mbar_init(&a0r_free[k], 1); }
     fence_barrier_init();
     mbar_arrive_expect_tx(bar_w, (uint32_t)(W1_BYTES + W2_BYTES + W3_BYTES));
     bulk_g2s(sW1, w1_img, W1_BYTES, bar_w);
@@ -143,6 +159,13 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
   // zero the two bias panels
   for (int i = tid; i < 2 * A0_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA0)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < (128 * 128 + C2 * 128) / 16; i += THREADS) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0, 0, 0, 0);
+  if (BULK) {
+    __syncthreads();  // the zero fill above covers the region the two tables below live in
+    // K columns 8..15 of every tile row: zeros, and k = 14, 15 = the constant 1 that multiplies b1 (hi, lo)
+    if (tid < 128) reinterpret_cast<uint4*>(sA0 + OFF_A0K1)[tid] = make_uint4(0u, 0u, 0u, pack2(1.f, 1.f));
+    const int ncache = min(my_tiles, CIDCAP) * 8;
+    for (int i = tid; i < ncache; i += THREADS) sCid[i] = __ldg(tile_cid + (size_t)first_tile * 8 + i);
+  }
   if (warp == 0) tmem_alloc(tmem_ptr, TM_COLS);
   // No thread may touch an mbarrier before thread 0 has initialised it: the previous CTA on this SM (possibly another
   // kernel) leaves arbitrary bytes there, and re-initialising a barrier other threads are parked on is undefined — seen
@@ -177,7 +200,30 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
   auto par_of = [](int t) { return (uint32_t)((t >> 1) & 1); };
   auto par4 = [](int t) { return (uint32_t)((t >> 2) & 1); };
 
-  if (warp >= 24 && warp < 28) {
+  if (BULK && warp >= 24 && warp < 28) {
+    // ================================================================ PRODUCER (BULK): one warp, one bulk copy per slot
+    // lane g < (slots of the tile) copies the rows of the centroid in slot g: (1 << shift) rows x 16 bytes, contiguous in
+    // the helper's table; lane 0 announces the tile's byte count on the ring buffer's barrier first.
+    if (warp == 24) {
+      const uint4* table = reinterpret_cast<const uint4*>(rel);
+      for (int t = 0; t < my_tiles; ++t) {
+        const int slot = t & (NB - 1);
+        const int shift = shift_of(first_tile + t);
+        const int nslot = 128 >> shift;
+        int cid = -1;
+        if (lane < nslot) cid = t < CIDCAP ? sCid[t * 8 + lane] : __ldg(tile_cid + (size_t)(first_tile + t) * 8 + lane);
+        const unsigned mask = __ballot_sync(0xffffffffu, cid >= 0);
+        if (t >= NB) mbar_wait(&a0r_free[slot], (uint32_t)(((t / NB) - 1) & 1));  // M1(t - NB) has read the buffer
+        S1_STAMP(0, t, 0)
+        const uint32_t bytes = 16u << shift;
+        if (lane == 0) mbar_arrive_expect_tx(&a0r_full[slot], (uint32_t)__popc(mask) * bytes);
+        __syncwarp();
+        if (cid >= 0)
+          bulk_g2s(sA0 + slot * A0B_BYTES + lane * bytes, table + (size_t)cid * 64, bytes, &a0r_full[slot]);
+        S1_STAMP(0, t, 1)
+      }
+    }
+  } else if (warp >= 24 && warp < 28) {
     // ================================================================ PRODUCER: one grouped row per thread
     const int pt = tid - 768;
     // tile row pt = sample (pt mod slot) of the centroid in slot (pt / slot); empty slots read row 0 (discarded later)
@@ -185,59 +231,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
     auto src_row = [&](int tile, int cid) {
       return cid < 0 ? (size_t)0 : (size_t)cid * 64 + (size_t)(pt & ((1 << shift_of(tile)) - 1));
     };
-    if (c <= 4) {
-      // Narrow features (VoteNet: c = 1 height or c = 3 xyz).  The producer's work per tile is ~150 cycles, but every
-      // value it needs is a chain of DEPENDENT global loads away (tile table -> table row -> feature row): centroid ids
-      // are requested FIVE tiles ahead, table rows FOUR and feature rows TWO, so each load has at least a tile period
-      // (usually two) to land; ~30 registers of look-ahead state.
-      // The look-ahead state lives in RINGS indexed by t & 3 with the loop unrolled four times, so every slot is a fixed
-      // register and a prefetched value is first touched by the instruction that needs it.  (Rotating named registers —
-      // r0 = r1; r1 = r2; ... — made each value wait for its load one iteration after it was issued: the kernel's tile
-      // period was pinned to one L2 round trip, 1235 cycles, with every other stage idle half of the time.)  A slot is
-      // refilled after its last use, i.e. behind the tile's arrive.
-      float4 R[4];        // table rows of tiles t .. t+3            (slot = tile & 3)
-      float F[4][4];      // features of tiles t, t+1 (, t+2)          (slot = tile & 3)
-      int C[2];           // centroid of this row in tiles t+4, t+5    (slot = tile & 1)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        R[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < my_tiles) R[k] = __ldg(rel + src_row(first_tile + k, cid_of(first_tile + k)));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) F[k][i] = 0.f;
-      }
-      C[0] = 4 < my_tiles ? cid_of(first_tile + 4) : -1;
-      C[1] = 5 < my_tiles ? cid_of(first_tile + 5) : -1;
-      auto load_feat = [&](const float4& r, float (&f)[4]) {
-        const float* fp = feat + (size_t)__float_as_int(r.w) * c;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) f[i] = i < c ? __ldg(fp + i) : 0.f;
-      };
-      if (my_tiles > 0) load_feat(R[0], F[0]);
-      if (my_tiles > 1) load_feat(R[1], F[1]);
-      for (int t0 = 0; t0 < my_tiles; t0 += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t0 + u;
-          if (t >= my_tiles) break;
-          const int s = u & 1;   // == t & 1
-          if (t >= 2) mbar_wait(&m1_done[s], par_of(t - 2));  // M1(t-2) finished reading A0[s]
-          if (warp == 24) { S1_STAMP(0, t, 0) }
-          uint8_t* a0 = sA0 + s * A0_BYTES;
-          *reinterpret_cast<uint4*>(a0 + sw128_offset((uint32_t)pt, 0)) =
-              make_uint4(pack2(R[u].x, R[u].y), pack2(R[u].z, F[u][0]), pack2(F[u][1], F[u][2]), pack2(F[u][3], 0.f));
-          *reinterpret_cast<uint4*>(a0 + sw128_offset((uint32_t)pt, 8)) =
-              make_uint4(0u, 0u, 0u, pack2(1.f, 1.f));  // k = 14, 15: the constant 1 that multiplies b1 (hi, lo)
-          fence_proxy_async_smem();
-          mbar_arrive(&a0_full[s]);
-          if (warp == 24) { S1_STAMP(0, t, 1) }
-          // look-ahead: features of tile t+2 (its table row was requested four tiles ago), table row of tile t+4 (its
-          // centroid id two tiles ago), centroid id of tile t+6
-          if (t + 2 < my_tiles) load_feat(R[(u + 2) & 3], F[(u + 2) & 3]);
-          if (t + 4 < my_tiles) R[u] = __ldg(rel + src_row(first_tile + t + 4, C[u & 1]));
-          if (t + 6 < my_tiles) C[u & 1] = cid_of(first_tile + t + 6);
-        }
-      }
-    } else {
+    {  // (c <= 4 takes the BULK instance)
     float4 r_cur = make_float4(0.f, 0.f, 0.f, 0.f), r_nxt = r_cur;   // table rows of tiles t, t+1
     if (my_tiles > 0) r_cur = __ldg(rel + src_row(first_tile, cid_of(first_tile)));
     if (my_tiles > 1) r_nxt = __ldg(rel + src_row(first_tile + 1, cid_of(first_tile + 1)));
@@ -285,13 +279,18 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
       const uint64_t bd = make_desc_sw128(smem_u32(sW1));
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t & 1;
-        MMA_WAIT(&a0_full[s], par_of(t));
+        const int slot = t & (NB - 1);
+        if (BULK) MMA_WAIT(&a0r_full[slot], (uint32_t)((t / NB) & 1)); else MMA_WAIT(&a0_full[s], par_of(t));
         if (t >= 2) MMA_WAIT(&d1_empty[s], par_of(t - 2));
         tc_fence_after_sync();
         S1_STAMP(1, t, 0)
         if (elect_one()) {
-          mma_f16_ss(tmem + TM_D1 + s * C1, make_desc_sw128(smem_u32(sA0 + s * A0_BYTES)), bd, id1, 0u);
+          // BULK: un-swizzled A (8-row groups 128 B apart; the K columns 8..15 are the shared constant block)
+          const uint64_t ad = BULK ? make_desc_nosw(smem_u32(sA0 + slot * A0B_BYTES), (uint32_t)(OFF_A0K1 - slot * A0B_BYTES), 128u)
+                                   : make_desc_sw128(smem_u32(sA0 + s * A0_BYTES));
+          mma_f16_ss(tmem + TM_D1 + s * C1, ad, bd, id1, 0u);
           mma_commit(&m1_done[s]);
+          if (BULK) mma_commit(&a0r_free[slot]);
         }
         __syncwarp();
         S1_STAMP(1, t, 1)
@@ -402,7 +401,10 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
       const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + TM_D3 + s * C3 + g * 64;
       // this half's four slot entries, requested BEFORE the wait for the accumulator so the (L2) latency hides behind it
       // (64-row slots: entry g; 32-row: entries 2g, 2g+1; 16-row: entries 4g..4g+3)
-      const int4 cc = __ldg(reinterpret_cast<const int4*>(tile_cid + (size_t)tile * 8) + (shift == 4 ? g : 0));
+      // (BULK: from the CTA's shared-memory copy of the table — when this stage paces the kernel the accumulator wait
+      // returns at once and a global load would be exposed every tile)
+      const int4 cc = (BULK && t < CIDCAP) ? reinterpret_cast<const int4*>(sCid + t * 8)[shift == 4 ? g : 0]
+                                           : __ldg(reinterpret_cast<const int4*>(tile_cid + (size_t)tile * 8) + (shift == 4 ? g : 0));
       mbar_wait(&m3_done[t & 3], par4(t));
       tc_fence_after_sync();
       if (q == 0) { S1_STAMP(6 + g, t, 0) }
@@ -462,20 +464,24 @@ extern int g_sa_sms, g_sa_split, g_sa_min_tpc;  // mlp_tc.cu
 size_t sa_rel_bytes(long long rows);                                                                  // sa_pack.cu
 int launch_sa_pack(int total_centroids, const int* pts_cnt, int* hdr, int* tile_cid, cudaStream_t st);  // sa_pack.cu
 void launch_group_rel(int n, int m, long long rows, const float* xyz, const float* new_xyz, const int* idx,
-                      const int* pts_cnt, void* rel, cudaStream_t st);  // sa_ws.cu
+                      const int* pts_cnt, void* rel, cudaStream_t st);  // sa_pack.cu
+void launch_group_a0(int n, int m, int c, long long rows, const float* xyz, const float* feat, const float* new_xyz,
+                     const int* idx, const int* pts_cnt, void* a0, cudaStream_t st);  // sa_pack.cu
 
 // returns -1 when no instance matches
 int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* feat, const float* new_xyz, const int* idx,
                      const int* pts_cnt, int c1, int c2, int c3, const float* b1, const float* b2, const float* b3, const void* w1_img,
                      const void* w2_img, const void* w3_img, float* out, void* workspace, cudaStream_t st) {
   if (workspace == nullptr || !(c1 == 64 && c2 == 64 && c3 == 128) || c > 11) return -1;  // k = 14, 15 carry the bias
-  auto kern = s1v2::sa1_ws2_kernel;
+  const bool bulk = c <= 4;   // the helper writes finished fp16 operand rows; the kernel stages tiles by bulk copies
+  auto kern = bulk ? s1v2::sa1_ws2_kernel<true> : s1v2::sa1_ws2_kernel<false>;
   VNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, s1v2::SMEM));
   int dev = 0, sms = 148;
   VNB_CUDA(cudaGetDevice(&dev));
   VNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long rows = (long long)b * m * 64;
-  launch_group_rel(n, m, rows, xyz, new_xyz, idx, pts_cnt, workspace, st);
+  if (bulk) launch_group_a0(n, m, c, rows, xyz, feat, new_xyz, idx, pts_cnt, workspace, st);
+  else launch_group_rel(n, m, rows, xyz, new_xyz, idx, pts_cnt, workspace, st);
   if (int rc = check_launch("sa_group_mlp_max: grouped relative coordinates")) return rc;
   int* hdr = reinterpret_cast<int*>(static_cast<char*>(workspace) + sa_rel_bytes(rows));
   int* tile_cid = hdr + 64;

@@ -120,6 +120,65 @@ void launch_group_rel(int n, int m, long long rows, const float* xyz, const floa
                                                                                      static_cast<float4*>(rel));
 }
 
+// Narrow-input variant (sa1: c <= 4 feature channels): the helper writes the FINISHED fp16 operand row of the first layer,
+// a0[(g*64+s)] = {x, y, z, f0, f1, f2, f3, 0} (relative coordinates, utils.py:51, and the gathered features, utils.py:53-55),
+// 16 bytes — the first eight K columns of a tile row.  A centroid's rows are contiguous, so the fused kernel stages a tile
+// with one bulk copy per slot (sa1_ws2.cu) instead of gathering through registers.
+__device__ __forceinline__ uint32_t a0_pack2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__global__ void __launch_bounds__(256) group_a0_kernel(int n, int m, int c, long long total_rows, const float* __restrict__ xyz,
+                                                       const float* __restrict__ feat, const float* __restrict__ new_xyz,
+                                                       const int* __restrict__ idx, const int* __restrict__ pts_cnt,
+                                                       uint4* __restrict__ a0) {
+  const long long t0 = (long long)blockIdx.x * (256 * GR_U) + threadIdx.x;
+  bool live[GR_U];
+  int pid[GR_U];
+#pragma unroll
+  for (int u = 0; u < GR_U; ++u) {
+    const long long t = t0 + 256 * u;
+    live[u] = t < total_rows;
+    if (live[u] && pts_cnt != nullptr) {
+      const int cn = __ldg(pts_cnt + (t >> 6));
+      const int slot = (cn <= 0 || cn > 32) ? 64 : (cn > 16 ? 32 : 16);
+      live[u] = (int)(t & 63) < slot;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < GR_U; ++u) pid[u] = live[u] ? __ldg(idx + t0 + 256 * u) : 0;
+  float px[GR_U], py[GR_U], pz[GR_U], cx[GR_U], cy[GR_U], cz[GR_U], f[GR_U][4];
+#pragma unroll
+  for (int u = 0; u < GR_U; ++u) {
+    px[u] = py[u] = pz[u] = cx[u] = cy[u] = cz[u] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[u][i] = 0.f;
+    if (!live[u]) continue;
+    const int g = (int)((t0 + 256 * u) >> 6);
+    const size_t src = (size_t)(g / m) * n + pid[u];
+    const float* pp = xyz + src * 3;
+    const float* cc = new_xyz + (size_t)g * 3;
+    const float* fp = feat + src * c;
+    px[u] = __ldg(pp); py[u] = __ldg(pp + 1); pz[u] = __ldg(pp + 2);
+    cx[u] = __ldg(cc); cy[u] = __ldg(cc + 1); cz[u] = __ldg(cc + 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < c) f[u][i] = __ldg(fp + i);
+  }
+#pragma unroll
+  for (int u = 0; u < GR_U; ++u) {
+    if (!live[u]) continue;
+    a0[t0 + 256 * u] = make_uint4(a0_pack2(px[u] - cx[u], py[u] - cy[u]), a0_pack2(pz[u] - cz[u], f[u][0]),
+                                  a0_pack2(f[u][1], f[u][2]), a0_pack2(f[u][3], 0.f));
+  }
+}
+
+void launch_group_a0(int n, int m, int c, long long rows, const float* xyz, const float* feat, const float* new_xyz,
+                     const int* idx, const int* pts_cnt, void* a0, cudaStream_t st) {
+  group_a0_kernel<<<(unsigned)((rows + 256 * GR_U - 1) / (256 * GR_U)), 256, 0, st>>>(n, m, c, rows, xyz, feat, new_xyz, idx,
+                                                                                    pts_cnt, static_cast<uint4*>(a0));
+}
+
 // workspace layout of the fused SA path: [rel: rows * 16 B][hdr: 256 B][tile_cid: (total/2 + 4) * 32 B]
 size_t sa_rel_bytes(long long rows) { return ((size_t)rows * 16 + 255) / 256 * 256; }
 size_t sa_tile_table_bytes(int total_centroids) { return 256 + ((size_t)total_centroids / 2 + 4) * 32; }

@@ -5,7 +5,8 @@
 //   * layer 3 is issued K-CHUNK-MAJOR (k-steps of chunk 0 for both channel halves, then chunk 1, ...) and H2 is handed
 //     over in four 32-column chunks, each with its own full/free mbarrier pair: the tensor pipe starts M3(t) when the
 //     first quarter of H2(t) exists and EPILOGUE2(t+1) refills a chunk as soon as M3(t) has consumed it, so E2 and M3
-//     overlap although H2 is single-buffered (shared memory is full);
+//     overlap although H2 is single-buffered (shared memory is full).  (Two 64-column chunks — NCHUNK = C2 / 64, the code
+//     is parametrised — make EPILOGUE2 17 % shorter but lengthen M3's tail behind it: tile period 3200 -> 3600 cycles.);
 //   * layers 2 and 3 have separate issuing warps: M2(t+1) never waits behind M3(t)'s operands or vice versa;
 //   * EPILOGUE3 uses two warps per TMEM lane quadrant (a warp pulls at most 64 B/cycle out of TMEM) and drains D3 in
 //     ~350 cycles, hidden behind M2 on the tensor pipe;
@@ -54,6 +55,7 @@ struct Cfg {
   static constexpr int TM_COLS = 512;
   static_assert(TM_D3 + C3 <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static constexpr int NSUB = C2 / 32;                       // EPILOGUE2 works in 32-column steps (one tcgen05.ld each)
   static constexpr int NCHUNK = C2 / 32;                     // H2 hand-over granularity: 32 columns = 2 k-steps
 };
 
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
   const bool tr = trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
 #define S2_STAMP(role, t, ph) \
   if (tr && (t) < 64) trace[((role) * 64 + (t)) * 2 + (ph)] = clock64();
-  constexpr int NCH = K::NCHUNK;
+  constexpr int NCH = K::NCHUNK, NSUB = K::NSUB, SPC = NSUB / NCH;   // hand-over chunks, 32-column steps, steps per chunk
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* sW2 = smem + K::OFF_W2;
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
   uint64_t* m3c_done = bars + 11;   // [NCH] tcgen05.commit: M3(t) has consumed chunk c (the last one == D3(t) complete)
   uint64_t* d3_empty = bars + 15;   //       256 epilogue-3 arrivals
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 32);
-  static_assert(NCH == 4, "barrier table laid out for 4 chunks");
+  static_assert(NCH <= 4 && NSUB % NCH == 0, "barrier table laid out for at most 4 chunks");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -247,8 +249,8 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
           tc_fence_after_sync();
           if (c == 0) { S2_STAMP(3, t, 0) }
 #pragma unroll
-          for (int k2 = 0; k2 < 2; ++k2) {
-            const uint32_t ks = (uint32_t)(2 * c + k2), pan = ks >> 2, kin = ks & 3;
+          for (int k2 = 0; k2 < 2 * SPC; ++k2) {
+            const uint32_t ks = (uint32_t)(2 * SPC * c + k2), pan = ks >> 2, kin = ks & 3;
 #pragma unroll
             for (int hh = 0; hh < C3 / 128; ++hh)
               mma_f16_ss(tmem + K::TM_D3 + hh * 128, make_desc_sw128(a0 + pan * (C3 * 128) + hh * (128 * 128) + kin * 32),
@@ -270,15 +272,15 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
       uint32_t v[2][32];
       tmem_ld_x32(tmem + lane_base + K::TM_D2 + s * C2, v[0]);
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        tmem_ld_wait();  // chunk c is in registers
-        if (c + 1 < NCH) {
+      for (int c = 0; c < NSUB; ++c) {
+        tmem_ld_wait();  // 32-column step c is in registers
+        if (c + 1 < NSUB) {
           tmem_ld_x32(tmem + lane_base + K::TM_D2 + s * C2 + (c + 1) * 32, v[(c + 1) & 1]);  // in flight during the math
         } else {
           tc_fence_before_sync();
           mbar_arrive(&d2_empty[s]);  // the whole accumulator has been read
         }
-        if (t >= 1) mbar_wait(&m3c_done[c], (uint32_t)((t - 1) & 1));  // M3(t-1) has consumed chunk c of H2
+        if (t >= 1 && c % SPC == 0) mbar_wait(&m3c_done[c / SPC], (uint32_t)((t - 1) & 1));  // M3(t-1) has consumed this chunk of H2
         const uint32_t* vc = v[c & 1];
         // bias of group ch+1 is loaded BEFORE group ch is stored (shared loads are kept behind earlier shared stores)
         float4 ba = *reinterpret_cast<const float4*>(sB2 + c * 32), bb = *reinterpret_cast<const float4*>(sB2 + c * 32 + 4);
@@ -299,8 +301,10 @@ __global__ void __launch_bounds__(THREADS, 1) sa_ws2_kernel(const int* __restric
           *reinterpret_cast<uint4*>(sH2 + (kk >> 6) * (128 * 128) + sw128_offset((uint32_t)tid, kk)) = pk;
           ba = na; bb = nb;
         }
-        fence_proxy_async_smem();
-        mbar_arrive(&h2c_full[c]);
+        if (c % SPC == SPC - 1) {
+          fence_proxy_async_smem();
+          mbar_arrive(&h2c_full[c / SPC]);
+        }
       }
       if (warp == 0) { S2_STAMP(2, t, 1) }
     }

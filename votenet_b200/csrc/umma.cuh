@@ -119,6 +119,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_byte_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Shared-memory matrix descriptor, K-major operand, NO swizzle (layout 0): 8-row x 16-byte core matrices, each 128
+// contiguous bytes; element (row, k) of a 16-bit operand sits at  (row & 7) * 16 + (row >> 3) * SBO + (k & 7) * 2 +
+// (k >> 3) * LBO  — SBO = byte distance between consecutive 8-row groups, LBO = byte distance between the two 8-column
+// halves of a K = 16 step (cute/atom/mma_traits_sm100.hpp: INTERLEAVE, ((8,m),(T,2)):((1T,SBO),(1,LBO))).  16-byte aligned.
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t smem_byte_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 // Instruction descriptor, kind::f16: A,B = fp16 (format 0), D = fp32 (c_format 1), both operands K-major.
 //   [4,6) c_format | [7,10) a_format | [10,13) b_format | 15 a_major | 16 b_major | [17,23) N>>3 | [24,29) M>>4
 __device__ __forceinline__ uint32_t make_idesc_f16_f32(uint32_t M, uint32_t N) {
@@ -163,6 +175,27 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------ registers -> TMEM (same lane / column mapping as the loads)
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,"
+      "%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Byte offset of element (row, k) inside ONE 64-column (128 B) K-major SW128 panel of 16-bit elements.
 __device__ __host__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t k) {

@@ -267,8 +267,9 @@ class Engine:
             fp_module_fused(f1.dist, f1.idx, s.lv[2].feat, pts2, [self.store.layer(f"fp1/conv_{i}") for i in range(2)],
                             f1.h[-1], stream=main)
             mark("fp", main)
+            # (the seed features are consumed inside the kernel only — the vote residual stays on chip — so they are not stored)
             fp_module_fused(f2.dist, f2.idx, s.lv[1].feat, f1.h[-1].view(B, f1.n, -1),
-                            [self.store.layer(f"fp2/conv_{i}") for i in range(2)], f2.h[-1],
+                            [self.store.layer(f"fp2/conv_{i}") for i in range(2)], None,
                             vote=(self.vote_fused, self.vote_x0, seeds_xyz, s.votes_xyz, s.votes_feat), stream=main)
         else:
             for fi, (f, skip, scope) in enumerate(zip(s.fp, (s.lv[2].feat, s.lv[1].feat), ("fp1", "fp2"))):
