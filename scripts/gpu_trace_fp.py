@@ -9,6 +9,9 @@ from votenet_b200.engine import Engine
 from votenet_b200.utils import fp_module_fused
 from votenet_b200.weights import make_synthetic_weights
 
+for kv in os.environ.get("VNB_TUNE", "").split(","):   # e.g. VNB_TUNE=sa_wait_ns=100,sa_variant=3
+    if kv:
+        check(lib.vnb_set_tuning(kv.split("=")[0].encode(), int(kv.split("=")[1])))
 dev = torch.device("cuda:0")
 cfg = VoteNetConfig()
 B = 8

@@ -9,6 +9,9 @@ from votenet_b200.tf_grouping import query_ball_point
 from votenet_b200.tf_sampling import farthest_point_sample, gather_point
 from votenet_b200.utils import WeightStore, sa_group_mlp_max
 from votenet_b200.weights import make_synthetic_weights
+for kv in os.environ.get("VNB_TUNE", "").split(","):   # e.g. VNB_TUNE=sa_wait_ns=100,sa_variant=3
+    if kv:
+        check(lib.vnb_set_tuning(kv.split("=")[0].encode(), int(kv.split("=")[1])))
 dev = torch.device("cuda:0")
 B, N = 8, 20000
 cfg = VoteNetConfig(); w = make_synthetic_weights(cfg, 0); store = WeightStore(w, device=dev, precision=1)

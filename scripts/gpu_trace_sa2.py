@@ -10,6 +10,9 @@ from votenet_b200.engine import Engine
 from votenet_b200.weights import make_synthetic_weights
 
 li = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+for kv in os.environ.get("VNB_TUNE", "").split(","):   # e.g. VNB_TUNE=sa_wait_ns=100,sa_variant=3
+    if kv:
+        check(lib.vnb_set_tuning(kv.split("=")[0].encode(), int(kv.split("=")[1])))
 dev = torch.device("cuda:0")
 cfg = VoteNetConfig()
 B = 8
