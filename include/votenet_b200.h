@@ -45,8 +45,10 @@ int vnb_set_tuning(const char* key, int value);
 /* Debugging aid: when given a device buffer of 16 x 10 int64, the next bucket-pruned FPS launches accumulate, per warp of
  * cloud 0, dependency-anchored cycle counts of the round's phases into it (scripts/gpu_fps_phases.py); NULL = off. */
 int vnb_debug_fps_profile(void* device_buffer_16x10_i64);
-/* Debugging aid: when given a device buffer of 8 x 64 x 2 int64, CTA 0 of the next fused-SA launches stamps clock64() at
- * the start / end of every pipeline stage (roles P, M1, M2, M3, E1, E2, E3a, E3b) of its first 64 tiles; NULL = off. */
+/* Debugging aid: when given a device buffer of 12 x 64 x 2 int64, CTA 0 of the next fused tensor-core launches stamps
+ * clock64() at the start / end of every pipeline stage of its first 64 tiles (sa1: roles P, M1, M2, M3, E1, E2, E3a, E3b;
+ * hoisted SA kernels: P, M2, E2, M3, E3; fused FP kernel: loader chunks and per-layer marks — scripts/gpu_trace_*.py
+ * decode them); NULL = off. */
 int vnb_debug_sa_trace(void* device_buffer_8x64x2_i64);
 /* debugging aid: host-mapped int[8]; a bounded device-side wait that gives up stores {source line, blockDim.x,
  * blockIdx.x, threadIdx.x, gridDim.x} there before it traps */

@@ -13,9 +13,9 @@ run() {  # name, timeout, tool args..., -- python args
   ( time timeout $to compute-sanitizer "$@" ) > $OUT/san_${TAG}_$name.txt 2>&1
   echo "== $name exit=$?"; summ $OUT/san_${TAG}_$name.txt
 }
-run memcheck_small 600 --tool memcheck python scripts/gpu_one_forward.py 2 2 small
-run memcheck_bench 900 --tool memcheck python scripts/gpu_one_forward.py 1 1 bench
-run racecheck_small 900 --tool racecheck --racecheck-report all python scripts/gpu_one_forward.py 2 2 small
-run initcheck_small 600 --tool initcheck python scripts/gpu_one_forward.py 1 1 small
-run synccheck_small 600 --tool synccheck --kernel-name-exclude "$TC" python scripts/gpu_one_forward.py 2 2 small
-run synccheck_tcgen05_only 300 --tool synccheck --kernel-name "$TC" python scripts/gpu_one_forward.py 1 1 small
+run memcheck_small 300 --tool memcheck python scripts/gpu_one_forward.py 2 2 small
+run memcheck_bench 400 --tool memcheck python scripts/gpu_one_forward.py 1 1 bench
+run racecheck_small 400 --tool racecheck --racecheck-report all python scripts/gpu_one_forward.py 2 2 small
+run initcheck_small 300 --tool initcheck python scripts/gpu_one_forward.py 1 1 small
+run synccheck_small 300 --tool synccheck --kernel-name-exclude "$TC" python scripts/gpu_one_forward.py 2 2 small
+run synccheck_tcgen05_only 200 --tool synccheck --kernel-name "$TC" python scripts/gpu_one_forward.py 1 1 small

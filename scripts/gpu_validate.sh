@@ -13,11 +13,12 @@ timeout 300 python scripts/gpu_stress.py 12 200 three_nn,prop_rest,bq34,sa1,sa2,
 timeout 200 python scripts/gpu_fps_phases.py room > gpurun_out/r2_fps_phases.txt 2>&1
 timeout 200 python scripts/gpu_fps_phases.py uniform | head -n 2 >> gpurun_out/r2_fps_phases.txt 2>&1
 timeout 200 python scripts/gpu_nms_probe.py > gpurun_out/r2_nms_probe.txt 2>&1
-bash scripts/gpu_sanitize.sh r2 > gpurun_out/r2_sanitizer_summary.txt 2>&1; tail -n 30 gpurun_out/r2_sanitizer_summary.txt
+# stage timelines of CTA 0 of the three fused tensor-core kernels (debug trace)
+( timeout 200 python scripts/gpu_trace_sa1.py; timeout 200 python scripts/gpu_trace_sa2.py 1; timeout 200 python scripts/gpu_trace_fp.py ) > gpurun_out/r2_stage_traces.txt 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/r2_ncu_launch_list_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --inflight 2 > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit=$?"
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:"fps_pruned_kernel|sa_ws2_kernel|sa1_ws2_kernel|fp_chain_kernel|grid_query_kernel|nms_cloud_kernel|linear_tc_kernel|merge_lists_kernel" -c 14 -f \
+    -k regex:"fps_pruned_kernel|sa_ws2_kernel|sa1_ws2_kernel|fp_chain_kernel|grid_query2_kernel|group_a0_kernel|group_rel_kernel|nms_cloud_kernel|linear_tc_kernel" -c 22 -f \
     -o gpurun_out/r2_full python scripts/gpu_one_forward.py 1 1 > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit=$?"
 python - <<'PY'
 import json

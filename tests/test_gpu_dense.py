@@ -78,7 +78,7 @@ def _sa_case(b, n, m, c, mlp, r, seed):
 
 @pytest.mark.parametrize("b,n,m,c,mlp,r", [(2, 3000, 256, 1, (64, 64, 128), 0.15), (1, 2000, 128, 3, (64, 64, 128), 0.2),
                                            (2, 1024, 128, 128, (128, 128, 256), 0.25), (1, 512, 64, 256, (128, 128, 256), 0.4),
-                                           (2, 1024, 64, 256, (128, 128, 128), 0.3)])
+                                           (2, 1024, 64, 256, (128, 128, 128), 0.3), (1, 1500, 96, 7, (64, 64, 128), 0.25)])
 @pytest.mark.parametrize("precision", [0, 1])
 def test_sa_group_mlp_max(cuda, b, n, m, c, mlp, r, precision):
     from votenet_b200.utils import WeightStore, sa_group_mlp_max

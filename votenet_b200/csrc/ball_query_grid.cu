@@ -138,81 +138,10 @@ __global__ void __launch_bounds__(BT) grid_build_kernel(int n, float cell_min, c
 }
 
 constexpr int GQ_WARPS = 8;
-__global__ void __launch_bounds__(GQ_WARPS * 32) grid_query_kernel(int n, int m, float d2_max, int nsample,
-                                                                    const float* __restrict__ xyz2,
-                                                                    const char* __restrict__ ws, size_t slice,
-                                                                    int* __restrict__ idx, int* __restrict__ pts_cnt) {
-  extern __shared__ uint32_t s_bm[];  // GQ_WARPS bitmaps of nw words
-  const int nw = (n + 31) / 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = blockIdx.x * GQ_WARPS + warp;
-  const int cloud = blockIdx.y;
-  if (j >= m) return;
-  uint32_t* bm = s_bm + (size_t)warp * nw;
-  const char* base = ws + (size_t)cloud * slice;
-  const GridHdr g = *reinterpret_cast<const GridHdr*>(base);
-  const int* cell_start = reinterpret_cast<const int*>(base + 32);
-  const float4* rec = reinterpret_cast<const float4*>(base + 32 + (size_t)CS_INTS * 4 + (size_t)GRID_MAX_CELLS * 4);
-  const float* q = xyz2 + ((size_t)cloud * m + j) * 3;
-  const float qx = q[0], qy = q[1], qz = q[2];
-  for (int w = lane; w < nw; w += 32) bm[w] = 0u;
-  __syncwarp();
-  // the query itself may lie outside the source points' bounding box: clamp like the builder does; a cell more than
-  // one step away from the unclamped coordinate cannot hold a hit, but visiting it is harmless (exact test below)
-  const int cx = cell_coord(qx, g.ox, g.inv, g.nx), cy = cell_coord(qy, g.oy, g.inv, g.ny), cz = cell_coord(qz, g.oz, g.inv, g.nz);
-  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-  for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z)
-    for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y) {
-      const int rowc = (z * g.ny + y) * g.nx;
-      const int s = cell_start[rowc + x0], e = cell_start[rowc + x1 + 1];  // cells x0..x1 are contiguous
-      for (int t = s + lane; t < e; t += 32) {
-        const float4 r = rec[t];
-        if (d2_ref_gpu(qx - r.x, qy - r.y, qz - r.z) <= d2_max) {
-          const int k = __float_as_int(r.w);
-          atomicOr(&bm[k >> 5], 1u << (k & 31));
-        }
-      }
-    }
-  __syncwarp();
-  // ---- emit the set bits in ascending order: lane owns a contiguous chunk of words
-  const int per = (nw + 31) / 32;
-  const int w0 = lane * per, w1 = min(nw, w0 + per);
-  int mine = 0;
-  for (int w = w0; w < w1; ++w) mine += __popc(bm[w]);
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  int pos = incl - mine;
-  int* row = idx + ((size_t)cloud * m + j) * nsample;
-  int first_local = -1;
-  for (int w = w0; w < w1 && pos < nsample; ++w) {
-    uint32_t bits = bm[w];
-    while (bits && pos < nsample) {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const int k = w * 32 + b;
-      if (first_local < 0) first_local = k;
-      row[pos++] = k;
-    }
-  }
-  // first hit overall = first hit of the lowest lane that has any
-  const unsigned havem = __ballot_sync(0xffffffffu, mine > 0);
-  if (total > 0) {
-    // a lane with hits but pos >= nsample from the start never set first_local; the lowest lane with hits starts at 0
-    const int first = __shfl_sync(0xffffffffu, first_local, __ffs(havem) - 1);
-    const int cnt = min(total, nsample);
-    for (int l = cnt + lane; l < nsample; l += 32) row[l] = first;
-  }
-  if (lane == 0) pts_cnt[(size_t)cloud * m + j] = min(total, nsample);
-}
 
-// Second-generation query (g_bq_variant 2, the default).  The first one cleared and re-read the whole n-bit bitmap for
-// every query (2 x 20 shared accesses per lane at n = 20000) and walked the nine x-runs through dependent loads; ncu showed
-// it issue-bound (77 % issue-active, ~1700 warp instructions per query).  Here
+// Query kernel.  (Its first generation cleared and re-read the whole n-bit bitmap for every query — 2 x 20 shared accesses
+// per lane at n = 20000 — and walked the nine x-runs through dependent loads; ncu showed it issue-bound: 77 % issue-active,
+// ~1700 warp instructions per query, 31 us for sa1.)  Here
 //   * the nine (start, end) pairs are loaded by lanes 0..8 at once and handed out by shuffles;
 //   * the bitmap is SPARSE-AWARE: lane l owns the `per` words [l * per, (l + 1) * per), per = ceil(words / 32); with
 //     per > GQ_DIRECT it also owns a summary word whose bit i says "word l * per + i is non-zero" (every hit sets it with
@@ -353,25 +282,16 @@ extern "C" int vnb_query_ball_point_prepared(int b, int n, int m, float radius, 
   cudaStream_t st = as_stream(stream);
   const size_t slice = grid_slice_bytes(n);
   const int nw = (n + 31) / 32;
-  if (g_bq_variant >= 2) {
-    const int per = (nw + 31) / 32;   // bitmap words per lane
-    const size_t smem = (size_t)GQ_WARPS * (32 + 32 * per) * 4;
-    VNB_REQUIRE(per <= 32 && smem <= 200 * 1024, "query_ball_point: n too large for the bitmap path");
-    const uint32_t inv = (uint32_t)((65536 + per - 1) / per);
-    auto kern = per > GQ_DIRECT ? grid_query2_kernel<true> : grid_query2_kernel<false>;
-    if (smem > 48 * 1024) VNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((m + GQ_WARPS - 1) / GQ_WARPS, b);   // one query per warp; the kernel's loop accepts any smaller grid
-    kern<<<grid, GQ_WARPS * 32, smem, st>>>(n, m, ball_d2_max(radius), nsample, per, inv, xyz2,
-                                            static_cast<const char*>(workspace), slice, idx, pts_cnt);
-    return check_launch("query_ball_point grid query");
-  }
-  const size_t smem = (size_t)GQ_WARPS * nw * 4;
-  VNB_REQUIRE(smem <= 200 * 1024, "query_ball_point: n too large for the bitmap path");
+  const int per = (nw + 31) / 32;   // bitmap words per lane
+  const size_t smem = (size_t)GQ_WARPS * (32 + 32 * per) * 4;
+  VNB_REQUIRE(per <= 32 && smem <= 200 * 1024, "query_ball_point: n too large for the bitmap path");
+  const uint32_t inv = (uint32_t)((65536 + per - 1) / per);
+  auto kern = per > GQ_DIRECT ? grid_query2_kernel<true> : grid_query2_kernel<false>;
   if (smem > 48 * 1024)  // (never lower the limit below the default: a profiler that patches the kernel needs the headroom)
-    VNB_CUDA(cudaFuncSetAttribute(grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((m + GQ_WARPS - 1) / GQ_WARPS, b);
-  grid_query_kernel<<<grid, GQ_WARPS * 32, smem, st>>>(n, m, ball_d2_max(radius), nsample, xyz2,
-                                                       static_cast<const char*>(workspace), slice, idx, pts_cnt);
+    VNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((m + GQ_WARPS - 1) / GQ_WARPS, b);   // one query per warp; the kernel's loop accepts any smaller grid
+  kern<<<grid, GQ_WARPS * 32, smem, st>>>(n, m, ball_d2_max(radius), nsample, per, inv, xyz2,
+                                          static_cast<const char*>(workspace), slice, idx, pts_cnt);
   return check_launch("query_ball_point grid query");
 }
 

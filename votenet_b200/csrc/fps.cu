@@ -39,7 +39,6 @@ extern int g_sa_variant;
 extern int g_sa_sms;
 extern int g_sa_split;
 extern int g_sa_min_tpc;
-extern int g_sa1_e3_split;
 int g_fps_mode = 1;   // 0: cluster barrier per round, 1: CTA champions in tagged slots + polling (default)
 int g_fps_cl = 0;     // 0: automatic cluster size, else forced (power of two <= 16)
 int g_fps_threads = 256;  // threads per CTA of the cluster kernel (256 / 512 / 1024)
@@ -371,7 +370,6 @@ extern "C" int vnb_set_tuning(const char* key, int value) {
   else if (k == "sa_sms") vnb::g_sa_sms = value;
   else if (k == "sa_split") vnb::g_sa_split = value < 1 ? 1 : value;
   else if (k == "sa_min_tpc") vnb::g_sa_min_tpc = value < 1 ? 1 : value;
-  else if (k == "sa1_e3_split") vnb::g_sa1_e3_split = value;
   else return set_err(VNB_ERR_INVALID, "set_tuning: unknown key %s", key);
   return VNB_OK;
 }

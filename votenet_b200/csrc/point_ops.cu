@@ -11,7 +11,7 @@ namespace vnb {
 
 static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;
-int g_bq_variant = 2;  // 0: brute-force scan, 1: cell grid + dense index bitmap, 2: cell grid + sparse-aware bitmap (1, 2 need the workspace entry point)
+int g_bq_variant = 1;  // 0: brute-force scan, 1: cell grid + sparse-aware index bitmap (needs the workspace entry point)
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 char* err_buf() { return g_err; }
 static std::vector<void (*)(int*)>& trap_setters() {

@@ -6,8 +6,8 @@
 //
 //   warps 0-3 / 4-7      EPILOGUE1 (even / odd tiles)  D1[s] -> ReLU, fp16 -> H1[t%4]        (thread = tile row = TMEM lane)
 //   warps 8-11 / 12-15   EPILOGUE2 (even / odd tiles)  D2[s] -> ReLU, fp16 -> H2[t%4]        (biases b1, b2 ride on the MMAs)
-//   warps 16-19 / 20-23  EPILOGUE3 (column half 0 / 1 of EVERY tile)  D3[s] (channel per lane) -> max over each centroid's
-//                        samples, +b3, ReLU -> out
+//   warps 16-19 / 20-23  EPILOGUE3 (even / odd tiles)  D3[s] (channel per lane) -> max over each centroid's 64 samples,
+//                        +b3, ReLU -> out
 //   warps 24-27          PRODUCER   one grouped row per thread: {rel_xyz, source row} from the helper kernel's table, c
 //                        feature floats; table rows prefetched two tiles ahead and features one tile ahead so no global
 //                        latency is exposed; fp16, swizzled 32-byte row of A0[s]
@@ -80,7 +80,7 @@ constexpr int OFF_A0K1 = NB * A0B_BYTES;    // constant K-half block, relative t
 constexpr int OFF_CID = OFF_A0K1 + A0B_BYTES;            // this CTA's slice of the tile table, relative to OFF_A0
 constexpr int CIDCAP = (2 * A0_BYTES - OFF_CID) / 32;    // tiles cached (the rest is read from global memory)
 
-template <bool BULK, bool E3SPLIT>
+template <bool BULK>
 __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* __restrict__ hdr,
                                                              const int* __restrict__ tile_cid,
                                                              const float4* __restrict__ rel,
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
   uint64_t* m1_done = bars + 3;    // [2]  commit
   uint64_t* d1_empty = bars + 5;   // [2]  128 E1 arrivals
   uint64_t* d2_empty = bars + 7;   // [2]  128 E2 arrivals
-  uint64_t* d3_empty = bars + 9;   // [2]  E3 arrivals: 256 (E3SPLIT: both column halves) or 128
+  uint64_t* d3_empty = bars + 9;   // [2]  128 E3 arrivals
   uint64_t* h1_full = bars + 11;   // [NH] 128 E1 arrivals                              (slot t&3, parity (t>>2)&1)
   uint64_t* m2_done = bars + 15;   // [NH] commit: D2[t&1] ready, H1[t&3] free again
   uint64_t* h2_full = bars + 19;   // [NH] 128 E2 arrivals
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
     mbar_init(bar_w, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a0_full[s], 128); mbar_init(&m1_done[s], 1); mbar_init(&d1_empty[s], 128); mbar_init(&d2_empty[s], 128);
-      mbar_init(&d3_empty[s], E3SPLIT ? 256 : 128);
+      mbar_init(&d3_empty[s], 128);
     }
     for (int k = 0; k < NH; ++k) {
       mbar_init(&h1_full[k], 128); mbar_init(&m2_done[k], 1); mbar_init(&h2_full[k], 128); mbar_init(&m3_done[k], 1);
@@ -388,134 +388,80 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
     }
   } else if (warp < 24) {
     // ================================================================ EPILOGUE 3: D3 -> max-pool -> out
-    if constexpr (E3SPLIT) {
-    // warp (16 + 4*g + q): EVERY tile, TMEM lane quadrant q (channels 32q..32q+31), column half g (samples 64g..64g+63):
-    // half the accumulator hold time of the form below, but every warp pays its per-tile fixed cost on every tile.
-      const int q = warp & 3, g = (warp >> 2) & 1;
-      const int ch = q * 32 + lane;
-      const float bias3 = sB3[ch];
-      for (int t = 0; t < my_tiles; ++t) {
-        const int s = t & 1;
-        const int tile = first_tile + t;
-        const int shift = shift_of(tile);
-        const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + TM_D3 + s * C3 + g * 64;
-        // this half's four slot entries, requested BEFORE the wait for the accumulator so the (L2) latency hides behind it
-        // (64-row slots: entry g; 32-row: entries 2g, 2g+1; 16-row: entries 4g..4g+3)
-        // (BULK: from the CTA's shared-memory copy of the table — when this stage paces the kernel the accumulator wait
-        // returns at once and a global load would be exposed every tile)
-        const int4 cc = (BULK && t < CIDCAP) ? reinterpret_cast<const int4*>(sCid + t * 8)[shift == 4 ? g : 0]
-                                             : __ldg(reinterpret_cast<const int4*>(tile_cid + (size_t)tile * 8) + (shift == 4 ? g : 0));
-        mbar_wait(&m3_done[t & 3], par4(t));
-        tc_fence_after_sync();
-        if (q == 0) { S1_STAMP(6 + g, t, 0) }
-        // four 16-column blocks; the load of block k+1 is in flight while block k is reduced
-        float mb[4];
-        {
-          uint32_t v[2][16];
-          tmem_ld_x16(tacc, v[0]);
-  #pragma unroll
-          for (int blk = 0; blk < 4; ++blk) {
-            tmem_ld_wait();
-            if (blk + 1 < 4) {
-              tmem_ld_x16(tacc + (blk + 1) * 16, v[(blk + 1) & 1]);
-            } else {
-              tc_fence_before_sync();
-              mbar_arrive(&d3_empty[s]);  // this warp's part of D3[s] has been read
-            }
-            const uint32_t* w = v[blk & 1];
-            float a0 = fmaxf(__uint_as_float(w[0]), __uint_as_float(w[4])), a1 = fmaxf(__uint_as_float(w[1]), __uint_as_float(w[5]));
-            float a2 = fmaxf(__uint_as_float(w[2]), __uint_as_float(w[6])), a3 = fmaxf(__uint_as_float(w[3]), __uint_as_float(w[7]));
-            a0 = fmaxf(fmaxf(a0, __uint_as_float(w[8])), __uint_as_float(w[12]));
-            a1 = fmaxf(fmaxf(a1, __uint_as_float(w[9])), __uint_as_float(w[13]));
-            a2 = fmaxf(fmaxf(a2, __uint_as_float(w[10])), __uint_as_float(w[14]));
-            a3 = fmaxf(fmaxf(a3, __uint_as_float(w[11])), __uint_as_float(w[15]));
-            mb[blk] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+    // warp (16 + 4*s + q): tiles of parity s, TMEM lane quadrant q (channels 32q..32q+31), both centroids of the tile.
+    // (Splitting every tile between the two groups by column half instead halves the accumulator hold time but makes
+    // every warp pay its fixed per-tile cost on every tile: tile period 1100 instead of 905 cycles, measured.)
+    const int q = warp & 3, s = (warp >> 2) & 1;
+    const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + TM_D3 + s * C3;
+    const int ch = q * 32 + lane;
+    const float bias3 = sB3[ch];
+    for (int t = s; t < my_tiles; t += 2) {
+      const int tile = first_tile + t;
+      const int shift = shift_of(tile);
+      // the tile's eight slot entries, requested BEFORE the wait for the accumulator so the (L2) latency hides behind it
+      // (BULK: from the CTA's shared-memory copy of the table — when this stage paces the kernel the wait returns at once)
+      int4 ca, cb;
+      if (BULK && t < CIDCAP) {
+        ca = reinterpret_cast<const int4*>(sCid + t * 8)[0];
+        cb = reinterpret_cast<const int4*>(sCid + t * 8)[1];
+      } else {
+        ca = __ldg(reinterpret_cast<const int4*>(tile_cid + (size_t)tile * 8));
+        cb = __ldg(reinterpret_cast<const int4*>(tile_cid + (size_t)tile * 8) + 1);
+      }
+      mbar_wait(&m3_done[t & 3], par4(t));
+      tc_fence_after_sync();
+      if (q == 0) { S1_STAMP(6 + s, t, 0) }
+      // eight 16-column blocks; the load of block k+1 is in flight while block k is reduced (two 16-register buffers —
+      // left to itself ptxas stopped hoisting the next load once the per-slot reduction was added, and eight exposed
+      // TMEM round trips made this stage pace the whole kernel)
+      float mbv[8];
+      {
+        uint32_t v[2][16];
+        tmem_ld_x16(tacc, v[0]);
+#pragma unroll
+        for (int blk = 0; blk < 8; ++blk) {
+          tmem_ld_wait();
+          if (blk + 1 < 8) {
+            tmem_ld_x16(tacc + (blk + 1) * 16, v[(blk + 1) & 1]);
+          } else {
+            tc_fence_before_sync();
+            mbar_arrive(&d3_empty[s]);  // D3[s] has been read
           }
+          const uint32_t* w = v[blk & 1];
+          float a0 = fmaxf(__uint_as_float(w[0]), __uint_as_float(w[4])), a1 = fmaxf(__uint_as_float(w[1]), __uint_as_float(w[5]));
+          float a2 = fmaxf(__uint_as_float(w[2]), __uint_as_float(w[6])), a3 = fmaxf(__uint_as_float(w[3]), __uint_as_float(w[7]));
+          a0 = fmaxf(fmaxf(a0, __uint_as_float(w[8])), __uint_as_float(w[12]));
+          a1 = fmaxf(fmaxf(a1, __uint_as_float(w[9])), __uint_as_float(w[13]));
+          a2 = fmaxf(fmaxf(a2, __uint_as_float(w[10])), __uint_as_float(w[14]));
+          a3 = fmaxf(fmaxf(a3, __uint_as_float(w[11])), __uint_as_float(w[15]));
+          mbv[blk] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
         }
+      }
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        // centroids whose samples sit in this half of the tile: one (64-row slots), two (32) or four (16)
+        int cid[4];
+        if (shift == 6) {
+          cid[0] = g == 0 ? ca.x : ca.y; cid[1] = cid[2] = cid[3] = -1;
+        } else if (shift == 5) {
+          cid[0] = g == 0 ? ca.x : ca.z; cid[1] = g == 0 ? ca.y : ca.w; cid[2] = cid[3] = -1;
+        } else {
+          cid[0] = g == 0 ? ca.x : cb.x; cid[1] = g == 0 ? ca.y : cb.y; cid[2] = g == 0 ? ca.z : cb.z; cid[3] = g == 0 ? ca.w : cb.w;
+        }
+        const float* mb = &mbv[4 * g];
         // bias + ReLU commute with the max
         if (shift == 6) {
-          const int cid = g == 0 ? cc.x : cc.y;
-          if (cid >= 0) out[(size_t)cid * C3 + ch] = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])) + bias3, 0.f);
+          if (cid[0] >= 0) out[(size_t)cid[0] * C3 + ch] = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])) + bias3, 0.f);
         } else if (shift == 5) {
-          const int c0 = g == 0 ? cc.x : cc.z, c1 = g == 0 ? cc.y : cc.w;
-          if (c0 >= 0) out[(size_t)c0 * C3 + ch] = fmaxf(fmaxf(mb[0], mb[1]) + bias3, 0.f);
-          if (c1 >= 0) out[(size_t)c1 * C3 + ch] = fmaxf(fmaxf(mb[2], mb[3]) + bias3, 0.f);
+          if (cid[0] >= 0) out[(size_t)cid[0] * C3 + ch] = fmaxf(fmaxf(mb[0], mb[1]) + bias3, 0.f);
+          if (cid[1] >= 0) out[(size_t)cid[1] * C3 + ch] = fmaxf(fmaxf(mb[2], mb[3]) + bias3, 0.f);
         } else {
-          const int cid[4] = {cc.x, cc.y, cc.z, cc.w};
-  #pragma unroll
+#pragma unroll
           for (int k = 0; k < 4; ++k)
             if (cid[k] >= 0) out[(size_t)cid[k] * C3 + ch] = fmaxf(mb[k] + bias3, 0.f);
         }
-        if (q == 0) { S1_STAMP(6 + g, t, 1) }
       }
-    } else {
-    // warp (16 + 4*s + q): tiles of parity s, TMEM lane quadrant q (channels 32q..32q+31), both centroids of the tile
-      const int q = warp & 3, s = (warp >> 2) & 1;
-      const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + TM_D3 + s * C3;
-      const int ch = q * 32 + lane;
-      const float bias3 = sB3[ch];
-      for (int t = s; t < my_tiles; t += 2) {
-        const int tile = first_tile + t;
-        const int shift = shift_of(tile);
-        // the tile's eight slot entries, requested BEFORE the wait for the accumulator so the (L2) latency hides behind it
-        const int4* crow = (BULK && t < CIDCAP) ? reinterpret_cast<const int4*>(sCid + t * 8)
-                                                : reinterpret_cast<const int4*>(tile_cid + (size_t)tile * 8);
-        const int4 ca = crow[0], cb = crow[1];
-        mbar_wait(&m3_done[t & 3], par4(t));
-        tc_fence_after_sync();
-        if (q == 0) { S1_STAMP(6 + s, t, 0) }
-        // eight 16-column blocks; the load of block k+1 is in flight while block k is reduced (two 16-register buffers —
-        // left to itself ptxas stopped hoisting the next load once the per-slot reduction was added, and eight exposed
-        // TMEM round trips made this stage pace the whole kernel)
-        float mbv[8];
-        {
-          uint32_t v[2][16];
-          tmem_ld_x16(tacc, v[0]);
-  #pragma unroll
-          for (int blk = 0; blk < 8; ++blk) {
-            tmem_ld_wait();
-            if (blk + 1 < 8) {
-              tmem_ld_x16(tacc + (blk + 1) * 16, v[(blk + 1) & 1]);
-            } else {
-              tc_fence_before_sync();
-              mbar_arrive(&d3_empty[s]);  // D3[s] has been read
-            }
-            const uint32_t* w = v[blk & 1];
-            float a0 = fmaxf(__uint_as_float(w[0]), __uint_as_float(w[4])), a1 = fmaxf(__uint_as_float(w[1]), __uint_as_float(w[5]));
-            float a2 = fmaxf(__uint_as_float(w[2]), __uint_as_float(w[6])), a3 = fmaxf(__uint_as_float(w[3]), __uint_as_float(w[7]));
-            a0 = fmaxf(fmaxf(a0, __uint_as_float(w[8])), __uint_as_float(w[12]));
-            a1 = fmaxf(fmaxf(a1, __uint_as_float(w[9])), __uint_as_float(w[13]));
-            a2 = fmaxf(fmaxf(a2, __uint_as_float(w[10])), __uint_as_float(w[14]));
-            a3 = fmaxf(fmaxf(a3, __uint_as_float(w[11])), __uint_as_float(w[15]));
-            mbv[blk] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-          }
-        }
-  #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          // centroids whose samples sit in this half of the tile: one (64-row slots), two (32) or four (16)
-          int cid[4];
-          if (shift == 6) {
-            cid[0] = g == 0 ? ca.x : ca.y; cid[1] = cid[2] = cid[3] = -1;
-          } else if (shift == 5) {
-            cid[0] = g == 0 ? ca.x : ca.z; cid[1] = g == 0 ? ca.y : ca.w; cid[2] = cid[3] = -1;
-          } else {
-            cid[0] = g == 0 ? ca.x : cb.x; cid[1] = g == 0 ? ca.y : cb.y; cid[2] = g == 0 ? ca.z : cb.z; cid[3] = g == 0 ? ca.w : cb.w;
-          }
-          const float* mb = &mbv[4 * g];
-          // bias + ReLU commute with the max
-          if (shift == 6) {
-            if (cid[0] >= 0) out[(size_t)cid[0] * C3 + ch] = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])) + bias3, 0.f);
-          } else if (shift == 5) {
-            if (cid[0] >= 0) out[(size_t)cid[0] * C3 + ch] = fmaxf(fmaxf(mb[0], mb[1]) + bias3, 0.f);
-            if (cid[1] >= 0) out[(size_t)cid[1] * C3 + ch] = fmaxf(fmaxf(mb[2], mb[3]) + bias3, 0.f);
-          } else {
-  #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (cid[k] >= 0) out[(size_t)cid[k] * C3 + ch] = fmaxf(mb[k] + bias3, 0.f);
-          }
-        }
-        if (q == 0) { S1_STAMP(6 + s, t, 1) }
-      }
+      if (q == 0) { S1_STAMP(6 + s, t, 1) }
     }
   }
 #undef S1_STAMP
@@ -527,7 +473,6 @@ __global__ void __launch_bounds__(THREADS, 1) sa1_ws2_kernel(int c, const int* _
 }  // namespace s1v2
 
 extern int g_sa_variant;  // mlp_tc.cu
-int g_sa1_e3_split = 0;
 long long* g_sa_trace = nullptr;  // debugging: device buffer of 12 x 64 x 2 int64 (vnb_debug_sa_trace)
 
 extern int g_sa_sms, g_sa_split, g_sa_min_tpc;  // mlp_tc.cu
@@ -544,9 +489,7 @@ int sa1_ws2_dispatch(int b, int n, int c, int m, const float* xyz, const float* 
                      const void* w2_img, const void* w3_img, float* out, void* workspace, cudaStream_t st) {
   if (workspace == nullptr || !(c1 == 64 && c2 == 64 && c3 == 128) || c > 11) return -1;  // k = 14, 15 carry the bias
   const bool bulk = c <= 4;   // the helper writes finished fp16 operand rows; the kernel stages tiles by bulk copies
-  const bool split = g_sa1_e3_split != 0;   // tuning "sa1_e3_split": max-pool warps split every tile by column half
-  auto kern = bulk ? (split ? s1v2::sa1_ws2_kernel<true, true> : s1v2::sa1_ws2_kernel<true, false>)
-                   : (split ? s1v2::sa1_ws2_kernel<false, true> : s1v2::sa1_ws2_kernel<false, false>);
+  auto kern = bulk ? s1v2::sa1_ws2_kernel<true> : s1v2::sa1_ws2_kernel<false>;
   VNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, s1v2::SMEM));
   int dev = 0, sms = 148;
   VNB_CUDA(cudaGetDevice(&dev));
