@@ -1,5 +1,5 @@
 """One or a few eager forwards (for compute-sanitizer / ncu runs):  gpu_one_forward.py [steps] [inflight] [bench|small]
-`bench` = the BASELINE shape (8 clouds x 20 000 points); `small` = 2 clouds x 4096 points through the same kernels
+`bench` = the BASELINE shape (8 clouds x 20 000 points); `small` = 2 clouds x 6144 points through the same kernels
 (every kernel of the forward runs, the sanitizers' 10-100x slow-down stays within minutes)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,7 +14,8 @@ inflight = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 shape = sys.argv[3] if len(sys.argv) > 3 else "bench"
 dev = torch.device("cuda:0")
 if shape == "small":
-    cfg = VoteNetConfig(num_points=4096,
+    cfg = VoteNetConfig(num_points=6144,   # > 4096: the ball query's summary-bitmap mode, like the bench shape
+                        
                         sa=(SAParams(512, 0.3, 64, (64, 64, 128)), SAParams(256, 0.5, 64, (128, 128, 256)),
                             SAParams(128, 0.9, 64, (128, 128, 256)), SAParams(64, 1.4, 64, (128, 128, 256))),
                         proposal=SAParams(64, 0.4, 64, (128, 128, 128), (128, 128, 79)))

@@ -4,7 +4,7 @@
 # sanitizers, and the ncu evidence that profiles/ keeps (launch list of the bench command + one --set full capture).
 mkdir -p gpurun_out
 rm -f gpurun_out/stage_errors.json
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 4
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -n 8
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -v Warning | tail -n 2
 python bench.py > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err; echo "bench exit=$?"
 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_1gpu_driverlike.json 2> gpurun_out/r2_bench_1gpu_driverlike.err; echo "bench (driver-like) exit=$?"

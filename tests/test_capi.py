@@ -36,10 +36,27 @@ def test_argument_validation_needs_no_gpu():
     assert lib.vnb_farthest_point_sample(1, 1 << 20, 4, null, null, null) == 1
     assert lib.vnb_query_ball_point(1, 8, 4, -1.0, 4, null, null, null, null, null) == 1
     assert lib.vnb_query_ball_point(1, 8, 4, 0.5, 0, null, null, null, null, null) == 1
+    # the two halves of the workspace ball query validate like the whole; without a workspace they are the scan / a no-op
+    assert lib.vnb_query_ball_point_prepare(1, 8, -1.0, null, null, null) == 1
+    assert b"radius" in lib.vnb_last_error()
+    assert lib.vnb_query_ball_point_prepare(1, 8, 0.5, null, null, null) == 0
+    assert lib.vnb_query_ball_point_prepared(1, 8, 4, 0.5, 0, null, null, null, null, null, null) == 1
+    assert b"nsample" in lib.vnb_last_error()
+    assert lib.vnb_query_ball_point_ws(1, 8, 4, -2.0, 4, null, null, null, null, null, null) == 1
     assert lib.vnb_nms3d(1, 4, null, null, null, 1.5, null, null, null, null, null) == 1
     assert b"iou_threshold" in lib.vnb_last_error()
     assert lib.vnb_sa_group_mlp_max(*([1, 8, 1, 2, 32] + [null] * 4 + [64, 64, 128] + [null] * 11 + [1, null, null])) == 1
     assert lib.vnb_linear(4, 8, 8, null, null, null, null, null, 7, null, null, 1, null) == 1
+    # fused FP kernel: 256-bit global accesses need 32-byte aligned feature buffers (checked before anything is launched)
+    cout = (C.c_int * 2)(256, 256)
+    ptrs = (C.c_void_p * 2)(0x1000, 0x2000)
+    fake = lambda a: C.c_void_p(a)  # noqa: E731  (never dereferenced: validation fails first)
+    rc = lib.vnb_fp_module_fused(1, 128, 64, 256, 256, fake(0x1000), fake(0x1000), fake(0x1010), fake(0x1000), 2, ptrs, ptrs, cout,
+                                 fake(0x1000), 0, None, None, None, None, None, None, None, None)
+    assert rc == 1 and b"32-byte aligned" in lib.vnb_last_error()
+    rc = lib.vnb_fp_module_fused(1, 128, 64, 256, 256, fake(0x1000), fake(0x1000), fake(0x1000), fake(0x1000), 2, ptrs, ptrs, cout,
+                                 None, 0, None, None, None, None, None, None, None, None)
+    assert rc == 1 and b"fp_out may be NULL only" in lib.vnb_last_error()
     # sizes
     assert lib.vnb_weight_image_bytes(128, 128) == 2 * 128 * 128
     assert lib.vnb_weight_image_bytes(6, 64) == 64 * 128
