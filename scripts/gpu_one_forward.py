@@ -15,7 +15,6 @@ shape = sys.argv[3] if len(sys.argv) > 3 else "bench"
 dev = torch.device("cuda:0")
 if shape == "small":
     cfg = VoteNetConfig(num_points=6144,   # > 4096: the ball query's summary-bitmap mode, like the bench shape
-                        
                         sa=(SAParams(512, 0.3, 64, (64, 64, 128)), SAParams(256, 0.5, 64, (128, 128, 256)),
                             SAParams(128, 0.9, 64, (128, 128, 256)), SAParams(64, 1.4, 64, (128, 128, 256))),
                         proposal=SAParams(64, 0.4, 64, (128, 128, 128), (128, 128, 79)))

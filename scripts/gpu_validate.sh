@@ -30,3 +30,4 @@ d = json.loads(open('gpurun_out/r2_bench_1gpu.json').read().strip().splitlines()
 for k in d['kernels']:
     print('   %-36s %8.4f ms  frac %.3f' % (k['kernel'], k['ms'], k['frac']))
 PY
+bash scripts/gpu_sanitize.sh r2 > gpurun_out/r2_sanitizer_summary.txt 2>&1; tail -n 30 gpurun_out/r2_sanitizer_summary.txt
