@@ -113,7 +113,7 @@ int vnb_query_ball_point(int b, int n, int m, float radius, int nsample, const f
 
 /* Same outputs, bit for bit, computed through a uniform grid + per-query index bitmap instead of the exhaustive scan
  * (see csrc/ball_query_grid.cu).  workspace: vnb_query_ball_point_workspace_bytes(b,n) bytes; with workspace == NULL
- * (or n < 1024, tuning knob bq_grid_min_n) this is vnb_query_ball_point. */
+ * (or n < 1024, tuning knob bq_grid_min_n, or n > 32768) this is vnb_query_ball_point. */
 size_t vnb_query_ball_point_workspace_bytes(int b, int n);
 int vnb_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
                             int* idx, int* pts_cnt, void* workspace, void* stream);

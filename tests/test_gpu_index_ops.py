@@ -271,10 +271,11 @@ def test_fps_exchange_variants(cuda, mode, thr, cl):
                                            (5000, 100, 3.0, 64, "uniform"), (6000, 200, 0.3, 32, "outside"), (4096, 64, 1e-4, 8, "uniform"),
                                            (7000, 256, 0.25, 64, "flat"), (2048, 1024, 0.4, 64, "room"), (1024, 512, 0.8, 64, "room"),
                                            (1024, 256, 0.3, 64, "uniform"), (1500, 100, 0.05, 64, "outside"), (5000, 700, 0.3, 64, "room"),
-                                           (20480, 64, 0.6, 64, "room")])
+                                           (20480, 64, 0.6, 64, "room"), (40000, 50, 0.3, 32, "uniform")])
 def test_ball_query_grid_matches_scan(cuda, n, m, r, ns, kind):
-    """The grid + bitmap kernel (n >= 1024) is bit-identical to the exhaustive scan and to the oracle, including queries
-    outside the source bounding box, degenerate (planar) clouds, huge and tiny radii."""
+    """The grid + bitmap kernel (1024 <= n <= 32768; both bitmap modes) is bit-identical to the exhaustive scan and to the
+    oracle, including queries outside the source bounding box, degenerate (planar) clouds, huge and tiny radii; larger
+    clouds take the scan through the same entry point."""
     from votenet_b200 import synth
     from votenet_b200._lib import check, lib
     from votenet_b200.tf_grouping import query_ball_point

@@ -256,8 +256,9 @@ extern "C" size_t vnb_query_ball_point_workspace_bytes(int b, int n) {
   return (size_t)b * grid_slice_bytes(n);
 }
 
+constexpr int GQ_MAX_N = 32 * 32 * 32;   // a lane owns at most 32 bitmap words (its summary word has 32 bits)
 static bool bq_grid_path(int n, float radius, const void* workspace) {
-  return workspace != nullptr && g_bq_variant != 0 && n >= g_bq_grid_min_n && radius > 1e-20f;
+  return workspace != nullptr && g_bq_variant != 0 && n >= g_bq_grid_min_n && n <= GQ_MAX_N && radius > 1e-20f;
 }
 
 // Build half of vnb_query_ball_point_ws: needs the searched set only, so a caller can run it before the queries exist
