@@ -256,6 +256,12 @@ def kernel_table(eng, cfg, peaks, flush):
         ms = t(lambda: check(lib.vnb_query_ball_point_ws(B, l.n, l.m, float(sa.radius), 64, dptr(src), dptr(l.xyz), dptr(l.idx),
                                                          dptr(l.cnt), dptr(l.bq_ws), sp())))
         hbm(f"ball_query_sa{li + 1}", ms, B * (l.n * 12 + l.m * 12 + l.m * 256 + l.m * 4), "latency-bound (compulsory bytes only)")
+        if l.bq_ws is not None and l.n >= 1024:   # grid path: the two halves of the call (the engine builds sa1's grid beside the FPS)
+            ms_b = t(lambda: check(lib.vnb_query_ball_point_prepare(B, l.n, float(sa.radius), dptr(src), dptr(l.bq_ws), sp())))
+            ms_q = t(lambda: check(lib.vnb_query_ball_point_prepared(B, l.n, l.m, float(sa.radius), 64, dptr(src), dptr(l.xyz),
+                                                                     dptr(l.idx), dptr(l.cnt), dptr(l.bq_ws), sp())))
+            rows[-1].update(ms_grid_build=ms_b, ms_query=ms_q)
+            rows[-1]["note"] += "; ms = grid build (one CTA per cloud; needs the searched set only) + query"
         ms = t(lambda: eng._sa(li, src, feat, l.n, c, l.xyz, l.idx, l.m, l.q, l.feat, st, s.sa_ws, l.cnt))
         tensor(f"sa{li + 1}_group_mlp_max", ms, mlp_flops(B * l.m * 64, 3 + c, sa.mlp),
                sa_executed(l.cnt, l.n, c, sa.mlp, eng.sa_layers[li][3] is not None))
